@@ -1,0 +1,4 @@
+/* Forwarding header: the reference's include path <lambda_snark/types.h>
+ * (cpp-core/include/lambda_snark/types.h) resolves to the B200 C ABI. */
+#pragma once
+#include "../lambda_snark_b200.h"

@@ -1,0 +1,276 @@
+/*
+ * lambda_snark_b200.h -- C ABI of the B200-native prover hot path.
+ *
+ * Part 1 is the drop-in surface: every symbol rust-api/lambda-snark-sys binds
+ * today (bindgen allowlist `lwe_.*`, `ntt_.*`, `lambda_snark_r1cs_.*`,
+ * rust-api/lambda-snark-sys/build.rs:197-199) plus `sample_gaussian`, with the
+ * reference's exact signatures, struct layouts, ownership and error rules.
+ * Each declaration cites the reference interface it replaces (paths relative
+ * to the reference repo).  Part 2 holds the batched / device-pointer
+ * extensions a GPU back-end needs to amortise launch and PCIe cost.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  `void* stream`
+ * is a cudaStream_t passed opaquely (NULL = the context's own stream).
+ *
+ * The legacy include paths <lambda_snark/{types,ntt,commitment,utils,r1cs}.h>
+ * are thin forwarding headers onto this file, so reference-side C++ (e.g.
+ * cpp-core/tests/test_ntt.cpp) compiles unchanged.
+ */
+#ifndef LAMBDA_SNARK_B200_H
+#define LAMBDA_SNARK_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define LSR_NOEXCEPT noexcept
+extern "C" {
+#else
+#define LSR_NOEXCEPT
+#endif
+
+/* ===================================================================== */
+/* Part 1a -- FFI types (cpp-core/include/lambda_snark/types.h:27-78)     */
+/* ===================================================================== */
+
+typedef struct LweContext LweContext;            /* types.h:27, opaque */
+typedef struct NttContext NttContext;            /* ntt.h:24,   opaque */
+
+/* types.h:36-39.  data[0] = payload byte length, data[1..] = payload.
+ * Here the payload is t = A*s + e + enc(m), k*n little-endian u64 words,
+ * row-major, natural coefficient order, every word in [0, q).  `data` is
+ * host memory owned by the library until lwe_commitment_free.            */
+typedef struct {
+    uint64_t* data;
+    size_t    len;
+} LweCommitment;
+
+/* types.h:44-47 */
+typedef struct {
+    uint64_t* randomness;
+    size_t    rand_len;
+} LweOpening;
+
+/* types.h:52-55 */
+typedef enum {
+    PROFILE_SCALAR_A = 0,
+    PROFILE_RING_B   = 1
+} ProfileType;
+
+/* types.h:60-67 (32 bytes).  Unlike the reference, which stores but ignores
+ * modulus / module_rank / sigma (commitment.cpp:108-111), all four numeric
+ * fields are honoured; see lwe_context_create.                            */
+typedef struct {
+    ProfileType profile;
+    uint32_t    security_level;
+    uint64_t    modulus;
+    uint32_t    ring_degree;
+    uint32_t    module_rank;
+    double      sigma;
+} PublicParams;
+
+/* types.h:72-78 */
+typedef enum {
+    LAMBDA_SNARK_OK                 = 0,
+    LAMBDA_SNARK_ERR_NULL_PTR       = 1,
+    LAMBDA_SNARK_ERR_INVALID_PARAMS = 2,
+    LAMBDA_SNARK_ERR_ALLOC_FAILED   = 3,
+    LAMBDA_SNARK_ERR_CRYPTO_FAILED  = 4
+} LambdaSnarkError;
+
+/* ===================================================================== */
+/* Part 1b -- NTT (cpp-core/include/lambda_snark/ntt.h, src/ntt.cpp)      */
+/* ===================================================================== */
+
+/* ntt.h:34 / ntt.cpp:30-70.  NULL when n == 0, n not a power of two, n
+ * outside [2, 2^17], q outside [2, 2^61), or no primitive 2n-th root of
+ * unity exists mod q (SEAL NTTTables throws -> NULL).  Tables use SEAL's
+ * minimal primitive root.  Also NULL if no CUDA device is usable.         */
+NttContext* ntt_context_create(uint64_t q, uint32_t n) LSR_NOEXCEPT;
+
+/* ntt.h:41 / ntt.cpp:72-74.  NULL-safe. */
+void ntt_context_free(NttContext* ctx) LSR_NOEXCEPT;
+
+/* ntt.h:55-59 / ntt.cpp:76-89.  In-place negacyclic forward NTT, natural
+ * order in, bit-reversed order out, output in [0,q).  0 on success, -1 on
+ * NULL ctx / NULL coeffs / n != degree (or a CUDA failure).                */
+int ntt_forward(const NttContext* ctx, uint64_t* coeffs, uint32_t n) LSR_NOEXCEPT;
+
+/* ntt.h:69-73 / ntt.cpp:91-104.  Exact inverse of ntt_forward (n^-1 folded in). */
+int ntt_inverse(const NttContext* ctx, uint64_t* evals, uint32_t n) LSR_NOEXCEPT;
+
+/* ntt.h:86-92 / ntt.cpp:106-119.  result[i] = a[i]*b[i] mod q, exact for any
+ * u64 inputs; result may alias a or b; NO check of n against the context;
+ * returns silently on any NULL argument.                                   */
+void ntt_mul_pointwise(const NttContext* ctx, uint64_t* result, const uint64_t* a,
+                       const uint64_t* b, uint32_t n) LSR_NOEXCEPT;
+
+/* ===================================================================== */
+/* Part 1c -- commitment (include/lambda_snark/commitment.h, src/commitment.cpp) */
+/* ===================================================================== */
+
+/* commitment.h:31 / commitment.cpp:102-132.  NULL on NULL params or
+ * unusable parameters.  Context key material (matrix A, trapdoor) is drawn
+ * from the OS entropy source, as the reference's SEAL keygen is.  The ring
+ * modulus is params->modulus when it is an NTT-friendly prime for
+ * ring_degree, else the built-in 17592169062401 (n <= 4096) /
+ * 17592180539393 (n <= 131072) -- the reference ignores the field entirely.*/
+LweContext* lwe_context_create(const PublicParams* params) LSR_NOEXCEPT;
+
+/* commitment.h:38 / commitment.cpp:134-136.  NULL-safe; zeroises key material. */
+void lwe_context_free(LweContext* ctx) LSR_NOEXCEPT;
+
+/* commitment.h:58-63 / commitment.cpp:138-164.  Message is padded with zeros
+ * or silently truncated to ring_degree words (commitment.cpp:146-149).
+ * seed == 0 draws fresh randomness (commitment.h:52 "0 = random"); any other
+ * seed makes the commitment a deterministic function of (context, message,
+ * seed).  NULL on NULL ctx / NULL message / failure.                        */
+LweCommitment* lwe_commit(LweContext* ctx, const uint64_t* message, size_t msg_len,
+                          uint64_t seed) LSR_NOEXCEPT;
+
+/* commitment.h:70 / commitment.cpp:166-177.  NULL-safe; zeroises then frees. */
+void lwe_commitment_free(LweCommitment* comm) LSR_NOEXCEPT;
+
+/* commitment.h:78 / commitment.cpp:179-198.  Deep copy; NULL on NULL/empty. */
+LweCommitment* lwe_commitment_clone(const LweCommitment* comm) LSR_NOEXCEPT;
+
+/* commitment.h:94-100 / commitment.cpp:200-232.  Opens the commitment with the
+ * context's trapdoor (the reference decrypts with the SEAL secret key) and
+ * compares the first msg_len decoded words with `message` in constant time.
+ * `opening` is ignored, as in the reference (commitment.cpp:205).
+ * 1 = match, 0 = mismatch (also msg_len > ring_degree), -1 = NULL argument
+ * or malformed container.                                                  */
+int lwe_verify_opening(const LweContext* ctx, const LweCommitment* commitment,
+                       const uint64_t* message, size_t msg_len,
+                       const LweOpening* opening) LSR_NOEXCEPT;
+
+/* commitment.h:113-118 / commitment.cpp:234-276.  sum_i (coeffs[i] mod p) * C_i,
+ * p = plaintext modulus (commitment.cpp:90 reduces coefficients the same way).
+ * NULL entries of `commitments` are skipped; NULL result on NULL arguments,
+ * count == 0, a malformed container, or when every entry was NULL.          */
+LweCommitment* lwe_linear_combine(const LweContext* ctx, const LweCommitment** commitments,
+                                  const uint64_t* coeffs, size_t count) LSR_NOEXCEPT;
+
+/* ===================================================================== */
+/* Part 1d -- sampler (include/lambda_snark/utils.h:27, src/utils.cpp:132-146) */
+/* ===================================================================== */
+
+/* CDT discrete Gaussian; samples are two's-complement int64 stored in u64.
+ * -1 on NULL output, len == 0, sigma <= 0 or non-finite.  Entropy: a fresh
+ * 256-bit key from the OS per call, expanded on the device.                */
+int sample_gaussian(uint64_t* output, size_t len, double sigma) LSR_NOEXCEPT;
+
+/* ===================================================================== */
+/* Part 1e -- R1CS handle (include/lambda_snark/r1cs.h:38-79, src/ffi.cpp:27-105),
+ * declared by hand in rust-api/lambda-snark-core/src/r1cs.rs:121-141.
+ * Host-only (a handful of sparse mat-vecs), NTL-free.                     */
+/* ===================================================================== */
+
+typedef struct {
+    uint32_t row;
+    uint32_t col;
+    uint64_t value;
+} SparseEntry;
+
+typedef struct {
+    SparseEntry* entries;
+    size_t       n_entries;
+    uint32_t     n_rows;
+    uint32_t     n_cols;
+} SparseMatrix;
+
+typedef struct {
+    uint64_t* values;
+    size_t    len;
+} R1CSWitness;
+
+LambdaSnarkError lambda_snark_r1cs_create(const SparseMatrix* A, const SparseMatrix* B,
+                                          const SparseMatrix* C, uint64_t modulus,
+                                          void** out_r1cs);
+LambdaSnarkError lambda_snark_r1cs_validate_witness(void* r1cs, const R1CSWitness* witness,
+                                                    bool* out_valid);
+void     lambda_snark_r1cs_free(void* r1cs);
+uint32_t lambda_snark_r1cs_num_constraints(void* r1cs);
+uint32_t lambda_snark_r1cs_num_variables(void* r1cs);
+
+/* ===================================================================== */
+/* Part 2 -- batched and device-pointer extensions (new; no reference      */
+/* counterpart: the reference is one polynomial / one commitment per call) */
+/* ===================================================================== */
+
+/* Library / device management.  All return 0 on success, -1 on failure.   */
+int         lsr_device_count(void) LSR_NOEXCEPT;
+int         lsr_set_device(int device) LSR_NOEXCEPT;   /* device new contexts bind to (per thread) */
+const char* lsr_version(void) LSR_NOEXCEPT;
+const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnostic string */
+
+/* Introspection used by the tests and the host wrappers. */
+uint64_t lsr_ntt_modulus(const NttContext* ctx) LSR_NOEXCEPT;
+uint32_t lsr_ntt_degree(const NttContext* ctx) LSR_NOEXCEPT;
+uint64_t lsr_ntt_root(const NttContext* ctx) LSR_NOEXCEPT;      /* minimal primitive 2n-th root */
+int      lsr_ntt_device(const NttContext* ctx) LSR_NOEXCEPT;
+
+/* batch polynomials, contiguous [batch][n], HOST memory, in place */
+int ntt_forward_batch(const NttContext* ctx, uint64_t* coeffs, size_t batch) LSR_NOEXCEPT;
+int ntt_inverse_batch(const NttContext* ctx, uint64_t* evals, size_t batch) LSR_NOEXCEPT;
+int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a,
+                            const uint64_t* b, size_t total) LSR_NOEXCEPT;
+
+/* same, DEVICE memory; asynchronous on `stream` */
+int lsr_ntt_forward_device(const NttContext* ctx, uint64_t* d_coeffs, size_t batch,
+                           void* stream) LSR_NOEXCEPT;
+int lsr_ntt_inverse_device(const NttContext* ctx, uint64_t* d_evals, size_t batch,
+                           void* stream) LSR_NOEXCEPT;
+int lsr_ntt_mul_pointwise_device(const NttContext* ctx, uint64_t* d_result, const uint64_t* d_a,
+                                 const uint64_t* d_b, size_t total, void* stream) LSR_NOEXCEPT;
+
+/* Reproducible context: same (params, seed32) -> same matrix A / trapdoor on
+ * every rank and on the CPU oracle.                                         */
+LweContext* lwe_context_create_seeded(const PublicParams* params,
+                                      const uint8_t seed32[32]) LSR_NOEXCEPT;
+
+uint64_t lsr_lwe_modulus(const LweContext* ctx) LSR_NOEXCEPT;          /* ring modulus q in use */
+uint64_t lsr_lwe_plain_modulus(const LweContext* ctx) LSR_NOEXCEPT;    /* p */
+uint64_t lsr_lwe_delta(const LweContext* ctx) LSR_NOEXCEPT;            /* (q-1)/p */
+size_t   lsr_lwe_commitment_words(const LweContext* ctx) LSR_NOEXCEPT; /* 1 + k*n */
+/* copies A-hat ([k][k][n], NTT domain) to host memory; for cross-checks */
+int      lsr_lwe_copy_matrix(const LweContext* ctx, uint64_t* out) LSR_NOEXCEPT;
+
+/* Path selection for lwe_commit_batch*: 0 auto, 1 force the generic
+ * multi-kernel path, 2 force the fused kernel (-1 at call time if it does
+ * not support the context's (n, k, sigma)).                                 */
+int lsr_lwe_set_commit_path(LweContext* ctx, int path) LSR_NOEXCEPT;
+
+/* `count` commitments in one call.  messages: [count][msg_len] (each padded /
+ * truncated to n as lwe_commit does); seeds: [count], all non-zero use is the
+ * caller's business (0 is NOT replaced here); out: [count][1 + k*n] words in
+ * the LweCommitment container layout.  HOST memory (pinned memory makes the
+ * copies overlap with the kernels).                                         */
+int lwe_commit_batch(LweContext* ctx, const uint64_t* messages, size_t msg_len,
+                     const uint64_t* seeds, size_t count, uint64_t* out_words) LSR_NOEXCEPT;
+
+/* same, DEVICE memory; asynchronous on `stream` */
+int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len,
+                                const uint64_t* d_seeds, size_t count, uint64_t* d_out_words,
+                                void* stream) LSR_NOEXCEPT;
+
+/* results[i] in {1, 0, -1} as lwe_verify_opening; commitments: [count][1+k*n]
+ * container words, messages: [count][msg_len].  HOST memory.                */
+int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words,
+                             const uint64_t* messages, size_t msg_len, size_t count,
+                             int* results) LSR_NOEXCEPT;
+
+/* Deterministic sampler: samples a pure function of (seed32, sigma, index);
+ * the oracle implements the same stream (lsro_sample_gaussian_seeded).      */
+int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
+                               const uint8_t seed32[32]) LSR_NOEXCEPT;
+
+/* s, e of the commitment (context, seed): two's-complement, each [k][n];
+ * test hook for the fused sampler.  HOST memory.                            */
+int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LSR_NOEXCEPT;
+
+#ifdef __cplusplus
+}  /* extern "C" */
+#endif
+#endif /* LAMBDA_SNARK_B200_H */

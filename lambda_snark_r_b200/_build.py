@@ -1,0 +1,86 @@
+"""In-tree build of the C-ABI library (nvcc, sm_100a only).
+
+Produces lambda_snark_r_b200/lib/liblambda_snark_core.so (what ctypes / a C
+harness loads) and liblambda_snark_core.a (what lambda-snark-sys would link;
+same name as the reference's static library, cpp-core/CMakeLists.txt:107).
+Objects are rebuilt only when a source or header is newer.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+OBJ = PKG / "_build"
+LIB = PKG / "lib"
+SO = LIB / "liblambda_snark_core.so"
+AR = LIB / "liblambda_snark_core.a"
+
+SOURCES = ["lsr_host.cpp", "lsr_r1cs.cpp", "lsr_abi.cpp", "lsr_ntt.cu", "lsr_commit.cu", "lsr_commit_fused.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _flags() -> list[str]:
+    return ["-std=c++17", "-O3", "-lineinfo", *ARCH, "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas",
+            "-ccbin", shutil.which("g++") or "g++",
+            "-I", str(CSRC), "-I", str(ROOT / "include")]
+
+
+def _newest_header() -> float:
+    hs = list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list((ROOT / "include").rglob("*.h"))
+    return max(h.stat().st_mtime for h in hs)
+
+
+def _compile(src: str, force: bool, verbose: bool) -> Path:
+    s = CSRC / src
+    o = OBJ / (s.stem + ".o")
+    stamp = max(s.stat().st_mtime, _newest_header(), Path(__file__).stat().st_mtime)
+    if not force and o.exists() and o.stat().st_mtime >= stamp:
+        return o
+    cmd = [_nvcc(), *_flags(), "-x", "cu" if s.suffix == ".cu" else "c++", "-c", str(s), "-o", str(o)]
+    if s.suffix != ".cu":
+        cmd = [_nvcc(), *_flags(), "-c", str(s), "-o", str(o)]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    if verbose and r.stderr.strip():
+        print(r.stderr)
+    return o
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    OBJ.mkdir(exist_ok=True)
+    LIB.mkdir(exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force, verbose), SOURCES))
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not SO.exists() or SO.stat().st_mtime < newest:
+        cmd = [_nvcc(), "-shared", *ARCH, "-ccbin", shutil.which("g++") or "g++", "-cudart", "static",
+               "-o", str(SO), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+        if AR.exists():
+            AR.unlink()
+        subprocess.run(["ar", "rcs", str(AR), *map(str, objs)], check=True)
+    return SO
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose=True)
+    print("built", p)

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's safe wrappers over the C ABI.
+
+The reference's host side is Rust (rust-api/lambda-snark/src/{context,commitment,
+opening}.rs); there is no Rust toolchain in this image, so the same thin RAII
+layer is written in Python with the same names, argument meaning and error
+behaviour:
+
+    LweContext            context.rs:14-76     (validate, pack PublicParams, create/free)
+    Commitment            commitment.rs:13-110 (new, linear_combine, as_bytes, clone, drop)
+    verify_opening_with_context, generate_opening, Opening
+                          opening.rs:104-222
+    NttContext            the ntt_* FFI (bound by lambda-snark-sys, no safe Rust wrapper)
+
+All arithmetic happens in the CUDA library; numpy / torch only carry buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .capi import LweCommitment, LweOpening, PublicParams, u64p
+
+
+class LambdaSnarkError(RuntimeError):
+    pass
+
+
+def _lib():
+    return capi.load()
+
+
+def _u64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(u64p)
+
+
+def _vp(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+def last_error() -> str:
+    return (_lib().lsr_last_error() or b"").decode()
+
+
+def device_count() -> int:
+    return int(_lib().lsr_device_count())
+
+
+def set_device(dev: int) -> None:
+    if _lib().lsr_set_device(dev) != 0:
+        raise LambdaSnarkError(f"lsr_set_device({dev}) failed: {last_error()}")
+
+
+# --------------------------------------------------------------------------- NTT
+class NttContext:
+    """ntt_context_create / ntt_context_free (ntt.h:34-41)."""
+
+    def __init__(self, q: int, n: int):
+        self._h = _lib().ntt_context_create(q, n)
+        if not self._h:
+            raise LambdaSnarkError(f"ntt_context_create({q}, {n}) returned NULL")
+        self.q, self.n = q, n
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib().ntt_context_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def root(self) -> int:
+        return int(_lib().lsr_ntt_root(self._h))
+
+    # single-polynomial drop-in calls (in place on a copy)
+    def forward(self, coeffs) -> np.ndarray:
+        a = _u64(coeffs).copy()
+        if _lib().ntt_forward(self._h, _p(a), a.size) != 0:
+            raise LambdaSnarkError("ntt_forward returned -1")
+        return a
+
+    def inverse(self, evals) -> np.ndarray:
+        a = _u64(evals).copy()
+        if _lib().ntt_inverse(self._h, _p(a), a.size) != 0:
+            raise LambdaSnarkError("ntt_inverse returned -1")
+        return a
+
+    def mul_pointwise(self, a, b) -> np.ndarray:
+        a, b = _u64(a), _u64(b)
+        r = np.zeros_like(a)
+        _lib().ntt_mul_pointwise(self._h, _p(r), _p(a), _p(b), a.size)
+        return r
+
+    # batched host-memory calls, [batch][n]
+    def forward_batch(self, polys, inplace: bool = False) -> np.ndarray:
+        a = _u64(polys) if inplace else _u64(polys).copy()
+        assert a.size % self.n == 0
+        if _lib().ntt_forward_batch(self._h, _vp(a), a.size // self.n) != 0:
+            raise LambdaSnarkError(f"ntt_forward_batch failed: {last_error()}")
+        return a
+
+    def inverse_batch(self, polys, inplace: bool = False) -> np.ndarray:
+        a = _u64(polys) if inplace else _u64(polys).copy()
+        assert a.size % self.n == 0
+        if _lib().ntt_inverse_batch(self._h, _vp(a), a.size // self.n) != 0:
+            raise LambdaSnarkError(f"ntt_inverse_batch failed: {last_error()}")
+        return a
+
+    def mul_pointwise_batch(self, a, b) -> np.ndarray:
+        a, b = _u64(a), _u64(b)
+        r = np.zeros_like(a)
+        if _lib().ntt_mul_pointwise_batch(self._h, _vp(r), _vp(a), _vp(b), a.size) != 0:
+            raise LambdaSnarkError(f"ntt_mul_pointwise_batch failed: {last_error()}")
+        return r
+
+    # device-memory calls: raw pointers (e.g. torch_tensor.data_ptr()) and a cudaStream_t
+    def forward_device(self, dptr: int, batch: int, stream: int = 0) -> None:
+        if _lib().lsr_ntt_forward_device(self._h, C.c_void_p(dptr), batch, C.c_void_p(stream)) != 0:
+            raise LambdaSnarkError(f"lsr_ntt_forward_device failed: {last_error()}")
+
+    def inverse_device(self, dptr: int, batch: int, stream: int = 0) -> None:
+        if _lib().lsr_ntt_inverse_device(self._h, C.c_void_p(dptr), batch, C.c_void_p(stream)) != 0:
+            raise LambdaSnarkError(f"lsr_ntt_inverse_device failed: {last_error()}")
+
+    def mul_pointwise_device(self, r: int, a: int, b: int, total: int, stream: int = 0) -> None:
+        if _lib().lsr_ntt_mul_pointwise_device(self._h, C.c_void_p(r), C.c_void_p(a), C.c_void_p(b), total,
+                                               C.c_void_p(stream)) != 0:
+            raise LambdaSnarkError(f"lsr_ntt_mul_pointwise_device failed: {last_error()}")
+
+
+# ------------------------------------------------------------------- commitment
+@dataclass
+class Params:
+    """lambda-snark-core Params/Profile::RingB (lambda-snark-core/src/lib.rs:129-196)."""
+    n: int = 4096
+    k: int = 2
+    q: int = 17592169062401
+    sigma: float = 3.19
+    security_level: int = 128
+
+    def validate(self) -> None:          # lib.rs validation: n pow2, k>0, q>=2^24, sigma>=3.0
+        if self.n <= 0 or self.n & (self.n - 1):
+            raise LambdaSnarkError("invalid params: n must be a power of two")
+        if self.k <= 0:
+            raise LambdaSnarkError("invalid params: k must be positive")
+        if self.q < (1 << 24):
+            raise LambdaSnarkError("invalid params: q must be at least 2^24")
+        if not self.sigma >= 3.0:
+            raise LambdaSnarkError("invalid params: sigma must be at least 3.0")
+
+    def to_ffi(self) -> PublicParams:
+        return PublicParams(capi.PROFILE_RING_B, self.security_level, self.q, self.n, self.k, self.sigma)
+
+
+class LweContext:
+    """context.rs:14-76.  `seed32` (extension) makes the context reproducible."""
+
+    def __init__(self, params: Params, seed32: bytes | None = None, validate: bool = True):
+        if validate:
+            params.validate()
+        self.params = params
+        pp = params.to_ffi()
+        if seed32 is None:
+            self._h = _lib().lwe_context_create(C.byref(pp))
+        else:
+            assert len(seed32) == 32
+            self._h = _lib().lwe_context_create_seeded(C.byref(pp), seed32)
+        if not self._h:
+            raise LambdaSnarkError(f"lwe_context_create returned NULL: {last_error()}")
+        lib = _lib()
+        self.q = int(lib.lsr_lwe_modulus(self._h))            # ring modulus actually in use
+        self.p = int(lib.lsr_lwe_plain_modulus(self._h))
+        self.delta = int(lib.lsr_lwe_delta(self._h))
+        self.words = int(lib.lsr_lwe_commitment_words(self._h))
+        self.n, self.k = params.n, params.k
+
+    def modulus(self) -> int:            # context.rs: ctx.modulus() is the caller's field modulus
+        return self.params.q
+
+    def as_ptr(self):
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _lib().lwe_context_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_commit_path(self, path: int) -> None:
+        if _lib().lsr_lwe_set_commit_path(self._h, path) != 0:
+            raise LambdaSnarkError("lsr_lwe_set_commit_path failed")
+
+    def matrix(self) -> np.ndarray:
+        out = np.zeros((self.k, self.k, self.n), dtype=np.uint64)
+        if _lib().lsr_lwe_copy_matrix(self._h, _p(out)) != 0:
+            raise LambdaSnarkError("lsr_lwe_copy_matrix failed")
+        return out
+
+    def sample_se(self, seed: int):
+        s = np.zeros((self.k, self.n), dtype=np.int64)
+        e = np.zeros((self.k, self.n), dtype=np.int64)
+        if _lib().lsr_lwe_sample_se(self._h, seed, s.ctypes.data_as(capi.i64p), e.ctypes.data_as(capi.i64p)) != 0:
+            raise LambdaSnarkError("lsr_lwe_sample_se failed")
+        return s, e
+
+    # batched extension: messages [count][msg_len], seeds [count] -> containers [count][words]
+    def commit_batch(self, messages, seeds, out: np.ndarray | None = None) -> np.ndarray:
+        m = _u64(messages)
+        count, msg_len = m.shape
+        s = _u64(seeds)
+        assert s.size == count
+        if out is None:
+            out = np.zeros((count, self.words), dtype=np.uint64)
+        if _lib().lwe_commit_batch(self._h, _vp(m), msg_len, _vp(s), count, _vp(out)) != 0:
+            raise LambdaSnarkError(f"lwe_commit_batch failed: {last_error()}")
+        return out
+
+    def commit_batch_ptr(self, msgs_ptr: int, msg_len: int, seeds_ptr: int, count: int, out_ptr: int) -> None:
+        """Host pointers (e.g. pinned torch tensors)."""
+        if _lib().lwe_commit_batch(self._h, C.c_void_p(msgs_ptr), msg_len, C.c_void_p(seeds_ptr), count,
+                                   C.c_void_p(out_ptr)) != 0:
+            raise LambdaSnarkError(f"lwe_commit_batch failed: {last_error()}")
+
+    def commit_batch_device(self, msgs_ptr: int, msg_len: int, seeds_ptr: int, count: int, out_ptr: int,
+                            stream: int = 0) -> None:
+        if _lib().lsr_lwe_commit_batch_device(self._h, C.c_void_p(msgs_ptr), msg_len, C.c_void_p(seeds_ptr), count,
+                                              C.c_void_p(out_ptr), C.c_void_p(stream)) != 0:
+            raise LambdaSnarkError(f"lsr_lwe_commit_batch_device failed: {last_error()}")
+
+    def verify_batch(self, containers, messages) -> np.ndarray:
+        cw = _u64(containers)
+        m = _u64(messages)
+        count, msg_len = m.shape
+        res = np.zeros(count, dtype=np.int32)
+        if _lib().lwe_verify_opening_batch(self._h, _vp(cw), _vp(m), msg_len, count,
+                                           res.ctypes.data_as(C.POINTER(C.c_int))) != 0:
+            raise LambdaSnarkError(f"lwe_verify_opening_batch failed: {last_error()}")
+        return res
+
+
+class Commitment:
+    """commitment.rs:13-110 -- owns an `LweCommitment*` returned by the library."""
+
+    def __init__(self, inner):
+        self._inner = inner
+
+    @classmethod
+    def new(cls, ctx: LweContext, message, seed: int) -> "Commitment":
+        # commitment.rs:31-45: reduce each field element mod ctx.modulus(), then lwe_commit
+        modulus = ctx.modulus()
+        msg = _u64([int(v) % modulus for v in message])
+        ptr = _p(msg) if msg.size else C.cast(C.c_void_p(8), u64p)     # non-null dangling, as Vec::as_ptr
+        inner = _lib().lwe_commit(ctx.as_ptr(), ptr, msg.size, seed)
+        if not inner:
+            raise LambdaSnarkError("CommitmentFailed")
+        return cls(inner)
+
+    @classmethod
+    def linear_combine(cls, ctx: LweContext, commitments, coeffs) -> "Commitment":
+        # commitment.rs:48-84
+        if len(commitments) == 0:
+            raise LambdaSnarkError("no commitments provided")
+        if len(commitments) != len(coeffs):
+            raise LambdaSnarkError("commitments/coeffs length mismatch")
+        modulus = ctx.modulus()
+        ptrs = (capi.LweCommitmentP * len(commitments))(*[c._inner for c in commitments])
+        cf = _u64([int(v) % modulus for v in coeffs])
+        inner = _lib().lwe_linear_combine(ctx.as_ptr(), ptrs, _p(cf), len(commitments))
+        if not inner:
+            raise LambdaSnarkError("CommitmentFailed")
+        return cls(inner)
+
+    def as_bytes(self) -> np.ndarray:
+        """commitment.rs:87-93: the u64 words the Fiat-Shamir transcript hashes."""
+        raw = self._inner.contents
+        return np.ctypeslib.as_array(raw.data, shape=(raw.len,))
+
+    def as_ffi_ptr(self):
+        return self._inner
+
+    def clone(self) -> "Commitment":
+        inner = _lib().lwe_commitment_clone(self._inner)
+        if not inner:
+            raise LambdaSnarkError("lwe_commitment_clone returned null")
+        return Commitment(inner)
+
+    def close(self) -> None:
+        if getattr(self, "_inner", None):
+            _lib().lwe_commitment_free(self._inner)
+            self._inner = None
+
+    __del__ = close
+
+
+def verify_commitment(ctx: LweContext, commitment: Commitment, message, randomness=None) -> int:
+    """Raw lwe_verify_opening: 1 / 0 / -1."""
+    msg = _u64(message)
+    mp = _p(msg) if msg.size else C.cast(C.c_void_p(8), u64p)
+    if randomness is None:
+        opening = LweOpening(None, 0)
+    else:
+        r = _u64(randomness)
+        opening = LweOpening(_p(r), r.size)
+    return int(_lib().lwe_verify_opening(ctx.as_ptr(), commitment.as_ffi_ptr(), mp, msg.size, C.byref(opening)))
+
+
+# ------------------------------------------------------------------ openings
+@dataclass
+class Opening:                              # opening.rs:20-60
+    evaluation: int
+    witness: list
+
+
+def _horner(coeffs, alpha: int, q: int) -> int:   # polynomial.rs:97-113
+    acc = 0
+    for c in reversed(list(coeffs)):
+        acc = (acc * alpha + int(c)) % q
+    return acc
+
+
+def generate_opening(coeffs, alpha: int, randomness: int, modulus: int) -> Opening:
+    """opening.rs:104-115: y = f(alpha); witness = [randomness, coeffs...]."""
+    cs = [int(c) % modulus for c in coeffs]
+    return Opening(_horner(cs, alpha % modulus, modulus), [randomness] + cs)
+
+
+def verify_opening_with_context(commitment: Commitment, alpha: int, opening: Opening, modulus: int,
+                                ctx: LweContext) -> bool:
+    """opening.rs:160-222."""
+    if opening.evaluation >= modulus:
+        return False
+    if len(opening.witness) < 2:
+        return False
+    coeffs = [int(c) % modulus for c in opening.witness[1:]]
+    if (_horner(coeffs, alpha % modulus, modulus) - opening.evaluation) % modulus != 0:
+        return False
+    return verify_commitment(ctx, commitment, coeffs, [opening.witness[0]]) == 1
+
+
+# -------------------------------------------------------------------- sampler
+def sample_gaussian(length: int, sigma: float, seed32: bytes | None = None) -> np.ndarray:
+    """sample_gaussian (utils.h:27); returns int64 samples.  Raises on -1."""
+    out = np.zeros(max(length, 1), dtype=np.uint64)
+    if seed32 is None:
+        rc = _lib().sample_gaussian(_p(out), length, float(sigma))
+    else:
+        rc = _lib().lsr_sample_gaussian_seeded(_p(out), length, float(sigma), seed32)
+    if rc != 0:
+        raise LambdaSnarkError("sample_gaussian returned -1")
+    return out[:length].view(np.int64)

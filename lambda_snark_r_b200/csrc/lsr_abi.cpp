@@ -1,0 +1,333 @@
+// lsr_abi.cpp -- the extern "C" surface declared in include/lambda_snark_b200.h.
+//
+// Mirrors the error and ownership conventions of the reference's C ABI
+// (cpp-core/src/ntt.cpp, commitment.cpp, utils.cpp): no exception crosses the
+// boundary, failures are NULL / -1, every returned object is freed by its
+// matching *_free, NULL frees are no-ops, commitments are zeroised on free.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "lambda_snark_b200.h"
+#include "lsr_engine.h"
+
+using lsr::u64;
+
+#define LSR_TRY try {
+#define LSR_CATCH(ret)                                                        \
+    } catch (const std::exception& e) {                                       \
+        std::fprintf(stderr, "%s error: %s\n", __func__, e.what());           \
+        lsr::set_error(e.what());                                             \
+        return ret;                                                           \
+    } catch (...) {                                                           \
+        std::fprintf(stderr, "%s error: unknown exception\n", __func__);      \
+        return ret;                                                           \
+    }
+
+static LweCommitment* new_commitment(size_t words) {
+    LweCommitment* c = new (std::nothrow) LweCommitment;
+    if (!c) return nullptr;
+    c->len = words;
+    c->data = new (std::nothrow) uint64_t[words];
+    if (!c->data) { delete c; return nullptr; }
+    return c;
+}
+
+// commitment.cpp:62-86 container check (+ our fixed payload size and range)
+static bool container_ok(const LweContext* ctx, const LweCommitment* c) {
+    if (!c || !c->data || c->len < 1) return false;
+    const uint64_t byte_len = c->data[0];
+    if (byte_len == 0 || byte_len > (c->len - 1) * sizeof(uint64_t)) return false;
+    const size_t kn = (size_t)ctx->k * ctx->n;
+    if (byte_len != kn * sizeof(uint64_t)) return false;
+    for (size_t i = 0; i < kn; i++) if (c->data[1 + i] >= ctx->q) return false;
+    return true;
+}
+
+extern "C" {
+
+/* ------------------------------------------------------------------ misc */
+const char* lsr_version(void) LSR_NOEXCEPT { return "lambda-snark-r_b200 0.1 (sm_100a)"; }
+const char* lsr_last_error(void) LSR_NOEXCEPT { return lsr::last_error(); }
+
+int lsr_device_count(void) LSR_NOEXCEPT {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lsr_set_device(int device) LSR_NOEXCEPT {
+    int n = lsr_device_count();
+    if (device < 0 || device >= n) { lsr::set_error("lsr_set_device: no such device"); return -1; }
+    lsr::set_device_choice(device);
+    return lsr::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ? 0 : -1;
+}
+
+/* ------------------------------------------------------------------- NTT */
+NttContext* ntt_context_create(uint64_t q, uint32_t n) LSR_NOEXCEPT {
+    LSR_TRY
+    if (n == 0) return nullptr;                       // ntt.cpp:31
+    return lsr::ntt_create(q, n);
+    LSR_CATCH(nullptr)
+}
+
+void ntt_context_free(NttContext* ctx) LSR_NOEXCEPT {
+    try { lsr::ntt_destroy(ctx); } catch (...) {}
+}
+
+int ntt_forward(const NttContext* ctx, uint64_t* coeffs, uint32_t n) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !coeffs || n != ctx->degree) return -1;   // ntt.cpp:81
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(coeffs), 1, false) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int ntt_inverse(const NttContext* ctx, uint64_t* evals, uint32_t n) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !evals || n != ctx->degree) return -1;    // ntt.cpp:96
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(evals), 1, true) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+void ntt_mul_pointwise(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,
+                       uint32_t n) LSR_NOEXCEPT {
+    try {
+        if (!ctx || !result || !a || !b) return;          // ntt.cpp:113 (silent)
+        lsr::pointwise_host(ctx, reinterpret_cast<u64*>(result), reinterpret_cast<const u64*>(a),
+                            reinterpret_cast<const u64*>(b), n);
+    } catch (...) {}
+}
+
+int ntt_forward_batch(const NttContext* ctx, uint64_t* coeffs, size_t batch) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !coeffs) return -1;
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(coeffs), batch, false) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int ntt_inverse_batch(const NttContext* ctx, uint64_t* evals, size_t batch) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !evals) return -1;
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(evals), batch, true) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,
+                            size_t total) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !result || !a || !b) return -1;
+    return lsr::pointwise_host(ctx, reinterpret_cast<u64*>(result), reinterpret_cast<const u64*>(a),
+                               reinterpret_cast<const u64*>(b), total) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_ntt_forward_device(const NttContext* ctx, uint64_t* d, size_t batch, void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d) return -1;
+    return lsr::ntt_forward_launch(ctx, reinterpret_cast<u64*>(d), batch, static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_ntt_inverse_device(const NttContext* ctx, uint64_t* d, size_t batch, void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d) return -1;
+    return lsr::ntt_inverse_launch(ctx, reinterpret_cast<u64*>(d), batch, static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_ntt_mul_pointwise_device(const NttContext* ctx, uint64_t* r, const uint64_t* a, const uint64_t* b,
+                                 size_t total, void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !r || !a || !b) return -1;
+    return lsr::pointwise_launch(ctx, reinterpret_cast<u64*>(r), reinterpret_cast<const u64*>(a),
+                                 reinterpret_cast<const u64*>(b), total, static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+uint64_t lsr_ntt_modulus(const NttContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->modulus : 0; }
+uint32_t lsr_ntt_degree(const NttContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->degree : 0; }
+uint64_t lsr_ntt_root(const NttContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->psi : 0; }
+int      lsr_ntt_device(const NttContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->device : -1; }
+
+/* ------------------------------------------------------------ commitment */
+LweContext* lwe_context_create_seeded(const PublicParams* params, const uint8_t seed32[32]) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!params || !seed32) return nullptr;               // commitment.cpp:103
+    return lsr::lwe_create(params->modulus, params->ring_degree, params->module_rank, params->sigma, seed32);
+    LSR_CATCH(nullptr)
+}
+
+LweContext* lwe_context_create(const PublicParams* params) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!params) return nullptr;
+    uint8_t seed[32];
+    if (!lsr::host::os_entropy(seed, sizeof(seed))) { lsr::set_error("no entropy source"); return nullptr; }
+    LweContext* c = lsr::lwe_create(params->modulus, params->ring_degree, params->module_rank, params->sigma, seed);
+    volatile uint8_t* sp = seed;
+    for (size_t i = 0; i < sizeof(seed); i++) sp[i] = 0;
+    return c;
+    LSR_CATCH(nullptr)
+}
+
+void lwe_context_free(LweContext* ctx) LSR_NOEXCEPT {
+    try { lsr::lwe_destroy(ctx); } catch (...) {}
+}
+
+uint64_t lsr_lwe_modulus(const LweContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->q : 0; }
+uint64_t lsr_lwe_plain_modulus(const LweContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->p : 0; }
+uint64_t lsr_lwe_delta(const LweContext* ctx) LSR_NOEXCEPT { return ctx ? ctx->delta : 0; }
+size_t   lsr_lwe_commitment_words(const LweContext* ctx) LSR_NOEXCEPT { return ctx ? lsr::lwe_words(ctx) : 0; }
+
+int lsr_lwe_copy_matrix(const LweContext* ctx, uint64_t* out) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !out) return -1;
+    if (!lsr::cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice")) return -1;
+    const size_t bytes = (size_t)ctx->k * ctx->k * ctx->n * sizeof(uint64_t);
+    return lsr::cuda_ok(cudaMemcpy(out, ctx->d_A, bytes, cudaMemcpyDeviceToHost), "copy matrix") ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_lwe_set_commit_path(LweContext* ctx, int path) LSR_NOEXCEPT {
+    if (!ctx || path < 0 || path > 2) return -1;
+    ctx->commit_path = path;
+    return 0;
+}
+
+LweCommitment* lwe_commit(LweContext* ctx, const uint64_t* message, size_t msg_len, uint64_t seed) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !message) return nullptr;                 // commitment.cpp:144
+    if (seed == 0) {                                      // commitment.h:52 "0 = random"
+        uint8_t buf[8];
+        do {
+            if (!lsr::host::os_entropy(buf, sizeof(buf))) return nullptr;
+            std::memcpy(&seed, buf, sizeof(seed));
+        } while (seed == 0);
+    }
+    const size_t words = lsr::lwe_words(ctx);
+    LweCommitment* c = new_commitment(words);
+    if (!c) return nullptr;
+    const size_t used = msg_len < ctx->n ? msg_len : ctx->n;   // commitment.cpp:146-149
+    if (!lsr::lwe_commit_host(ctx, reinterpret_cast<const u64*>(message), used, reinterpret_cast<const u64*>(&seed), 1,
+                              reinterpret_cast<u64*>(c->data))) {
+        lwe_commitment_free(c);
+        return nullptr;
+    }
+    return c;
+    LSR_CATCH(nullptr)
+}
+
+int lwe_commit_batch(LweContext* ctx, const uint64_t* messages, size_t msg_len, const uint64_t* seeds,
+                     size_t count, uint64_t* out_words) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !seeds || !out_words || (!messages && msg_len)) return -1;
+    return lsr::lwe_commit_host(ctx, reinterpret_cast<const u64*>(messages), msg_len,
+                                reinterpret_cast<const u64*>(seeds), count, reinterpret_cast<u64*>(out_words)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len,
+                                const uint64_t* d_seeds, size_t count, uint64_t* d_out_words,
+                                void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d_seeds || !d_out_words || (!d_messages && msg_len)) return -1;
+    return lsr::lwe_commit_launch(ctx, reinterpret_cast<const u64*>(d_messages), msg_len,
+                                  reinterpret_cast<const u64*>(d_seeds), count,
+                                  reinterpret_cast<u64*>(d_out_words), static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+void lwe_commitment_free(LweCommitment* comm) LSR_NOEXCEPT {
+    if (!comm) return;                                    // commitment.cpp:167
+    if (comm->data) {
+        volatile uint64_t* p = comm->data;                // zeroise (commitment.cpp:169-173)
+        for (size_t i = 0; i < comm->len; i++) p[i] = 0;
+        delete[] comm->data;
+    }
+    delete comm;
+}
+
+LweCommitment* lwe_commitment_clone(const LweCommitment* comm) LSR_NOEXCEPT {
+    if (!comm || comm->len == 0 || !comm->data) return nullptr;   // commitment.cpp:180-182
+    LweCommitment* c = new_commitment(comm->len);
+    if (!c) return nullptr;
+    std::memcpy(c->data, comm->data, comm->len * sizeof(uint64_t));
+    return c;
+}
+
+int lwe_verify_opening(const LweContext* ctx, const LweCommitment* commitment, const uint64_t* message,
+                       size_t msg_len, const LweOpening* /*opening*/) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !commitment || !message) return -1;       // commitment.cpp:207
+    if (!container_ok(ctx, commitment)) return -1;        // :210-212
+    if (msg_len > ctx->n) return 0;                       // :219-221
+    int result = -1;
+    if (!lsr::lwe_verify_host(ctx, reinterpret_cast<const u64*>(commitment->data),
+                              reinterpret_cast<const u64*>(message), msg_len, 1, &result)) return -1;
+    return result;
+    LSR_CATCH(-1)
+}
+
+int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words, const uint64_t* messages,
+                             size_t msg_len, size_t count, int* results) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !comm_words || !results || (!messages && msg_len)) return -1;
+    return lsr::lwe_verify_host(ctx, reinterpret_cast<const u64*>(comm_words),
+                                reinterpret_cast<const u64*>(messages), msg_len, count, results) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+LweCommitment* lwe_linear_combine(const LweContext* ctx, const LweCommitment** commitments,
+                                  const uint64_t* coeffs, size_t count) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !commitments || !coeffs || count == 0) return nullptr;   // commitment.cpp:240-242
+    const size_t kn = (size_t)ctx->k * ctx->n;
+    std::vector<u64> payloads;
+    std::vector<u64> cf;
+    for (size_t i = 0; i < count; i++) {
+        if (!commitments[i]) continue;                    // :248-250
+        if (!container_ok(ctx, commitments[i])) return nullptr;   // :253-255
+        payloads.insert(payloads.end(), commitments[i]->data + 1, commitments[i]->data + 1 + kn);
+        cf.push_back(coeffs[i]);
+    }
+    if (cf.empty()) return nullptr;                       // :268-270
+    LweCommitment* out = new_commitment(1 + kn);
+    if (!out) return nullptr;
+    out->data[0] = kn * sizeof(uint64_t);
+    if (!lsr::lwe_lincomb_host(ctx, payloads.data(), cf.data(), cf.size(), reinterpret_cast<u64*>(out->data + 1))) {
+        lwe_commitment_free(out);
+        return nullptr;
+    }
+    return out;
+    LSR_CATCH(nullptr)
+}
+
+int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !s || !e) return -1;
+    return lsr::lwe_sample_se_host(ctx, seed, s, e) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+/* --------------------------------------------------------------- sampler */
+int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma, const uint8_t seed32[32]) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!output || len == 0 || !(sigma > 0.0) || !std::isfinite(sigma) || !seed32) return -1;   // utils.cpp:133-135
+    return lsr::sample_gaussian_host(reinterpret_cast<u64*>(output), len, sigma, seed32) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int sample_gaussian(uint64_t* output, size_t len, double sigma) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!output || len == 0 || !(sigma > 0.0) || !std::isfinite(sigma)) return -1;               // utils.cpp:133-135
+    uint8_t seed[32];
+    if (!lsr::host::os_entropy(seed, sizeof(seed))) return -1;
+    const bool ok = lsr::sample_gaussian_host(reinterpret_cast<u64*>(output), len, sigma, seed);
+    volatile uint8_t* sp = seed;
+    for (size_t i = 0; i < sizeof(seed); i++) sp[i] = 0;
+    return ok ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+}  // extern "C"

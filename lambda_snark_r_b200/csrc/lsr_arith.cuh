@@ -1,0 +1,121 @@
+// lsr_arith.cuh -- modular arithmetic on u64 residues for sm_100a.
+//
+// B200 has no 64-bit integer multiplier: everything here is spelled in 32-bit
+// IMAD (mad.lo / mad.hi / mad.wide), the pipe that bounds the NTT.  Counts in
+// comments are IMAD-pipe instructions per call.
+#pragma once
+#include "lsr_common.h"
+
+namespace lsr {
+
+__device__ __forceinline__ u32 lo32(u64 x) { return (u32)x; }
+__device__ __forceinline__ u32 hi32(u64 x) { return (u32)(x >> 32); }
+__device__ __forceinline__ u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+__device__ __forceinline__ u64 mad_wide(u32 a, u32 b, u64 c) {
+    u64 d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul_wide(u32 a, u32 b) {
+    u64 d;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ u32 mad_lo(u32 a, u32 b, u32 c) {
+    u32 d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// low 64 bits of  x*w + y*z   (6 IMAD, no carry chains: the two wide products
+// accumulate in one 64-bit register pair, the four cross terms only touch the
+// high word)
+__device__ __forceinline__ u64 mullo2_acc(u64 x, u64 w, u64 y, u64 z) {
+    u64 acc = mul_wide(lo32(x), lo32(w));
+    acc = mad_wide(lo32(y), lo32(z), acc);
+    u32 h = hi32(acc);
+    h = mad_lo(lo32(x), hi32(w), h);
+    h = mad_lo(hi32(x), lo32(w), h);
+    h = mad_lo(lo32(y), hi32(z), h);
+    h = mad_lo(hi32(y), lo32(z), h);
+    return pack64(lo32(acc), h);
+}
+
+// Truncated Shoup multiplication: x * w mod q, lazily.
+//   ws = floor(w * 2^64 / q), nq = 2^64 - q, any x < 2^64, w < q < 2^62.
+// The quotient estimate drops the low partial product and the carries of the
+// two cross products, so it undershoots floor(x*ws/2^64) by at most 2; the
+// exact Shoup remainder is < 2q, hence the result is in [0, 4q).
+// 9 IMAD + 2 ALU.
+__device__ __forceinline__ u64 mulred4(u64 x, u64 w, u64 ws, u64 nq) {
+    const u32 x0 = lo32(x), x1 = hi32(x);
+    const u32 s0 = lo32(ws), s1 = hi32(ws);
+    const u32 a = __umulhi(x1, s0);
+    const u32 b = __umulhi(x0, s1);
+    const u64 qh = mad_wide(x1, s1, (u64)a) + (u64)b;
+    return mullo2_acc(x, w, qh, nq);
+}
+
+// Exact Shoup multiplication (SEAL multiply_uint_mod_lazy): result in [0, 2q).
+__device__ __forceinline__ u64 mulred2(u64 x, u64 w, u64 ws, u64 nq) {
+    const u64 qh = __umul64hi(x, ws);
+    return mullo2_acc(x, w, qh, nq);
+}
+
+// x >= m ? x - m : x, written so the subtraction's borrow is the predicate
+__device__ __forceinline__ u64 csub(u64 x, u64 m) {
+    const u64 t = x - m;
+    return x < m ? x : t;
+}
+
+// v < 2^7 * q  ->  [0, q).   3 IMAD + shifts + one conditional subtract.
+__device__ __forceinline__ u64 reduce_small(u64 v, const ModParams& mp) {
+    const u32 vs = (u32)(v >> mp.red_sh);
+    const u32 est = __umulhi(vs, mp.red_c);           // floor(v/q) - 1 <= est <= floor(v/q)
+    u64 acc = mad_wide(est, lo32(mp.nq), v);          // v - est*q  (mod 2^64)
+    const u32 h = mad_lo(est, hi32(mp.nq), hi32(acc));
+    return csub(pack64(lo32(acc), h), mp.q);
+}
+
+// Exact reduction of a 128-bit value (SEAL barrett_reduce_128, used by
+// multiply_uint_mod): (z1:z0) mod q for any z, q < 2^61.
+__device__ __forceinline__ u64 barrett128(u64 z0, u64 z1, const ModParams& mp) {
+    // tmp3 = floor(z * ratio / 2^128) up to an error of 1
+    const u64 c1 = __umul64hi(z0, mp.bar_lo);
+    const u64 t2lo = z0 * mp.bar_hi;
+    const u64 t2hi = __umul64hi(z0, mp.bar_hi);
+    const u64 s1 = t2lo + c1;
+    const u64 carry1 = s1 < t2lo;
+    const u64 t3lo = z1 * mp.bar_lo;
+    const u64 t3hi = __umul64hi(z1, mp.bar_lo);
+    const u64 s2 = s1 + t3lo;
+    const u64 carry2 = s2 < s1;
+    const u64 qhat = z1 * mp.bar_hi + t2hi + carry1 + t3hi + carry2;
+    const u64 r = z0 - qhat * mp.q;
+    return csub(r, mp.q);
+}
+
+// exact (a * b) mod q for any u64 a, b  (ntt.cpp:116-118 -> multiply_uint_mod)
+__device__ __forceinline__ u64 mulmod_exact(u64 a, u64 b, const ModParams& mp) {
+    return barrett128(a * b, __umul64hi(a, b), mp);
+}
+
+// exact x mod q for any u64 x
+__device__ __forceinline__ u64 reduce64(u64 x, const ModParams& mp) {
+    return barrett128(x, 0, mp);
+}
+
+// Input sanitiser: SEAL documents [0, 4q) inputs for the lazy forward
+// transform; anything larger is reduced exactly (rare, warp-divergent branch)
+// so that every u64 input has a defined result: NTT(x mod q).
+__device__ __forceinline__ u64 sanitize(u64 x, u64 limit, const ModParams& mp) {
+    if (__builtin_expect(x >= limit, 0)) x = reduce64(x, mp);
+    return x;
+}
+
+// modular add/sub on canonical residues
+__device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
+__device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+}  // namespace lsr

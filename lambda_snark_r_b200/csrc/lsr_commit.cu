@@ -1,0 +1,508 @@
+// lsr_commit.cu -- Module-LWE commitment engine behind lwe_* (K4-K7).
+//
+// Replaces cpp-core/src/commitment.cpp (SEAL BFV symmetric encryption + zstd
+// container) with t = A*s + e + Delta*m over R_q = Z_q[X]/(X^n+1), the
+// definition north_star asks for.  This file holds the
+// context life cycle and the GENERIC multi-kernel path, valid for every (n, k)
+// the NTT supports:
+//     sample_se -> forward NTT (batch*k) -> matvec -> inverse NTT -> finalize
+// lsr_commit_fused.cu holds the single-kernel fused path used for the
+// headline configuration.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "lsr_arith.cuh"
+#include "lsr_engine.h"
+#include "lsr_sampler.cuh"
+
+namespace lsr {
+
+bool fused_commit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
+                         size_t count, u64* d_out, cudaStream_t stream);   // lsr_commit_fused.cu
+bool fused_prepare(LweContext* ctx, cudaStream_t stream);                  // lsr_commit_fused.cu
+
+static ChaChaKey make_key(const LweContext* c) {
+    ChaChaKey k;
+    for (int i = 0; i < 8; i++) k.k[i] = c->key[i];
+    return k;
+}
+
+// ---------------------------------------------------------------------------
+// generic K7-in-K4: one thread per (commitment, 16-coefficient chunk).
+// Randomness layout of DESIGN.md 3.3: block b = 2P + (j>>3) gives the 64-bit
+// u of coefficient j of polynomial P; block 4k bit 16P + j gives its sign.
+// s -> S[b][P][n] as residues, e -> out payload (finalize adds the rest).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+sample_se_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, u64 q, u32 n, u32 k,
+                 const u64* __restrict__ seeds, size_t count, u64* __restrict__ S,
+                 u64* __restrict__ out, size_t out_stride) {
+    const size_t chunks = n >> 4;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * chunks) return;
+    const size_t b = idx / chunks;
+    const u32 tau = (u32)(idx % chunks);
+    const u64 seed = seeds[b];
+    const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
+    u32 sg[16];
+    chacha_block(key, s_lo, s_hi, tau, kDomCommit | (4u * k), sg);
+    for (u32 P = 0; P < 2 * k; P++) {
+        u64* dst = (P < k) ? S + ((b * k + P) * (size_t)n) + 16u * tau
+                           : out + b * out_stride + 1 + (size_t)(P - k) * n + 16u * tau;
+        const u32 sbits = sg[P >> 1] >> ((P & 1) * 16);
+#pragma unroll
+        for (u32 h = 0; h < 2; h++) {
+            u32 x[16];
+            chacha_block(key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
+#pragma unroll
+            for (u32 w = 0; w < 8; w++) {
+                const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
+                const u32 mag = cdt_magnitude_global(cdf, cdf_n, u);
+                const u32 j = 8 * h + w;
+                dst[j] = signed_residue(mag, (sbits >> j) & 1u, q);
+            }
+        }
+    }
+}
+
+// S[b][.][x] <- A[.][.][x] * S[b][.][x]   (NTT-domain mat-vec, in place)
+template <int KMAX>
+__global__ void __launch_bounds__(256)
+matvec_kernel(const ModParams mp, const u64* __restrict__ A, u32 n, u32 k, size_t count,
+              u64* __restrict__ S) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * n) return;
+    const size_t b = idx / n;
+    const u32 x = (u32)(idx % n);
+    u64 sv[KMAX];
+    u64* base = S + b * k * (size_t)n + x;
+#pragma unroll
+    for (u32 j = 0; j < KMAX; j++) if (j < k) sv[j] = base[(size_t)j * n];
+    for (u32 i = 0; i < k; i++) {
+        u64 acc = 0;
+#pragma unroll
+        for (u32 j = 0; j < KMAX; j++) {
+            if (j < k) acc = addmod(acc, mulmod_exact(A[((size_t)i * k + j) * n + x], sv[j], mp), mp.q);
+        }
+        base[(size_t)i * n] = acc;
+    }
+}
+
+// out[b] = [k*n*8, S[b] + e (already in out) + [i==k-1] Delta*(m mod p)]
+__global__ void __launch_bounds__(256)
+finalize_kernel(const ModParams mp, u64 delta, u64 p, u32 n, u32 k, const u64* __restrict__ S,
+                const u64* __restrict__ msgs, size_t msg_len, size_t count, u64* __restrict__ out,
+                size_t out_stride) {
+    const size_t kn = (size_t)k * n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * kn) return;
+    const size_t b = idx / kn;
+    const size_t r = idx % kn;
+    u64* o = out + b * out_stride;
+    if (r == 0) o[0] = kn * 8;
+    u64 v = addmod(S[idx], o[1 + r], mp.q);
+    const size_t x = r - (size_t)(k - 1) * n;          // coefficient index if last row
+    if (r >= (size_t)(k - 1) * n && x < msg_len) {     // msg_len already clamped to n
+        const u64 m = msgs[b * msg_len + x] % p;
+        v = addmod(v, mulmod_exact(delta, m, mp), mp.q);
+    }
+    o[1 + r] = v;
+}
+
+// A[k-1][j] = f_j - sum_i z_i * A[i][j]   (context set-up; F holds f-hat)
+__global__ void trapdoor_row_kernel(const ModParams mp, u32 n, u32 k, const u64* __restrict__ zh,
+                                    const u64* __restrict__ F, u64* __restrict__ A) {
+    const u32 idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= k * n) return;
+    const u32 j = idx / n, x = idx % n;
+    u64 acc = F[(size_t)j * n + x];
+    for (u32 i = 0; i + 1 < k; i++) {
+        const u64 prod = mulmod_exact(zh[(size_t)i * n + x], A[((size_t)i * k + j) * n + x], mp);
+        acc = submod(acc, prod, mp.q);
+    }
+    A[((size_t)(k - 1) * k + j) * n + x] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// K6: verification.  check -> copy rows 0..k-2 -> forward NTT -> U = sum z*t
+// -> inverse NTT -> decode + compare.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+verify_prepare_kernel(u64 q, u32 n, u32 k, const u64* __restrict__ comm, size_t stride, size_t count,
+                      u64* __restrict__ T, int* __restrict__ invalid) {
+    const size_t kn = (size_t)k * n;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * kn) return;
+    const size_t b = idx / kn, r = idx % kn;
+    const u64* c = comm + b * stride;
+    if (r == 0 && c[0] != kn * 8) invalid[b] = 1;
+    const u64 v = c[1 + r];
+    if (v >= q) invalid[b] = 1;
+    if (r < (size_t)(k - 1) * n) T[b * (size_t)(k - 1) * n + r] = v < q ? v : 0;
+}
+
+__global__ void __launch_bounds__(256)
+verify_dot_kernel(const ModParams mp, u32 n, u32 k, const u64* __restrict__ zh,
+                  const u64* __restrict__ T, size_t count, u64* __restrict__ U) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * n) return;
+    const size_t b = idx / n;
+    const u32 x = (u32)(idx % n);
+    u64 acc = 0;
+    for (u32 i = 0; i + 1 < k; i++)
+        acc = addmod(acc, mulmod_exact(zh[(size_t)i * n + x], T[(b * (k - 1) + i) * (size_t)n + x], mp), mp.q);
+    U[idx] = acc;
+}
+
+// diff[b] |= decode(U + t_last)[x] ^ msg[x]  for x < msg_len  (commitment.cpp:223-226)
+__global__ void __launch_bounds__(256)
+verify_decode_kernel(u64 q, u64 delta, u64 p, u32 n, u32 k, const u64* __restrict__ U,
+                     const u64* __restrict__ comm, size_t stride, const u64* __restrict__ msgs,
+                     size_t msg_len, size_t count, unsigned long long* __restrict__ diff) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * msg_len) return;
+    const size_t b = idx / msg_len, x = idx % msg_len;
+    u64 last = comm[b * stride + 1 + (size_t)(k - 1) * n + x];
+    if (last >= q) last = 0;                                  // flagged invalid elsewhere
+    const u64 v = addmod(U[b * (size_t)n + x], last, q);
+    const u64 d = ((v + delta / 2) / delta) % p;
+    const u64 df = d ^ msgs[b * msg_len + x];
+    if (df) atomicOr(diff + b, (unsigned long long)df);
+}
+
+// K5: out[x] = sum_i (c_i mod p) * t_i[x] mod q  (commitment.cpp:257-265)
+__global__ void __launch_bounds__(256)
+lincomb_kernel(const ModParams mp, u64 p, size_t kn, const u64* __restrict__ payloads,
+               const u64* __restrict__ coeffs, size_t count, u64* __restrict__ out) {
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= kn) return;
+    u64 acc = 0;
+    for (size_t i = 0; i < count; i++)
+        acc = addmod(acc, mulmod_exact(coeffs[i] % p, payloads[i * kn + x], mp), mp.q);
+    out[x] = acc;
+}
+
+// K7 standalone: sample i uses draws (2i, 2i+1) of stream (key, dom=kDomSample),
+// i.e. one ChaCha block per 4 samples (utils.cpp:95-121 draw order)
+__global__ void __launch_bounds__(128)
+sample_gaussian_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, size_t len,
+                       u64* __restrict__ out) {
+    const size_t blk = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (blk * 4 >= len) return;
+    u32 x[16];
+    chacha_block(key, (u32)blk, (u32)(blk >> 32), 0u, kDomSample, x);
+#pragma unroll
+    for (u32 w = 0; w < 4; w++) {
+        const size_t i = blk * 4 + w;
+        if (i < len) {
+            const u64 u1 = (u64)x[4 * w] | ((u64)x[4 * w + 1] << 32);
+            const u32 mag = cdt_magnitude_global(cdf, cdf_n, u1);
+            out[i] = (u64)signed_value(mag, x[4 * w + 2] & 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ life cycle
+static inline unsigned grid_for(size_t items, unsigned block) { return (unsigned)((items + block - 1) / block); }
+
+size_t lwe_words(const LweContext* c) { return 1 + (size_t)c->k * c->n; }
+
+LweContext* lwe_create(u64 modulus_req, uint32_t n, uint32_t k, double sigma, const uint8_t seed32[32]) {
+    // SEAL BFV needs a power-of-two degree >= 1024 (reference test_commitment.cpp:16);
+    // here any power of two in [16, 2^17] works (16 = one randomness chunk)
+    if (n < 16 || (n & (n - 1)) || n > (1u << kMaxLogN)) { set_error("lwe_context_create: bad ring_degree"); return nullptr; }
+    if (k < 1 || k > 16) { set_error("lwe_context_create: bad module_rank"); return nullptr; }
+    std::vector<u64> cdf = host::build_cdt(sigma);
+    if (cdf.empty()) { set_error("lwe_context_create: bad sigma"); return nullptr; }
+    const u64 q = host::ntt_friendly_prime(modulus_req, n)
+                      ? modulus_req
+                      : (n <= 4096 ? kDefaultModulusSmall : kDefaultModulusLarge);
+
+    LweContext* c = new (std::nothrow) LweContext;
+    if (!c) return nullptr;
+    c->q = q; c->n = n; c->k = k; c->sigma = sigma;
+    c->p = host::plain_modulus(q);
+    c->delta = (q - 1) / c->p;
+    c->cdf = std::move(cdf);
+    host::load_key(seed32, c->key);
+    c->ntt = ntt_create(q, n);
+    if (!c->ntt) { delete c; return nullptr; }
+    c->device = c->ntt->device;
+    c->logn = c->ntt->logn;
+
+    const size_t poly = (size_t)n * sizeof(u64);
+    bool ok = cuda_ok(cudaMalloc(&c->d_A, poly * k * k), "cudaMalloc(A)") &&
+              cuda_ok(cudaMalloc(&c->d_zh, poly * std::max<uint32_t>(k - 1, 1)), "cudaMalloc(z)") &&
+              cuda_ok(cudaMalloc(&c->d_cdf, c->cdf.size() * sizeof(u64)), "cudaMalloc(cdf)") &&
+              cuda_ok(cudaMemcpy(c->d_cdf, c->cdf.data(), c->cdf.size() * sizeof(u64), cudaMemcpyHostToDevice), "upload cdf");
+    u64* d_F = nullptr;
+    ok = ok && cuda_ok(cudaMalloc(&d_F, poly * k), "cudaMalloc(f)");
+    if (ok) {
+        std::vector<u64> tmp(n);
+        for (uint32_t i = 0; ok && i + 1 < k; i++) {
+            for (uint32_t j = 0; ok && j < k; j++) {
+                host::uniform_poly(c->key, i * k + j, q, n, tmp.data());
+                ok = cuda_ok(cudaMemcpy(c->d_A + ((size_t)i * k + j) * n, tmp.data(), poly, cudaMemcpyHostToDevice), "upload A");
+            }
+        }
+        for (uint32_t P = 0; ok && P < 2 * k - 1; P++) {
+            host::gaussian_poly(c->key, P, c->cdf, q, n, tmp.data());
+            u64* dst = P < k - 1 ? c->d_zh + (size_t)P * n : d_F + (size_t)(P - (k - 1)) * n;
+            ok = cuda_ok(cudaMemcpy(dst, tmp.data(), poly, cudaMemcpyHostToDevice), "upload trapdoor");
+        }
+        std::fill(tmp.begin(), tmp.end(), 0);   // host copy of secret material
+    }
+    cudaStream_t s = c->ntt->stream;
+    if (ok && k > 1) ok = ntt_forward_launch(c->ntt, c->d_zh, k - 1, s);
+    if (ok) ok = ntt_forward_launch(c->ntt, d_F, k, s);
+    if (ok) {
+        trapdoor_row_kernel<<<grid_for((size_t)k * n, 256), 256, 0, s>>>(c->ntt->mp, n, k, c->d_zh, d_F, c->d_A);
+        ok = cuda_ok(cudaGetLastError(), "trapdoor_row_kernel") && fused_prepare(c, s) &&
+             cuda_ok(cudaStreamSynchronize(s), "context setup");
+    }
+    if (d_F) { cudaMemset(d_F, 0, poly * k); cudaFree(d_F); }
+    if (!ok) { lwe_destroy(c); return nullptr; }
+    return c;
+}
+
+void lwe_destroy(LweContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    // commitment.h:34 promises zeroisation of sensitive data
+    if (c->d_zh) { cudaMemset(c->d_zh, 0, (size_t)std::max<uint32_t>(c->k - 1, 1) * c->n * sizeof(u64)); cudaFree(c->d_zh); }
+    if (c->d_A) cudaFree(c->d_A);
+    if (c->d_A2) cudaFree(c->d_A2);
+    if (c->d_cdf) cudaFree(c->d_cdf);
+    for (auto& s : c->scratch) s.release();
+    ntt_destroy(c->ntt);
+    volatile uint32_t* kp = c->key;
+    for (int i = 0; i < 8; i++) kp[i] = 0;
+    delete c;
+}
+
+// ------------------------------------------------------------------- generic
+static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
+                                  const u64* d_seeds, size_t count, u64* d_out, cudaStream_t s) {
+    const uint32_t n = c->n, k = c->k;
+    const size_t words = lwe_words(c);
+    const size_t L = std::min<size_t>(msg_len, n);
+    // scratch S: chunk so it stays <= 1 GiB
+    const size_t per = (size_t)k * n * sizeof(u64);
+    const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)1 << 30) / per));
+    if (!c->scratch[0].reserve(chunk * per)) return false;
+    u64* S = static_cast<u64*>(c->scratch[0].ptr);
+    const ChaChaKey key = make_key(c);
+    for (size_t done = 0; done < count; done += chunk) {
+        const size_t cnt = std::min(chunk, count - done);
+        u64* out = d_out + done * words;
+        sample_se_kernel<<<grid_for(cnt * (n >> 4), 128), 128, 0, s>>>(key, c->d_cdf, (u32)c->cdf.size(), c->q, n, k,
+                                                                      d_seeds + done, cnt, S, out, words);
+        if (!cuda_ok(cudaGetLastError(), "sample_se_kernel")) return false;
+        if (!ntt_forward_launch(c->ntt, S, cnt * k, s)) return false;
+        matvec_kernel<16><<<grid_for(cnt * n, 256), 256, 0, s>>>(c->ntt->mp, c->d_A, n, k, cnt, S);
+        if (!cuda_ok(cudaGetLastError(), "matvec_kernel")) return false;
+        if (!ntt_inverse_launch(c->ntt, S, cnt * k, s)) return false;
+        // messages are addressed with their true stride msg_len; only the first L words are used
+        finalize_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->ntt->mp, c->delta, c->p, n, k, S,
+                                                                  d_msgs + done * msg_len, msg_len, cnt, out, words);
+        if (!cuda_ok(cudaGetLastError(), "finalize_kernel")) return false;
+        (void)L;
+    }
+    return true;
+}
+
+bool lwe_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
+                       size_t count, u64* d_out, cudaStream_t stream) {
+    if (count == 0) return true;
+    const bool fused_ok = fused_commit_supported(c);
+    if (c->commit_path == 2 && !fused_ok) { set_error("fused commit path does not support this context"); return false; }
+    if (fused_ok && c->commit_path != 1) return fused_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream);
+    return generic_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream);
+}
+
+// Host path: chunks alternate between two streams (H2D msgs+seeds -> kernels ->
+// D2H commitments).  The generic path's S scratch is shared, so with the
+// generic path the two streams are serialised through one stream instead.
+bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const u64* seeds,
+                     size_t count, u64* out) {
+    if (count == 0) return true;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t words = lwe_words(c);
+    const size_t eff_len = std::max<size_t>(msg_len, 1);
+    const size_t chunk = std::min<size_t>(count, 512);
+    const bool fused = fused_commit_supported(c) && c->commit_path != 1;
+    const int nbuf = (fused && count > chunk) ? 2 : 1;
+    for (int b = 0; b < nbuf; b++) {
+        if (!c->scratch[1 + 3 * b].reserve(chunk * eff_len * sizeof(u64))) return false;
+        if (!c->scratch[2 + 3 * b].reserve(chunk * sizeof(u64))) return false;
+        if (!c->scratch[3 + 3 * b].reserve(chunk * words * sizeof(u64))) return false;
+    }
+    bool ok = true;
+    int b = 0;
+    for (size_t done = 0; ok && done < count; done += chunk) {
+        const size_t cnt = std::min(chunk, count - done);
+        cudaStream_t s = nbuf == 1 ? c->ntt->stream : c->ntt->copy_streams[b];
+        u64* dm = static_cast<u64*>(c->scratch[1 + 3 * b].ptr);
+        u64* ds = static_cast<u64*>(c->scratch[2 + 3 * b].ptr);
+        u64* dout = static_cast<u64*>(c->scratch[3 + 3 * b].ptr);
+        if (msg_len) ok = cuda_ok(cudaMemcpyAsync(dm, msgs + done * msg_len, cnt * msg_len * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D msgs");
+        ok = ok && cuda_ok(cudaMemcpyAsync(ds, seeds + done, cnt * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D seeds") &&
+             lwe_commit_launch(c, dm, msg_len, ds, cnt, dout, s) &&
+             cuda_ok(cudaMemcpyAsync(out + done * words, dout, cnt * words * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H");
+        if (nbuf == 2) b ^= 1;
+    }
+    if (nbuf == 1) ok = cuda_ok(cudaStreamSynchronize(c->ntt->stream), "sync") && ok;
+    else for (int i = 0; i < 2; i++) ok = cuda_ok(cudaStreamSynchronize(c->ntt->copy_streams[i]), "sync") && ok;
+    return ok;
+}
+
+bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs, size_t msg_len,
+                     size_t count, int* results) {
+    if (count == 0) return true;
+    const uint32_t n = c->n, k = c->k;
+    if (msg_len > n) {                       // commitment.cpp:219-221: decoded.size() < msg_len -> 0
+        for (size_t i = 0; i < count; i++) results[i] = 0;
+        // (container errors still win, as load() precedes decode in the reference)
+    }
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t words = lwe_words(c);
+    const size_t cmp_len = std::min<size_t>(msg_len, n);
+    const size_t chunk = std::min<size_t>(count, 1024);
+    cudaStream_t s = c->ntt->stream;
+    if (!c->scratch[0].reserve(chunk * words * sizeof(u64))) return false;                       // containers
+    if (!c->scratch[1].reserve(chunk * std::max<size_t>(cmp_len, 1) * sizeof(u64))) return false; // messages
+    if (!c->scratch[2].reserve(chunk * std::max<uint32_t>(k - 1, 1) * (size_t)n * sizeof(u64))) return false;  // T
+    if (!c->scratch[3].reserve(chunk * (size_t)n * sizeof(u64))) return false;                    // U
+    if (!c->scratch[4].reserve(chunk * (sizeof(int) + sizeof(unsigned long long)))) return false; // flags
+    u64* d_comm = static_cast<u64*>(c->scratch[0].ptr);
+    u64* d_msg = static_cast<u64*>(c->scratch[1].ptr);
+    u64* d_T = static_cast<u64*>(c->scratch[2].ptr);
+    u64* d_U = static_cast<u64*>(c->scratch[3].ptr);
+    unsigned long long* d_diff = static_cast<unsigned long long*>(c->scratch[4].ptr);
+    int* d_inv = reinterpret_cast<int*>(d_diff + chunk);
+    std::vector<unsigned long long> h_diff(chunk);
+    std::vector<int> h_inv(chunk);
+    std::vector<u64> packed;
+    bool ok = true;
+    for (size_t done = 0; ok && done < count; done += chunk) {
+        const size_t cnt = std::min(chunk, count - done);
+        ok = cuda_ok(cudaMemcpyAsync(d_comm, comm_words + done * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D comm") &&
+             cuda_ok(cudaMemsetAsync(d_diff, 0, chunk * (sizeof(int) + sizeof(unsigned long long)), s), "memset");
+        if (ok && cmp_len) {
+            // compare only the first cmp_len words of each message (stride msg_len on the host)
+            const u64* src = msgs + done * msg_len;
+            if (cmp_len != msg_len) {
+                packed.resize(cnt * cmp_len);
+                for (size_t i = 0; i < cnt; i++) std::memcpy(&packed[i * cmp_len], src + i * msg_len, cmp_len * sizeof(u64));
+                src = packed.data();
+            }
+            ok = cuda_ok(cudaMemcpyAsync(d_msg, src, cnt * cmp_len * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D msgs");
+        }
+        if (!ok) break;
+        verify_prepare_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->q, n, k, d_comm, words, cnt, d_T, d_inv);
+        ok = cuda_ok(cudaGetLastError(), "verify_prepare_kernel");
+        if (ok && k > 1) ok = ntt_forward_launch(c->ntt, d_T, cnt * (k - 1), s);
+        if (ok) {
+            verify_dot_kernel<<<grid_for(cnt * n, 256), 256, 0, s>>>(c->ntt->mp, n, k, c->d_zh, d_T, cnt, d_U);
+            ok = cuda_ok(cudaGetLastError(), "verify_dot_kernel");
+        }
+        if (ok && k > 1) ok = ntt_inverse_launch(c->ntt, d_U, cnt, s);
+        if (ok && cmp_len) {
+            verify_decode_kernel<<<grid_for(cnt * cmp_len, 256), 256, 0, s>>>(c->q, c->delta, c->p, n, k, d_U, d_comm, words,
+                                                                            d_msg, cmp_len, cnt, d_diff);
+            ok = cuda_ok(cudaGetLastError(), "verify_decode_kernel");
+        }
+        ok = ok && cuda_ok(cudaMemcpyAsync(h_diff.data(), d_diff, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "D2H") &&
+             cuda_ok(cudaMemcpyAsync(h_inv.data(), d_inv, cnt * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(s), "sync");
+        if (!ok) break;
+        for (size_t i = 0; i < cnt; i++) {
+            if (h_inv[i]) results[done + i] = -1;
+            else if (msg_len > n) results[done + i] = 0;
+            else results[done + i] = h_diff[i] == 0 ? 1 : 0;
+        }
+    }
+    return ok;
+}
+
+bool lwe_lincomb_host(const LweContext* c, const u64* payloads, const u64* coeffs, size_t count,
+                      u64* out_payload) {
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t kn = (size_t)c->k * c->n;
+    cudaStream_t s = c->ntt->stream;
+    if (!c->scratch[0].reserve(count * kn * sizeof(u64))) return false;
+    if (!c->scratch[1].reserve(count * sizeof(u64))) return false;
+    if (!c->scratch[2].reserve(kn * sizeof(u64))) return false;
+    u64* d_p = static_cast<u64*>(c->scratch[0].ptr);
+    u64* d_c = static_cast<u64*>(c->scratch[1].ptr);
+    u64* d_o = static_cast<u64*>(c->scratch[2].ptr);
+    bool ok = cuda_ok(cudaMemcpyAsync(d_p, payloads, count * kn * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D") &&
+              cuda_ok(cudaMemcpyAsync(d_c, coeffs, count * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D");
+    if (ok) {
+        lincomb_kernel<<<grid_for(kn, 256), 256, 0, s>>>(c->ntt->mp, c->p, kn, d_p, d_c, count, d_o);
+        ok = cuda_ok(cudaGetLastError(), "lincomb_kernel");
+    }
+    return ok && cuda_ok(cudaMemcpyAsync(out_payload, d_o, kn * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H") &&
+           cuda_ok(cudaStreamSynchronize(s), "sync");
+}
+
+// test hook: s, e of one commitment through the generic sampler kernel
+bool lwe_sample_se_host(const LweContext* c, u64 seed, int64_t* s_out, int64_t* e_out) {
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const uint32_t n = c->n, k = c->k;
+    const size_t kn = (size_t)k * n, words = 1 + kn;
+    cudaStream_t st = c->ntt->stream;
+    if (!c->scratch[0].reserve(kn * sizeof(u64))) return false;
+    if (!c->scratch[1].reserve(words * sizeof(u64))) return false;
+    if (!c->scratch[2].reserve(sizeof(u64))) return false;
+    u64* S = static_cast<u64*>(c->scratch[0].ptr);
+    u64* O = static_cast<u64*>(c->scratch[1].ptr);
+    u64* dseed = static_cast<u64*>(c->scratch[2].ptr);
+    bool ok = cuda_ok(cudaMemcpyAsync(dseed, &seed, sizeof(u64), cudaMemcpyHostToDevice, st), "H2D");
+    if (!ok) return false;
+    sample_se_kernel<<<grid_for(n >> 4, 128), 128, 0, st>>>(make_key(c), c->d_cdf, (u32)c->cdf.size(), c->q, n, k, dseed, 1, S, O, words);
+    std::vector<u64> hs(kn), he(kn);
+    ok = cuda_ok(cudaGetLastError(), "sample_se_kernel") &&
+         cuda_ok(cudaMemcpyAsync(hs.data(), S, kn * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H") &&
+         cuda_ok(cudaMemcpyAsync(he.data(), O + 1, kn * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H") &&
+         cuda_ok(cudaStreamSynchronize(st), "sync");
+    if (!ok) return false;
+    const u64 half = c->q / 2;
+    for (size_t i = 0; i < kn; i++) {
+        s_out[i] = hs[i] > half ? -(int64_t)(c->q - hs[i]) : (int64_t)hs[i];
+        e_out[i] = he[i] > half ? -(int64_t)(c->q - he[i]) : (int64_t)he[i];
+    }
+    return true;
+}
+
+bool sample_gaussian_host(u64* out, size_t len, double sigma, const uint8_t seed32[32]) {
+    std::vector<u64> cdf = host::build_cdt(sigma);
+    if (cdf.empty()) return false;
+    if (!cuda_ok(cudaSetDevice(current_device_choice()), "cudaSetDevice")) return false;
+    ChaChaKey key;
+    host::load_key(seed32, key.k);
+    u64 *d_cdf = nullptr, *d_out = nullptr;
+    cudaStream_t s = nullptr;
+    bool ok = cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate") &&
+              cuda_ok(cudaMalloc(&d_cdf, cdf.size() * sizeof(u64)), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&d_out, len * sizeof(u64)), "cudaMalloc") &&
+              cuda_ok(cudaMemcpyAsync(d_cdf, cdf.data(), cdf.size() * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D");
+    if (ok) {
+        sample_gaussian_kernel<<<grid_for((len + 3) / 4, 128), 128, 0, s>>>(key, d_cdf, (u32)cdf.size(), len, d_out);
+        ok = cuda_ok(cudaGetLastError(), "sample_gaussian_kernel") &&
+             cuda_ok(cudaMemcpyAsync(out, d_out, len * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(s), "sync");
+    }
+    if (d_cdf) cudaFree(d_cdf);
+    if (d_out) { cudaMemsetAsync(d_out, 0, len * sizeof(u64), s); cudaStreamSynchronize(s); cudaFree(d_out); }
+    if (s) cudaStreamDestroy(s);
+    for (int i = 0; i < 8; i++) key.k[i] = 0;
+    return ok;
+}
+
+}  // namespace lsr

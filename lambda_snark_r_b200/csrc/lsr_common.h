@@ -1,0 +1,57 @@
+// lsr_common.h -- types shared by the host runtime and the sm_100a kernels.
+//
+// Everything the kernels need about a modulus or an NTT table travels BY VALUE
+// in these structs (kernel parameters live in the constant bank, so q, 2^64-q,
+// the Barrett ratio etc. are uniform constant operands, not loads).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include <vector_types.h>   // ulonglong2 (CUDA toolkit header, host-safe)
+
+namespace lsr {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u64 kDefaultModulusSmall = 17592169062401ULL;  // reference r1cs.rs:527, 2-adicity 13
+constexpr u64 kDefaultModulusLarge = 17592180539393ULL;  // 44-bit, 2-adicity 18
+constexpr int kMaxLogN = 17;                              // SEAL_POLY_MOD_DEGREE_MAX = 131072
+constexpr int kChaChaRounds = 8;
+
+constexpr u32 kDomMatrix = 0x01000000u;
+constexpr u32 kDomTrap   = 0x02000000u;
+constexpr u32 kDomCommit = 0x03000000u;
+constexpr u32 kDomSample = 0x05000000u;
+
+// Modulus constants.  "lazy" policies: butterflies carry unreduced values and
+// only the last stage reduces; valid while the worst-case growth fits in 63
+// bits.  Otherwise the SEAL-style guarded Harvey
+// butterfly ([0,4q) forward, [0,2q) inverse) is used.
+struct ModParams {
+    u64 q;
+    u64 nq;        // 2^64 - q
+    u64 q2;        // 2q
+    u64 q4;        // 4q
+    u64 bar_lo;    // floor(2^128 / q), low word
+    u64 bar_hi;    //                   high word
+    u32 red_sh;    // reduce_small(v): est = umulhi32(v >> red_sh, red_c), v < 2^7 q
+    u32 red_c;
+    u32 lazy_fwd;  // (4 + 4 logn) q < 2^63
+    u32 lazy_inv;  // 2^(logn+2) q < 2^63
+};
+
+// Device twiddle tables, both indexed [m + group] for the stage with m groups
+// (m = 1, 2, 4, ..., n/2): .x = w, .y = floor(w * 2^64 / q).
+//   fwd[m + g] = SEAL root_powers[m + g]          = psi^brv(m + g)
+//   inv[m + g] = SEAL inv_root_powers[n - 2m + 1 + g]  (SEAL consumes them
+//                sequentially from index 1; re-indexed so both directions
+//                address twiddles the same way); inv[1] is pre-multiplied by
+//                n^-1 (SEAL folds the scalar into the last stage the same way)
+struct NttTables {
+    const ulonglong2* fwd;
+    const ulonglong2* inv;
+    ulonglong2 n_inv;   // (n^-1, shoup)
+};
+
+}  // namespace lsr

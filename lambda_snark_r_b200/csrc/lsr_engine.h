@@ -1,0 +1,112 @@
+// lsr_engine.h -- host runtime objects behind the C ABI (NttContext, LweContext)
+// and the launchers of the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "lsr_common.h"
+#include "lsr_host.h"
+
+namespace lsr {
+
+// thread-local diagnostic (lsr_last_error)
+void set_error(const std::string& msg);
+const char* last_error();
+bool cuda_ok(cudaError_t e, const char* what);
+int current_device_choice();          // device chosen by lsr_set_device on this thread (default 0)
+void set_device_choice(int dev);
+
+// RAII device buffer that only grows
+struct DeviceScratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool reserve(size_t need);
+    void release();
+};
+
+struct PinnedScratch {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool reserve(size_t need);
+    void release();
+};
+
+}  // namespace lsr
+
+// The opaque handle of ntt.h:24 (reference layout: cpp-core/src/ntt.cpp:21-26)
+struct NttContext {
+    lsr::u64 modulus = 0;
+    uint32_t degree = 0;
+    uint32_t logn = 0;
+    lsr::u64 psi = 0;
+    int device = 0;
+    lsr::ModParams mp{};
+    lsr::NttTables tables{};          // device pointers
+    ulonglong2* d_fwd = nullptr;
+    ulonglong2* d_inv = nullptr;
+    cudaStream_t stream = nullptr;    // used by the host-pointer entry points
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
+    mutable std::mutex mu;            // serialises use of the scratch buffers
+    mutable lsr::DeviceScratch scratch[3];
+};
+
+// The opaque handle of types.h:27 (reference layout: cpp-core/src/commitment.cpp:31-40).
+// Holds the Module-LWE public matrix A-hat (NTT domain), the trapdoor z-hat
+// that plays the role of the reference's SEAL secret key in
+// lwe_verify_opening, the CDT, and the PRF key of the commitment randomness.
+struct LweContext {
+    lsr::u64 q = 0, p = 0, delta = 0;
+    uint32_t n = 0, k = 0, logn = 0;
+    double sigma = 0.0;
+    int device = 0;
+    uint32_t key[8] = {0};
+    std::vector<lsr::u64> cdf;        // host copy (full table)
+    NttContext* ntt = nullptr;        // owned
+    lsr::u64* d_A = nullptr;          // [k][k][n] residues, NTT domain
+    ulonglong2* d_A2 = nullptr;       // same with Shoup quotients, fused-kernel layout
+    lsr::u64* d_zh = nullptr;         // [k-1][n]
+    lsr::u64* d_cdf = nullptr;        // [cdf.size()]
+    int commit_path = 0;              // 0 auto, 1 generic, 2 fused
+    mutable std::mutex mu;
+    mutable lsr::DeviceScratch scratch[8];
+};
+
+namespace lsr {
+
+LweContext* lwe_create(u64 modulus_req, uint32_t n, uint32_t k, double sigma, const uint8_t seed32[32]);
+void lwe_destroy(LweContext* ctx);
+size_t lwe_words(const LweContext* ctx);
+
+// device-pointer commit: msgs [count][msg_len], seeds [count], out [count][1+k*n]
+bool lwe_commit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
+                       size_t count, u64* d_out, cudaStream_t stream);
+bool lwe_commit_host(const LweContext* ctx, const u64* msgs, size_t msg_len, const u64* seeds,
+                     size_t count, u64* out);
+// results[i] in {1,0,-1}
+bool lwe_verify_host(const LweContext* ctx, const u64* comm_words, const u64* msgs, size_t msg_len,
+                     size_t count, int* results);
+// payloads: [count][k*n] host words (already validated), coeffs [count]; out payload [k*n]
+bool lwe_lincomb_host(const LweContext* ctx, const u64* payloads, const u64* coeffs, size_t count,
+                      u64* out_payload);
+bool lwe_sample_se_host(const LweContext* ctx, u64 seed, int64_t* s, int64_t* e);
+bool sample_gaussian_host(u64* out, size_t len, double sigma, const uint8_t seed32[32]);
+bool fused_commit_supported(const LweContext* ctx);
+
+NttContext* ntt_create(u64 q, uint32_t n);
+void ntt_destroy(NttContext* ctx);
+
+// asynchronous launches on `stream`; data on the context's device
+bool ntt_forward_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
+bool ntt_inverse_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
+bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64* d_b, size_t total,
+                      cudaStream_t stream);
+
+// host-pointer paths (H2D, kernel, D2H, synchronised), chunked + double buffered
+bool ntt_transform_host(const NttContext* ctx, u64* host, size_t batch, bool inverse);
+bool pointwise_host(const NttContext* ctx, u64* r, const u64* a, const u64* b, size_t total);
+
+}  // namespace lsr

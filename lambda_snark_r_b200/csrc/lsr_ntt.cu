@@ -1,0 +1,244 @@
+// lsr_ntt.cu -- NttContext life cycle, kernel instantiation and launchers for
+// K1 (forward), K2 (inverse), K3 (pointwise).  Replaces the SEAL calls of the
+// reference's cpp-core/src/ntt.cpp.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "lsr_engine.h"
+#include "lsr_ntt.cuh"
+
+namespace lsr {
+
+// ------------------------------------------------------------------ utilities
+static thread_local std::string g_error;
+static thread_local int g_device_choice = 0;
+
+void set_error(const std::string& msg) { g_error = msg; }
+const char* last_error() { return g_error.c_str(); }
+int current_device_choice() { return g_device_choice; }
+void set_device_choice(int dev) { g_device_choice = dev; }
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    set_error(msg);
+    std::fprintf(stderr, "lambda_snark_b200: %s\n", msg.c_str());   // reference logs to stderr too
+    return false;
+}
+
+bool DeviceScratch::reserve(size_t need) {
+    if (need <= bytes) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+    if (!cuda_ok(cudaMalloc(&ptr, need), "cudaMalloc(scratch)")) { ptr = nullptr; return false; }
+    bytes = need;
+    return true;
+}
+void DeviceScratch::release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; bytes = 0;
+}
+bool PinnedScratch::reserve(size_t need) {
+    if (need <= bytes) return true;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; bytes = 0;
+    if (!cuda_ok(cudaMallocHost(&ptr, need), "cudaMallocHost")) { ptr = nullptr; return false; }
+    bytes = need;
+    return true;
+}
+void PinnedScratch::release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; bytes = 0;
+}
+
+// ------------------------------------------------------------------- launches
+template <typename K>
+static bool ensure_smem(K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return true;
+    return cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                   "cudaFuncSetAttribute(smem)");
+}
+
+template <int LOGN, int LT, bool INV>
+static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s) {
+    constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
+    const size_t smem = sizeof(u64) << TL;
+    const size_t tiles = (total + ((size_t)1 << TL) - 1) >> TL;
+    if (tiles == 0) return true;
+    if (tiles > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    const bool lazy = INV ? c->mp.lazy_inv : c->mp.lazy_fwd;
+    if (lazy) {
+        auto k = ntt_tile_kernel<LOGN, LT, true, INV>;
+        if (!ensure_smem(k, smem)) return false;
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+    } else {
+        auto k = ntt_tile_kernel<LOGN, LT, false, INV>;
+        if (!ensure_smem(k, smem)) return false;
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+    }
+    return cuda_ok(cudaGetLastError(), "ntt_tile_kernel launch");
+}
+
+template <int LOGN, int S, bool INV>
+static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    const size_t cols = batch << (LOGN - S);
+    const size_t blocks = (cols + kNttThreads - 1) / kNttThreads;
+    if (blocks == 0) return true;
+    if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    const bool lazy = INV ? c->mp.lazy_inv : c->mp.lazy_fwd;
+    if (lazy) ntt_column_kernel<LOGN, S, true, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    else      ntt_column_kernel<LOGN, S, false, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
+}
+
+// n <= 2^14: one kernel, the polynomial never leaves shared memory.
+// n >  2^14: column kernel (first LOGN-12 stages) + tile kernel on 4096-blocks.
+template <int LOGN, bool INV>
+static bool launch_transform(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    const size_t total = batch << LOGN;
+    if constexpr (LOGN <= 14) {
+        return launch_tile<LOGN, LOGN, INV>(c, d, total, s);
+    } else {
+        constexpr int S = LOGN - 12;
+        if (!INV) return launch_column<LOGN, S, false>(c, d, batch, s) && launch_tile<LOGN, 12, false>(c, d, total, s);
+        return launch_tile<LOGN, 12, true>(c, d, total, s) && launch_column<LOGN, S, true>(c, d, batch, s);
+    }
+}
+
+template <bool INV>
+static bool dispatch(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    switch (c->logn) {
+        case 1: return launch_transform<1, INV>(c, d, batch, s);
+        case 2: return launch_transform<2, INV>(c, d, batch, s);
+        case 3: return launch_transform<3, INV>(c, d, batch, s);
+        case 4: return launch_transform<4, INV>(c, d, batch, s);
+        case 5: return launch_transform<5, INV>(c, d, batch, s);
+        case 6: return launch_transform<6, INV>(c, d, batch, s);
+        case 7: return launch_transform<7, INV>(c, d, batch, s);
+        case 8: return launch_transform<8, INV>(c, d, batch, s);
+        case 9: return launch_transform<9, INV>(c, d, batch, s);
+        case 10: return launch_transform<10, INV>(c, d, batch, s);
+        case 11: return launch_transform<11, INV>(c, d, batch, s);
+        case 12: return launch_transform<12, INV>(c, d, batch, s);
+        case 13: return launch_transform<13, INV>(c, d, batch, s);
+        case 14: return launch_transform<14, INV>(c, d, batch, s);
+        case 15: return launch_transform<15, INV>(c, d, batch, s);
+        case 16: return launch_transform<16, INV>(c, d, batch, s);
+        case 17: return launch_transform<17, INV>(c, d, batch, s);
+        default: set_error("unsupported ring degree"); return false;
+    }
+}
+
+bool ntt_forward_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream) {
+    return dispatch<false>(ctx, d_data, batch, stream);
+}
+bool ntt_inverse_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream) {
+    return dispatch<true>(ctx, d_data, batch, stream);
+}
+
+bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64* d_b, size_t total,
+                      cudaStream_t stream) {
+    if (total == 0) return true;
+    size_t blocks = (total / 2 + 255) / 256;
+    blocks = std::max<size_t>(1, std::min<size_t>(blocks, 148 * 16));   // grid-stride, multiple of the SM count
+    pointwise_mul_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ctx->mp, d_r, d_a, d_b, total);
+    return cuda_ok(cudaGetLastError(), "pointwise_mul_kernel launch");
+}
+
+// ------------------------------------------------------------------ life cycle
+NttContext* ntt_create(u64 q, uint32_t n) {
+    host::NttHostTables ht;
+    if (!host::build_ntt_tables(q, n, ht)) {
+        set_error("ntt_context_create: invalid (q, n)");
+        return nullptr;
+    }
+    const int dev = current_device_choice();
+    if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
+    NttContext* c = new (std::nothrow) NttContext;
+    if (!c) return nullptr;
+    c->modulus = q; c->degree = n; c->logn = ht.logn; c->psi = ht.psi; c->device = dev;
+    c->mp = host::make_mod_params(q, ht.logn);
+    const size_t bytes = sizeof(ulonglong2) * n;
+    bool ok = cuda_ok(cudaMalloc(&c->d_fwd, bytes), "cudaMalloc(twiddles)") &&
+              cuda_ok(cudaMalloc(&c->d_inv, bytes), "cudaMalloc(twiddles)") &&
+              cuda_ok(cudaMemcpy(c->d_fwd, ht.fwd.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles") &&
+              cuda_ok(cudaMemcpy(c->d_inv, ht.inv.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles") &&
+              cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; ok && i < 2; ++i)
+        ok = cuda_ok(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!ok) { ntt_destroy(c); return nullptr; }
+    c->tables.fwd = c->d_fwd;
+    c->tables.inv = c->d_inv;
+    c->tables.n_inv = ht.n_inv;
+    return c;
+}
+
+void ntt_destroy(NttContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (auto& s : c->scratch) s.release();
+    if (c->d_fwd) cudaFree(c->d_fwd);
+    if (c->d_inv) cudaFree(c->d_inv);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (auto& s : c->copy_streams) if (s) cudaStreamDestroy(s);
+    delete c;
+}
+
+// ---------------------------------------------------------------- host paths
+// Chunks of <= 32 MiB alternate between two streams, each running
+// H2D -> kernel -> D2H in order, so copies of one chunk overlap the kernel of
+// the other (fully so when the caller's memory is page-locked).
+bool ntt_transform_host(const NttContext* c, u64* host, size_t batch, bool inverse) {
+    if (batch == 0) return true;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t n = c->degree;
+    const size_t poly_bytes = n * sizeof(u64);
+    size_t chunk = std::max<size_t>(1, ((size_t)32 << 20) / poly_bytes);
+    chunk = std::min(chunk, batch);
+    const int nbuf = batch > chunk ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b)
+        if (!c->scratch[b].reserve(chunk * poly_bytes)) return false;
+    size_t done = 0;
+    int b = 0;
+    bool ok = true;
+    while (ok && done < batch) {
+        const size_t cnt = std::min(chunk, batch - done);
+        cudaStream_t s = nbuf == 1 ? c->stream : c->copy_streams[b];
+        u64* d = static_cast<u64*>(c->scratch[b].ptr);
+        u64* h = host + done * n;
+        ok = cuda_ok(cudaMemcpyAsync(d, h, cnt * poly_bytes, cudaMemcpyHostToDevice, s), "H2D") &&
+             (inverse ? ntt_inverse_launch(c, d, cnt, s) : ntt_forward_launch(c, d, cnt, s)) &&
+             cuda_ok(cudaMemcpyAsync(h, d, cnt * poly_bytes, cudaMemcpyDeviceToHost, s), "D2H");
+        done += cnt;
+        b ^= 1;
+    }
+    if (nbuf == 1) ok = cuda_ok(cudaStreamSynchronize(c->stream), "sync") && ok;
+    else for (int i = 0; i < 2; ++i) ok = cuda_ok(cudaStreamSynchronize(c->copy_streams[i]), "sync") && ok;
+    return ok;
+}
+
+bool pointwise_host(const NttContext* c, u64* r, const u64* a, const u64* b, size_t total) {
+    if (total == 0) return true;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t chunk = std::min<size_t>(total, (size_t)4 << 20);   // 32 MiB per operand
+    for (int i = 0; i < 2; ++i)
+        if (!c->scratch[i].reserve(chunk * sizeof(u64))) return false;
+    u64* da = static_cast<u64*>(c->scratch[0].ptr);
+    u64* db = static_cast<u64*>(c->scratch[1].ptr);
+    cudaStream_t s = c->stream;
+    bool ok = true;
+    for (size_t done = 0; ok && done < total; done += chunk) {
+        const size_t cnt = std::min(chunk, total - done);
+        ok = cuda_ok(cudaMemcpyAsync(da, a + done, cnt * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D") &&
+             cuda_ok(cudaMemcpyAsync(db, b + done, cnt * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D") &&
+             pointwise_launch(c, da, da, db, cnt, s) &&
+             cuda_ok(cudaMemcpyAsync(r + done, da, cnt * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(s), "sync");
+    }
+    return ok;
+}
+
+}  // namespace lsr

@@ -1,0 +1,84 @@
+// lsr_sampler.cuh -- device side of K7: ChaCha keystream + CDT discrete Gaussian.
+//
+// Replaces the reference's sample_gaussian / sample_single
+// (cpp-core/src/utils.cpp:95-146).  The CDT itself is built on the host with
+// the reference's long-double code (lsr_host.cpp build_cdt) and only evaluated
+// here.  Entropy: std::random_device (utils.cpp:138) becomes a keyed ChaCha
+// stream so CPU oracle and GPU agree bit for bit and results do not depend on
+// how a batch is sharded.
+//
+// Constant time: like the reference's linear scan, the sample is computed as
+// the COUNT of table entries below u (the table is non-decreasing and ends at
+// 2^64-1, so the count equals the reference's "first k with cdf[k] >= u"), with
+// no data-dependent branch or address.
+#pragma once
+#include "lsr_common.h"
+
+namespace lsr {
+
+__device__ __forceinline__ u32 rotl32(u32 v, int c) { return __funnelshift_l(v, v, c); }
+
+#define LSR_QR(a, b, c, d)                       \
+    a += b; d ^= a; d = rotl32(d, 16);           \
+    c += d; b ^= c; b = rotl32(b, 12);           \
+    a += b; d ^= a; d = rotl32(d, 8);            \
+    c += d; b ^= c; b = rotl32(b, 7);
+
+struct ChaChaKey { u32 k[8]; };
+
+// one ChaCha block, kChaChaRounds rounds, output x[16]
+__device__ __forceinline__ void chacha_block(const ChaChaKey& key, u32 w12, u32 w13, u32 w14,
+                                             u32 w15, u32 (&x)[16]) {
+    x[0] = 0x61707865u; x[1] = 0x3320646eu; x[2] = 0x79622d32u; x[3] = 0x6b206574u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[4 + i] = key.k[i];
+    x[12] = w12; x[13] = w13; x[14] = w14; x[15] = w15;
+#pragma unroll
+    for (int r = 0; r < kChaChaRounds; r += 2) {
+        LSR_QR(x[0], x[4], x[8], x[12])  LSR_QR(x[1], x[5], x[9], x[13])
+        LSR_QR(x[2], x[6], x[10], x[14]) LSR_QR(x[3], x[7], x[11], x[15])
+        LSR_QR(x[0], x[5], x[10], x[15]) LSR_QR(x[1], x[6], x[11], x[12])
+        LSR_QR(x[2], x[7], x[8], x[13])  LSR_QR(x[3], x[4], x[9], x[14])
+    }
+    x[0] += 0x61707865u; x[1] += 0x3320646eu; x[2] += 0x79622d32u; x[3] += 0x6b206574u;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[4 + i] += key.k[i];
+    x[12] += w12; x[13] += w13; x[14] += w14; x[15] += w15;
+}
+
+// CDT table passed by value: lives in the kernel-parameter constant bank, so
+// with the loops unrolled every entry is an immediate constant operand.
+constexpr int kCdtInline = 64;
+struct CdtParam {
+    u32 count;                 // entries in use (<= kCdtInline); trailing 2^64-1 entries trimmed
+    u32 pad;
+    u64 cdf[kCdtInline];       // unused entries = 2^64-1 (never "below u")
+};
+
+// magnitude = #{k : cdf[k] < u}; NCH8 = ceil(count / 8)
+template <int NCH8>
+__device__ __forceinline__ u32 cdt_magnitude(const CdtParam& t, u64 u) {
+    u32 below = 0;
+#pragma unroll
+    for (int k = 0; k < NCH8 * 8; k++) below += (u32)(t.cdf[k] < u);
+    return below;
+}
+
+// table in global memory, any size
+__device__ __forceinline__ u32 cdt_magnitude_global(const u64* __restrict__ cdf, u32 count, u64 u) {
+    u32 below = 0;
+    for (u32 k = 0; k < count; k++) below += (u32)(__ldg(cdf + k) < u);
+    return below;
+}
+
+// signed sample as a residue mod q: sign applies only when magnitude != 0
+__device__ __forceinline__ u64 signed_residue(u32 mag, u32 sign_bit, u64 q) {
+    const u64 neg = q - (u64)mag;
+    return (sign_bit & (u32)(mag != 0)) ? neg : (u64)mag;
+}
+__device__ __forceinline__ long long signed_value(u32 mag, u32 sign_bit) {
+    const long long m = (long long)mag;
+    return (sign_bit & (u32)(mag != 0)) ? -m : m;
+}
+
+}  // namespace lsr

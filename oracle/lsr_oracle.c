@@ -407,6 +407,7 @@ void lsro_chacha_block(const uint32_t key[8], uint32_t w12, uint32_t w13,
 #define DOM_MATRIX 0x01000000u
 #define DOM_TRAP   0x02000000u
 #define DOM_COMMIT 0x03000000u
+#define DOM_SAMPLE 0x05000000u
 
 struct lsro_lwe {
     uint64_t q, p, delta;
@@ -474,6 +475,37 @@ static uint64_t stream_u64(stream_t *s, uint64_t idx) {
     return (uint64_t)s->buf[2 * w] | ((uint64_t)s->buf[2 * w + 1] << 32);
 }
 
+static void load_key(const uint8_t seed32[32], uint32_t key[8]) {
+    for (int i = 0; i < 8; i++) {
+        key[i] = (uint32_t)seed32[4 * i] | ((uint32_t)seed32[4 * i + 1] << 8) |
+                 ((uint32_t)seed32[4 * i + 2] << 16) | ((uint32_t)seed32[4 * i + 3] << 24);
+    }
+}
+
+/* utils.cpp:132-146 with std::random_device replaced by a keyed stream */
+int lsro_sample_gaussian_seeded(uint64_t *out, size_t len, double sigma, const uint8_t seed32[32]) {
+    if (!out || len == 0 || !(sigma > 0.0) || !isfinite(sigma) || !seed32) return -1;
+    uint64_t *cdf = (uint64_t *)malloc(sizeof(uint64_t) * 32768);
+    if (!cdf) return -1;
+    size_t cn = lsro_cdt_build(sigma, cdf, 32768);
+    if (!cn) { free(cdf); return -1; }
+    uint32_t key[8];
+    load_key(seed32, key);
+    uint32_t blk[16];
+    for (size_t i = 0; i < len; i++) {
+        if ((i & 3) == 0) {
+            uint64_t B = i >> 2;
+            lsro_chacha_block(key, (uint32_t)B, (uint32_t)(B >> 32), 0, DOM_SAMPLE, blk);
+        }
+        uint32_t w = (uint32_t)(i & 3) * 4;
+        uint64_t u1 = (uint64_t)blk[w] | ((uint64_t)blk[w + 1] << 32);
+        uint64_t u2 = (uint64_t)blk[w + 2] | ((uint64_t)blk[w + 3] << 32);
+        out[i] = (uint64_t)lsro_cdt_sample(cdf, cn, u1, u2);
+    }
+    free(cdf);
+    return 0;
+}
+
 lsro_lwe *lsro_lwe_create(uint64_t modulus_req, uint32_t n, uint32_t k, double sigma,
                           const uint8_t seed32[32]) {
     if (!seed32) return NULL;
@@ -486,10 +518,7 @@ lsro_lwe *lsro_lwe_create(uint64_t modulus_req, uint32_t n, uint32_t k, double s
     c->q = ntt_friendly(modulus_req, n) ? modulus_req : (n <= 4096 ? LSRO_Q0 : LSRO_Q1);
     c->p = plain_modulus(c->q);
     c->delta = (c->q - 1) / c->p;
-    for (int i = 0; i < 8; i++) {
-        c->key[i] = (uint32_t)seed32[4 * i] | ((uint32_t)seed32[4 * i + 1] << 8) |
-                    ((uint32_t)seed32[4 * i + 2] << 16) | ((uint32_t)seed32[4 * i + 3] << 24);
-    }
+    load_key(seed32, c->key);
     c->ntt = lsro_ntt_create(c->q, n);
     c->cdf = (uint64_t *)malloc(sizeof(uint64_t) * 32768);
     c->cdf_n = c->cdf ? lsro_cdt_build(sigma, c->cdf, 32768) : 0;

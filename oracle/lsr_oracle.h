@@ -72,6 +72,10 @@ size_t  lsro_cdt_build(double sigma, uint64_t *cdf, size_t cap);
 /* utils.cpp:95-121 with the two random_u64 draws supplied by the caller */
 int64_t lsro_cdt_sample(const uint64_t *cdf, size_t count, uint64_t u1, uint64_t u2);
 
+/* deterministic sample_gaussian: sample i uses 64-bit draws (2i, 2i+1) of the
+ * ChaCha stream keyed by seed32 (domain 0x05), 8 draws per block */
+int lsro_sample_gaussian_seeded(uint64_t *out, size_t len, double sigma, const uint8_t seed32[32]);
+
 /* ChaCha block (rounds = LSRO_CHACHA_ROUNDS), RFC 7539 quarter round */
 #define LSRO_CHACHA_ROUNDS 8
 void lsro_chacha_block(const uint32_t key[8], uint32_t w12, uint32_t w13,

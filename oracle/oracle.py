@@ -78,6 +78,8 @@ class _Lib:
         lib.lsro_cdt_build.argtypes = [C.c_double, u64p, C.c_size_t]
         lib.lsro_cdt_sample.restype = C.c_int64
         lib.lsro_cdt_sample.argtypes = [u64p, C.c_size_t, C.c_uint64, C.c_uint64]
+        lib.lsro_sample_gaussian_seeded.restype = C.c_int
+        lib.lsro_sample_gaussian_seeded.argtypes = [u64p, C.c_size_t, C.c_double, C.c_char_p]
         lib.lsro_chacha_block.argtypes = [C.POINTER(C.c_uint32)] + [C.c_uint32] * 4 + [C.POINTER(C.c_uint32)]
         lib.lsro_lwe_create.restype = C.c_void_p
         lib.lsro_lwe_create.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_char_p]
@@ -210,6 +212,14 @@ def cdt_build(sigma: float) -> np.ndarray:
 def cdt_sample(cdf: np.ndarray, u1: int, u2: int) -> int:
     cdf = _np_u64(cdf)
     return int(lib().lib.lsro_cdt_sample(_ptr(cdf), cdf.size, u1, u2))
+
+
+def sample_gaussian_seeded(length: int, sigma: float, seed32: bytes) -> np.ndarray:
+    out = np.zeros(length, dtype=np.uint64)
+    rc = lib().lib.lsro_sample_gaussian_seeded(_ptr(out), length, float(sigma), seed32)
+    if rc != 0:
+        raise ValueError("sample_gaussian -> -1")
+    return out.view(np.int64)
 
 
 def chacha_block(key8, w12: int, w13: int, w14: int, w15: int) -> np.ndarray:
