@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the prover hot path on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  (reference arm: CPU, host cores)
+
+A "step" is one pass of the hot path over one batch of synthetic input: a
+batch of Module-LWE commitments t = A*s + e + Delta*m at n=4096, k=2,
+q=17592169062401, sigma=3.19 (BASELINE.json configs[3]); each commitment runs
+the sampler, k forward NTTs, the k x k NTT-domain mat-vec and k inverse NTTs
+inside ONE fused kernel.  The batched NTT sweep at the same n (configs[2]) is
+reported beside it under "ntt".
+
+value      : commitments/s, whole job, inputs resident in HBM (CUDA events)
+e2e        : same metric through the C ABI's host-pointer call lwe_commit_batch
+             with pinned HOST buffers, copies inside the timed region
+roofline   : dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json),
+             plus the integer-multiply roofline it is actually bound by
+cpu_baseline / --impl reference : the oracle's C port of the same algorithm on
+             the host cores (the reference's SEAL path cannot be built here)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+N_RING, K_RANK, Q_MOD, SIGMA = 4096, 2, 17592169062401, 3.19
+CTX_SEED = bytes(range(32))
+SEED_BASE = 0xC0FFEE
+ALG_BYTES_COMMIT = 8 * N_RING + 8 * K_RANK * N_RING + 8          # message in + container out
+ALG_BYTES_NTT = 16 * N_RING                                       # read + write, in place
+BUTTERFLIES_NTT = (N_RING // 2) * 12
+IMAD_PER_MODMUL = 10                                              # SURVEY 8d normalisation
+MODMUL_COMMIT = 2 * K_RANK * BUTTERFLIES_NTT + K_RANK * (N_RING // 2) + K_RANK * K_RANK * N_RING   # 118784
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_note():
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        return json.loads(p.read_text())
+    return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm
+def cpu_commit_rate(target_s: float, threads: int | None = None):
+    """Oracle C port (kind "port"), all host threads, bounded sample of the same workload."""
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    ctx = O.OracleLwe(Q_MOD, N_RING, K_RANK, SIGMA, CTX_SEED, native=native)
+    threads = threads or O.max_threads()
+    rng = np.random.Generator(np.random.PCG64(0x5EED))
+
+    def run(count):
+        msgs = rng.integers(0, Q_MOD, size=(count, N_RING), dtype=np.uint64)
+        seeds = (np.arange(count, dtype=np.uint64) + np.uint64(SEED_BASE))
+        out = np.zeros((count, ctx.words), dtype=np.uint64)
+        t0 = time.perf_counter()
+        ctx.commit_batch(msgs, seeds, threads=threads, out=out)
+        return time.perf_counter() - t0
+
+    calib = max(threads * 4, 16)
+    dt = run(calib)
+    count = int(max(calib, min(200000, calib * target_s / max(dt, 1e-6))))
+    count -= count % threads or 0
+    dt = run(count)
+    return count / dt, threads, count, dt, native
+
+
+def cpu_ntt_rate(target_s: float, threads: int | None = None):
+    from oracle import oracle as O
+    try:
+        O.build(native=True)
+        native = True
+    except Exception:
+        native = False
+    ctx = O.OracleNtt(Q_MOD, N_RING, native=native)
+    threads = threads or O.max_threads()
+    rng = np.random.Generator(np.random.PCG64(0x5EED))
+    calib = threads * 64
+    x = rng.integers(0, Q_MOD, size=(calib, N_RING), dtype=np.uint64)
+    t0 = time.perf_counter(); ctx.forward_inplace(x, threads); dt = time.perf_counter() - t0
+    count = int(max(calib, min(2_000_000, calib * target_s / max(dt, 1e-6))))
+    x = rng.integers(0, Q_MOD, size=(count, N_RING), dtype=np.uint64)
+    t0 = time.perf_counter(); ctx.forward_inplace(x, threads); dt = time.perf_counter() - t0
+    return count / dt, threads, count, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_step = max(2.0, min(20.0, 60.0 / max(args.steps + args.warmup, 1)))
+    rates = []
+    meta = None
+    for i in range(args.warmup + args.steps):
+        rate, threads, count, dt, native = cpu_commit_rate(per_step)
+        meta = (threads, count, native)
+        if i >= args.warmup:
+            rates.append((count, dt))
+    total = sum(c for c, _ in rates)
+    secs = sum(d for _, d in rates)
+    value = total / secs
+    threads, count, native = meta
+    sample = (f"{count} commitments per step (n={N_RING}, k={K_RANK}, full-length messages), "
+              f"{threads} OpenMP threads, oracle C port of the same algorithm"
+              f"{' (-march=native)' if native else ''}; SEAL/BFV reference cannot be built here")
+    line = {
+        "impl": "reference", "metric": "lwe_commitments_per_sec", "value": value, "unit": "commitments/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / max(len(rates), 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(count, "cpu"),
+        "cpu_baseline": {"value": value, "unit": "commitments/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "commitments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(batch, where):
+    return {"workload": f"Module-LWE commitment batch, fused NTT-domain ring mat-vec (BASELINE configs[3]); "
+                        f"n={N_RING}, k={K_RANK}, q={Q_MOD}, sigma={SIGMA}, seeded s/e, full-length uniform messages",
+            "n": N_RING, "k": K_RANK, "q": Q_MOD, "sigma": SIGMA, "batch_per_gpu": int(batch), "where": where,
+            "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)"}
+
+
+# ------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from lambda_snark_r_b200 import api, capi
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = api.LweContext(api.Params(n=N_RING, k=K_RANK, q=Q_MOD, sigma=SIGMA), seed32=CTX_SEED)
+    ntt = api.NttContext(Q_MOD, N_RING)
+    words = ctx.words
+    B = args.batch
+    # weak scaling: every rank owns B commitments; global index = rank*B + i decides seed and message
+    g = torch.Generator(device=dev); g.manual_seed(0x5EED + rank)
+    msgs = torch.randint(0, Q_MOD, (B, N_RING), device=dev, dtype=torch.int64, generator=g)
+    seeds = (torch.arange(B, device=dev, dtype=torch.int64) + (SEED_BASE + rank * B))
+    out = torch.empty((B, words), device=dev, dtype=torch.int64)
+
+    def step():
+        ctx.commit_batch_device(msgs.data_ptr(), N_RING, seeds.data_ptr(), B, out.data_ptr(), stream)
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step, args.warmup, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- NTT sweep point at the same n (BASELINE configs[2])
+    NB = args.ntt_batch
+    data = torch.randint(0, Q_MOD, (NB, N_RING), device=dev, dtype=torch.int64, generator=g)
+    data2 = torch.randint(0, Q_MOD, (NB, N_RING), device=dev, dtype=torch.int64, generator=g)
+    ms_fwd = timed(lambda: ntt.forward_device(data.data_ptr(), NB, stream), args.warmup, args.steps) / args.steps
+    ms_inv = timed(lambda: ntt.inverse_device(data.data_ptr(), NB, stream), args.warmup, args.steps) / args.steps
+    ms_mul = timed(lambda: ntt.mul_pointwise_device(data2.data_ptr(), data.data_ptr(), data2.data_ptr(), NB * N_RING, stream),
+                   args.warmup, args.steps) / args.steps
+
+    # ---- end to end through the host-pointer C ABI, pinned host buffers
+    EB = args.e2e_batch
+    h_msgs = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
+    h_seeds = (torch.arange(EB, dtype=torch.int64) + (SEED_BASE + rank * EB)).pin_memory()
+    h_out = torch.empty((EB, words), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        ctx.commit_batch_ptr(h_msgs.data_ptr(), N_RING, h_seeds.data_ptr(), EB, h_out.data_ptr())
+
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_value = world * EB / (e2e_ms * 1e-3)
+
+    # ---- final gather over NVLink (outside the timed step: no data-path collective in the hot path)
+    gather = None
+    if world > 1:
+        GB_ = min(B, 2048)
+        part = out[:GB_].contiguous()
+        full = torch.empty((world * GB_, words), device=dev, dtype=torch.int64)
+        for _ in range(2):
+            dist.all_gather_into_tensor(full, part)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); dist.all_gather_into_tensor(full, part); e1.record()
+        barrier()
+        gms = max_over_ranks(e0.elapsed_time(e1))
+        gather = {"op": "ncclAllGather of the commitment containers", "commitments_per_rank": GB_, "ms": gms,
+                  "GBps_in_per_rank": (world - 1) * GB_ * words * 8 / (gms * 1e-3) / 1e9}
+
+    # ---- integer roofline denominator (measured on this GPU)
+    imad_wide = C.c_double(0); imad_lo = C.c_double(0); mhz = C.c_double(0)
+    capi.load().lsr_measure_imad_peak(1, C.byref(imad_wide), C.byref(mhz))
+    capi.load().lsr_measure_imad_peak(0, C.byref(imad_lo), None)
+    imad_peak = max(imad_wide.value, imad_lo.value)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm_peak, hbm_src = peaks()
+    tr = traffic_note()
+    commit_gbs = B * ALG_BYTES_COMMIT / (ms_step * 1e-3) / 1e9
+    commit_imad = B * MODMUL_COMMIT * IMAD_PER_MODMUL / (ms_step * 1e-3) / 1e9
+
+    def ntt_block(ms, extra_modmul=0):
+        rate = world * NB / (ms * 1e-3)
+        gbs = NB * ALG_BYTES_NTT / (ms * 1e-3) / 1e9
+        gimad = NB * (BUTTERFLIES_NTT + extra_modmul) * IMAD_PER_MODMUL / (ms * 1e-3) / 1e9
+        return {"value": rate, "unit": "NTT/s", "ms_per_step": ms,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                             "imad_achieved_gimad_s": gimad, "imad_peak_gimad_s": imad_peak,
+                             "imad_frac": gimad / imad_peak if imad_peak else None}}
+
+    # CPU baseline: bounded sample of the same workload on this box's host cores
+    cpu_rate, cpu_threads, cpu_count, cpu_dt, native = cpu_commit_rate(args.cpu_seconds)
+    ntt_cpu_rate, _, ntt_cpu_count, ntt_cpu_dt = cpu_ntt_rate(min(args.cpu_seconds, 5.0))
+
+    mul_gbs = NB * N_RING * 24 / (ms_mul * 1e-3) / 1e9
+    line = {
+        "metric": "lwe_commitments_per_sec", "value": value, "unit": "commitments/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(B, "hbm-resident"),
+        "roofline": {
+            "kernel": "fused_commit_kernel<12,2,5>", "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": commit_gbs / hbm_peak, "peak_source": hbm_src,
+            "traffic": (tr.get("fused_commit_bytes_per_commitment") or 0) * B or None,
+            "algorithmic_bytes_per_commitment": ALG_BYTES_COMMIT,
+            "binding_bound": "imad (integer multiply pipe), not hbm",
+            "imad_achieved_gimad_s": commit_imad, "imad_peak_gimad_s": imad_peak,
+            "imad_frac": commit_imad / imad_peak if imad_peak else None,
+            "imad_peak_source": f"lsr_measure_imad_peak on this GPU (mad.wide {imad_wide.value:.0f}, mad.lo {imad_lo.value:.0f} GIMAD/s)",
+            "imad_model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d); sampler not counted",
+        },
+        "cpu_baseline": {"value": cpu_rate, "unit": "commitments/s", "cores": cpu_threads, "kind": "port",
+                         "sample": f"{cpu_count} commitments in {cpu_dt:.1f}s, oracle C port, {cpu_threads} OpenMP threads"
+                                   f"{' -march=native' if native else ''}",
+                         "ntt_forward_per_s": ntt_cpu_rate},
+        "e2e": {"value": e2e_value, "unit": "commitments/s", "h2d_bytes_per_step": EB * (N_RING + 1) * 8,
+                "d2h_bytes_per_step": EB * words * 8, "batch_per_gpu": EB, "ms_per_step": e2e_ms,
+                "api": "lwe_commit_batch (C ABI, pinned host buffers)"},
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "ntt": {"batch_per_gpu": NB, "forward": ntt_block(ms_fwd), "inverse": ntt_block(ms_inv, N_RING // 2),
+                "pointwise": {"value": world * NB * N_RING / (ms_mul * 1e-3), "unit": "coefficients/s", "ms_per_step": ms_mul,
+                              "roofline": {"bound": "hbm", "achieved": mul_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": mul_gbs / hbm_peak}}},
+    }
+    if gather:
+        line["gather"] = gather
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="commitments per GPU per step")
+    ap.add_argument("--ntt-batch", type=int, default=16384, help="polynomials per GPU per NTT step")
+    ap.add_argument("--e2e-batch", type=int, default=4096)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

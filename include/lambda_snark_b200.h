@@ -205,6 +205,12 @@ int         lsr_set_device(int device) LSR_NOEXCEPT;   /* device new contexts bi
 const char* lsr_version(void) LSR_NOEXCEPT;
 const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnostic string */
 
+/* Integer-multiply roofline denominator: dependency-free mad.wide.u32 (wide=1)
+ * or mad.lo.u32 (wide=0) on every SM, timed with CUDA events; result in
+ * 10^9 IMAD per second.  sm_mhz_effective (optional) = the SM clock implied by
+ * 64 lanes/clk/SM.                                                          */
+int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_mhz_effective) LSR_NOEXCEPT;
+
 /* Introspection used by the tests and the host wrappers. */
 uint64_t lsr_ntt_modulus(const NttContext* ctx) LSR_NOEXCEPT;
 uint32_t lsr_ntt_degree(const NttContext* ctx) LSR_NOEXCEPT;

@@ -22,7 +22,8 @@ LIB = PKG / "lib"
 SO = LIB / "liblambda_snark_core.so"
 AR = LIB / "liblambda_snark_core.a"
 
-SOURCES = ["lsr_host.cpp", "lsr_r1cs.cpp", "lsr_abi.cpp", "lsr_ntt.cu", "lsr_commit.cu", "lsr_commit_fused.cu"]
+SOURCES = ["lsr_host.cpp", "lsr_r1cs.cpp", "lsr_abi.cpp", "lsr_ntt.cu", "lsr_commit.cu", "lsr_commit_fused.cu",
+           "lsr_microbench.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

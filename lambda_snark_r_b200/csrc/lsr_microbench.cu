@@ -1,0 +1,76 @@
+// lsr_microbench.cu -- measures the integer-multiply roofline denominator.
+//
+// MEASURED_PEAKS.json records HBM and tensor peaks only; the NTT is bound by
+// the 32-bit IMAD pipe, so its peak is measured here the same way the driver
+// measures the others: a dependency-free loop of mad.wide.u32 / mad.lo.u32 on
+// every SM, timed with CUDA events ("the builder must measure it").
+#include <cuda_runtime.h>
+
+#include "lambda_snark_b200.h"
+#include "lsr_engine.h"
+
+namespace lsr {
+
+constexpr int kChains = 8;     // independent accumulators per thread (latency 4, issue every 2)
+constexpr int kInner = 64;
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+imad_peak_kernel(unsigned iters, unsigned seed, unsigned long long* sink) {
+    unsigned a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 1u;
+    unsigned long long acc[kChains];
+    unsigned lo[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; c++) { acc[c] = a + c; lo[c] = b + c; }
+    for (unsigned it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < kInner; r++) {
+#pragma unroll
+            for (int c = 0; c < kChains; c++) {
+                if (WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+                else      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(a), "r"(b));
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int c = 0; c < kChains; c++) s += acc[c] + lo[c];
+    if (s == 0x123456789abcdefULL) *sink = s;     // never true in practice; defeats DCE
+}
+
+}  // namespace lsr
+
+extern "C" int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_mhz_effective) LSR_NOEXCEPT {
+    using namespace lsr;
+    if (!gimad_per_s) return -1;
+    int dev = current_device_choice();
+    if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return -1;
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return -1;
+    unsigned long long* sink = nullptr;
+    if (!cuda_ok(cudaMalloc(&sink, sizeof(*sink)), "cudaMalloc")) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const unsigned blocks = prop.multiProcessorCount * 8;    // 8 CTAs x 256 threads = 64 warps / SM
+    const unsigned iters = 2000;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        if (wide) imad_peak_kernel<true><<<blocks, 256>>>(iters, rep, sink);
+        else      imad_peak_kernel<false><<<blocks, 256>>>(iters, rep, sink);
+        cudaEventRecord(e1);
+        if (!cuda_ok(cudaEventSynchronize(e1), "imad_peak_kernel")) { cudaFree(sink); return -1; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double ops = (double)blocks * 256.0 * iters * kInner * kChains;
+        const double rate = ops / (ms * 1e-3) / 1e9;
+        if (rep > 0 && rate > best) best = rate;     // first repetition is warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *gimad_per_s = best;
+    if (sm_mhz_effective) *sm_mhz_effective = best * 1e3 / (64.0 * prop.multiProcessorCount);   // if 64 lanes/clk/SM
+    return 0;
+}

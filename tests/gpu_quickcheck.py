@@ -57,7 +57,7 @@ def check_commit(q, n, k, sigma, rng, paths=(1, 2)):
     count = 5
     msgs = rng.integers(0, 2**64, size=(count, n), dtype=np.uint64)
     msgs[0, :] = 0
-    seeds = np.arange(1, count + 1, dtype=np.uint64) * 0x9E3779B97F4A7C15 % 2**64
+    seeds = np.array([(i * 0x9E3779B97F4A7C15) % 2**64 for i in range(1, count + 1)], dtype=np.uint64)
     want = orc.commit_batch(msgs, seeds)
     for path in paths:
         try:

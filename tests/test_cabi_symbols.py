@@ -1,0 +1,121 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads without a GPU, exports every
+symbol include/lambda_snark_b200.h declares, and keeps the reference's struct
+layouts (cpp-core/include/lambda_snark/types.h, r1cs.h).  No GPU compute here."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from lambda_snark_r_b200 import capi
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "lambda_snark_b200.h"
+
+# the 19 symbols the reference exports for this path minus the four
+# Lean exporters (no callers, SEAL-specific, out of scope)
+REFERENCE_SYMBOLS = [
+    "lwe_context_create", "lwe_context_free", "lwe_commit", "lwe_commitment_free", "lwe_commitment_clone",
+    "lwe_verify_opening", "lwe_linear_combine", "ntt_context_create", "ntt_context_free", "ntt_forward",
+    "ntt_inverse", "ntt_mul_pointwise", "sample_gaussian", "lambda_snark_r1cs_create",
+    "lambda_snark_r1cs_validate_witness", "lambda_snark_r1cs_free", "lambda_snark_r1cs_num_constraints",
+    "lambda_snark_r1cs_num_variables",
+]
+
+
+def declared_functions() -> list[str]:
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    text = re.sub(r"typedef\s+(struct|enum)\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{}]*\)\s*(?:LSR_NOEXCEPT)?\s*;", text)
+    return sorted(set(names))
+
+
+def test_library_is_built_and_loads():
+    assert capi.LIB_PATH.exists(), "build the CUDA library first: python -m lambda_snark_r_b200._build"
+    lib = capi.load()
+    assert b"sm_100a" in lib.lsr_version()
+    assert lib.lsr_device_count() >= 0
+
+
+def test_every_declared_symbol_is_exported():
+    lib = C.CDLL(str(capi.LIB_PATH))
+    declared = declared_functions()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    for name in REFERENCE_SYMBOLS:
+        assert name in declared and hasattr(lib, name)
+
+
+def test_ctypes_table_covers_the_header():
+    assert sorted(capi.SIGNATURES) == declared_functions()
+
+
+def test_struct_layouts_match_the_reference():
+    assert C.sizeof(capi.PublicParams) == 32                        # types.h:60-67
+    assert capi.PublicParams.modulus.offset == 8
+    assert capi.PublicParams.ring_degree.offset == 16
+    assert capi.PublicParams.module_rank.offset == 20
+    assert capi.PublicParams.sigma.offset == 24
+    assert C.sizeof(capi.LweCommitment) == 16 and capi.LweCommitment.len.offset == 8
+    assert C.sizeof(capi.LweOpening) == 16
+    assert C.sizeof(capi.SparseEntry) == 16 and capi.SparseEntry.value.offset == 8
+    assert C.sizeof(capi.SparseMatrix) == 24 and capi.SparseMatrix.n_cols.offset == 20
+    assert C.sizeof(capi.R1CSWitness) == 16
+
+
+def test_header_compiles_as_c_and_cxx_with_static_layout_asserts(tmp_path):
+    src = r'''
+#include "lambda_snark/types.h"
+#include "lambda_snark/ntt.h"
+#include "lambda_snark/commitment.h"
+#include "lambda_snark/utils.h"
+#include "lambda_snark/r1cs.h"
+#include <stddef.h>
+#ifdef __cplusplus
+#define SA static_assert
+#else
+#define SA _Static_assert
+#endif
+SA(sizeof(PublicParams) == 32, "PublicParams");
+SA(offsetof(PublicParams, sigma) == 24, "sigma");
+SA(sizeof(LweCommitment) == 16, "LweCommitment");
+SA(sizeof(SparseEntry) == 16, "SparseEntry");
+SA(sizeof(SparseMatrix) == 24, "SparseMatrix");
+SA(LAMBDA_SNARK_ERR_CRYPTO_FAILED == 4, "error codes");
+int main(void) { NttContext* (*f)(uint64_t, uint32_t) = ntt_context_create; return sizeof(f) == 0; }
+'''
+    for name, cc, std in (("t.c", "gcc", "-std=c11"), ("t.cpp", "g++", "-std=c++17")):
+        f = tmp_path / name
+        f.write_text(src)
+        r = subprocess.run([cc, std, "-Wall", "-Werror", "-I", str(ROOT / "include"), "-c", str(f), "-o",
+                            str(tmp_path / (name + ".o"))], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_null_and_invalid_arguments_need_no_gpu():
+    lib = capi.load()
+    # lambda-snark-sys/src/lib.rs:28-34
+    assert not lib.lwe_context_create(None)
+    # ntt.cpp:31,41 / SEAL rules: rejected before any device work
+    for q, n in ((12289, 0), (12289, 3), (12289, 1), (12289, 4096), (1 << 61, 16), (17592186044417, 4096)):
+        assert not lib.ntt_context_create(q, n)
+    lib.ntt_context_free(None)                                       # test_ntt.cpp:89
+    lib.lwe_context_free(None)
+    lib.lwe_commitment_free(None)                                    # test_commitment.cpp:112
+    assert lib.ntt_forward(None, None, 4) == -1                      # test_ntt.cpp:86
+    assert not lib.lwe_commit(None, None, 0, 0)                      # test_commitment.cpp:104
+    assert not lib.lwe_commitment_clone(None)
+    assert lib.lwe_verify_opening(None, None, None, 0, None) == -1
+    assert not lib.lwe_linear_combine(None, None, None, 0)
+    buf = (C.c_uint64 * 16)()
+    assert lib.sample_gaussian(None, 16, 3.2) == -1                  # test_utils.cpp:29-33
+    assert lib.sample_gaussian(buf, 0, 3.2) == -1
+    assert lib.sample_gaussian(buf, 16, 0.0) == -1
+    assert lib.sample_gaussian(buf, 16, float("inf")) == -1
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        capi.load(tmp_path / "liblambda_snark_core.so")

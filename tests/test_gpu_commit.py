@@ -1,0 +1,328 @@
+"""GPU parity tests for K4-K7 (-m gpu): commitments, verification, linear
+combination and the sampler through the C ABI, bit for bit against the oracle,
+plus the reference's own commitment tests ported assertion for assertion."""
+import ctypes as C
+import hashlib
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import Q0, Q1, Q60, uniform
+from lambda_snark_r_b200 import api, capi, sharding
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parent / "golden"
+SEED32 = bytes(range(32))
+TEST_MODULUS = 17592186044417       # 2^44+1, the (composite) modulus of the reference's Rust tests
+
+
+def mk(n=4096, k=2, q=Q0, sigma=3.19, seed32=SEED32):
+    return api.LweContext(api.Params(n=n, k=k, q=q, sigma=sigma), seed32=seed32, validate=False)
+
+
+# ---------------------------------------------- cpp-core/tests/test_commitment.cpp
+@pytest.fixture(scope="module")
+def ref_ctx(gpu):
+    # test_commitment.cpp:12-20 -- modulus 12289, n 4096, k 2, sigma 3.19, OS-random keys
+    ctx = api.LweContext(api.Params(n=4096, k=2, q=12289, sigma=3.19), validate=False)
+    yield ctx
+    ctx.close()
+
+
+def test_ref_commit_basic(ref_ctx):
+    c = api.Commitment.new(ref_ctx, [1, 2, 3, 4], 0x1234)          # :37-47
+    w = c.as_bytes()
+    assert w.size > 0 and int(w[0]) == (w.size - 1) * 8
+
+
+def test_ref_commit_binding(ref_ctx):
+    c1 = api.Commitment.new(ref_ctx, [1, 2, 3], 0)                 # :49-75 (seed 0 = random)
+    c2 = api.Commitment.new(ref_ctx, [4, 5, 6], 0)
+    assert not np.array_equal(c1.as_bytes(), c2.as_bytes())
+    c3 = api.Commitment.new(ref_ctx, [1, 2, 3], 0x1234)            # :77-100 same seed, different message
+    c4 = api.Commitment.new(ref_ctx, [4, 5, 6], 0x1234)
+    assert not np.array_equal(c3.as_bytes(), c4.as_bytes())
+    # seed 0 draws fresh randomness every time (commitment.h:52)
+    assert not np.array_equal(c1.as_bytes(), api.Commitment.new(ref_ctx, [1, 2, 3], 0).as_bytes())
+
+
+def test_ref_null_pointer_handling(ref_ctx):
+    lib = capi.load()                                              # :102-113
+    assert not lib.lwe_commit(None, None, 0, 0)
+    assert not lib.lwe_commit(ref_ctx.as_ptr(), None, 10, 0)
+    lib.lwe_commitment_free(None)
+
+
+def test_ref_verify_opening_matches_message(ref_ctx):
+    msg = [7, 11, 13, 17]                                          # :115-132
+    c = api.Commitment.new(ref_ctx, msg, 0)
+    assert api.verify_commitment(ref_ctx, c, msg, [0]) == 1
+    wrong = list(msg); wrong[1] ^= 1
+    assert api.verify_commitment(ref_ctx, c, wrong, [0]) == 0
+
+
+def test_ref_linear_combination(ref_ctx):
+    m1, m2 = [1, 2, 3, 4], [5, 6, 7, 8]                            # :134-166
+    c1 = api.Commitment.new(ref_ctx, m1, 0)
+    c2 = api.Commitment.new(ref_ctx, m2, 0)
+    comb = api.Commitment.linear_combine(ref_ctx, [c1, c2], [2, 3])
+    expected = [2 * a + 3 * b for a, b in zip(m1, m2)]
+    assert api.verify_commitment(ref_ctx, comb, expected, [0]) == 1
+    expected[0] += 1
+    assert api.verify_commitment(ref_ctx, comb, expected, [0]) == 0
+
+
+# --------------------------------------------------- Rust-side tests (commitment.rs, lwe_verification.rs)
+@pytest.fixture(scope="module")
+def rust_ctx(gpu):
+    ctx = api.LweContext(api.Params(n=4096, k=2, q=TEST_MODULUS, sigma=3.19))
+    yield ctx
+    ctx.close()
+
+
+def test_rust_linear_combination_roundtrip(rust_ctx):
+    # commitment.rs:163-219, null opening
+    msg1 = [i + 1 for i in range(4)]
+    msg2 = [(i + 1) * 2 for i in range(4)]
+    c1 = api.Commitment.new(rust_ctx, msg1, 0)
+    c2 = api.Commitment.new(rust_ctx, msg2, 1)
+    comb = api.Commitment.linear_combine(rust_ctx, [c1, c2], [2, 3])
+    expected = [(2 * a + 3 * b) % TEST_MODULUS for a, b in zip(msg1, msg2)]
+    assert api.verify_commitment(rust_ctx, comb, expected, None) == 1
+    with pytest.raises(api.LambdaSnarkError):
+        api.Commitment.linear_combine(rust_ctx, [], [])
+    with pytest.raises(api.LambdaSnarkError):
+        api.Commitment.linear_combine(rust_ctx, [c1], [1, 2])
+
+
+def test_rust_lwe_verification(rust_ctx):
+    # tests/lwe_verification.rs: the #[ignore]d tests pass here because commitments are
+    # deterministic in (context, message, seed) and the context can open them
+    for witness, seed, alpha in (([1, 7, 13, 91], 0x1234, 12345), ([1, 7, 13, 91], 0xABCD, 54321),
+                                 ([1, 314, 628, 471, 471], 0xDEADBEEF, 98765), ([1, 2, 3, 4], 0x7777, 11111)):
+        c = api.Commitment.new(rust_ctx, witness, seed)
+        op = api.generate_opening(witness, alpha, seed, TEST_MODULUS)
+        for _ in range(3):                                          # test_lwe_verification_deterministic
+            assert api.verify_opening_with_context(c, alpha, op, TEST_MODULUS, rust_ctx)
+        assert np.array_equal(c.as_bytes(), api.Commitment.new(rust_ctx, witness, seed).as_bytes())
+    # test_lwe_verification_wrong_polynomial (not ignored upstream)
+    c1 = api.Commitment.new(rust_ctx, [1, 7, 13, 91], 0x1234)
+    op2 = api.generate_opening([1, 7, 13, 92], 12345, 0x1234, TEST_MODULUS)
+    assert not api.verify_opening_with_context(c1, 12345, op2, TEST_MODULUS, rust_ctx)
+    # test_lwe_verification_multiple_witnesses: cross-verification fails
+    ca = api.Commitment.new(rust_ctx, [1, 2, 3], 0x1111)
+    cb = api.Commitment.new(rust_ctx, [4, 5, 6], 0x2222)
+    oa = api.generate_opening([1, 2, 3], 7777, 0x1111, TEST_MODULUS)
+    ob = api.generate_opening([4, 5, 6], 7777, 0x2222, TEST_MODULUS)
+    assert api.verify_opening_with_context(ca, 7777, oa, TEST_MODULUS, rust_ctx)
+    assert api.verify_opening_with_context(cb, 7777, ob, TEST_MODULUS, rust_ctx)
+    assert not api.verify_opening_with_context(ca, 7777, ob, TEST_MODULUS, rust_ctx)
+    assert not api.verify_opening_with_context(cb, 7777, oa, TEST_MODULUS, rust_ctx)
+
+
+def test_clone_and_free(rust_ctx):
+    c = api.Commitment.new(rust_ctx, [9, 8, 7], 5)                 # commitment.rs:18-27,96-107
+    d = c.clone()
+    assert np.array_equal(c.as_bytes(), d.as_bytes())
+    assert c.as_bytes().ctypes.data != d.as_bytes().ctypes.data
+    c.close()
+    assert api.verify_commitment(rust_ctx, d, [9, 8, 7]) == 1
+    lib = capi.load()
+    empty = capi.LweCommitment(None, 0)
+    assert not lib.lwe_commitment_clone(C.byref(empty))            # commitment.cpp:180-182
+
+
+# ------------------------------------------------------------- parity vs oracle
+@pytest.mark.parametrize("n,k,q", [(4096, 2, Q0), (4096, 1, Q0), (4096, 3, Q0), (4096, 4, Q0), (1024, 2, Q0),
+                                   (2048, 2, Q0), (8192, 2, Q1), (256, 2, Q0), (16, 1, Q0), (64, 3, Q0),
+                                   (16384, 2, Q1), (4096, 2, Q60), (4096, 5, Q0)])
+def test_commit_matches_oracle_on_both_paths(gpu, rng, n, k, q):
+    ctx = mk(n, k, q)
+    orc = O.OracleLwe(q, n, k, 3.19, SEED32)
+    assert (ctx.q, ctx.p, ctx.delta, ctx.words) == (orc.q, orc.p, orc.delta, orc.words)
+    assert np.array_equal(ctx.matrix(), orc.matrix())
+    s_g, e_g = ctx.sample_se(0xC0FFEE)
+    s_o, e_o = orc.sample_se(0xC0FFEE)
+    assert np.array_equal(s_g, s_o) and np.array_equal(e_g, e_o)
+    count = 7
+    msgs = rng.integers(0, 2**64, size=(count, n), dtype=np.uint64)
+    msgs[0, :] = 0
+    msgs[1, :] = ctx.p - 1
+    seeds = sharding.global_seeds(0xC0FFEE, 0, count)
+    want = orc.commit_batch(msgs, seeds)
+    ran = 0
+    for path in (1, 2):
+        ctx.set_commit_path(path)
+        try:
+            got = ctx.commit_batch(msgs, seeds)
+        except api.LambdaSnarkError:
+            assert path == 2          # the fused kernel covers a subset of shapes; the generic path covers all
+            continue
+        assert np.array_equal(got, want), f"path {path}"
+        ran += 1
+    assert ran >= 1
+    if (n, k, q) == (4096, 2, Q0):
+        assert ran == 2               # the headline configuration must run fused
+    ctx.close()
+
+
+@pytest.mark.parametrize("msg_len", [0, 1, 5, 4095, 4096, 4097, 5000])
+def test_ragged_messages_truncate_and_pad(gpu, rng, msg_len):
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    count = 3
+    msgs = rng.integers(0, ctx.p, size=(count, max(msg_len, 1)), dtype=np.uint64)[:, :msg_len]
+    msgs = np.ascontiguousarray(msgs).reshape(count, msg_len)
+    seeds = np.array([11, 12, 13], dtype=np.uint64)
+    want = np.stack([orc.commit(msgs[i], int(seeds[i])) for i in range(count)])
+    for path in (1, 2):
+        ctx.set_commit_path(path)
+        assert np.array_equal(ctx.commit_batch(msgs, seeds), want)
+    ctx.set_commit_path(0)
+    if msg_len <= 4096:
+        assert ctx.verify_batch(want, msgs).tolist() == [1] * count
+    else:
+        assert ctx.verify_batch(want, msgs).tolist() == [0] * count      # commitment.cpp:219-221
+    ctx.close()
+
+
+def test_golden_digests_on_device(gpu):
+    g = json.loads((GOLD / "commit_kat.json").read_text())
+    for c in g["cases"]:
+        ctx = mk(c["n"], c["k"], Q0, c["sigma"])
+        assert hashlib.sha256(ctx.matrix().tobytes()).hexdigest() == c["matrix_sha256"]
+        cm = api.Commitment.new(ctx, c["msg"], c["seed"])
+        assert hashlib.sha256(cm.as_bytes().tobytes()).hexdigest() == c["sha256"]
+        ctx.close()
+
+
+def test_verify_and_lincomb_match_oracle(gpu, rng):
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    count = 9
+    msgs = rng.integers(0, ctx.p, size=(count, 50), dtype=np.uint64)
+    seeds = sharding.global_seeds(5, 0, count)
+    cms = ctx.commit_batch(msgs, seeds)
+    bad = msgs.copy(); bad[::2, 17] ^= 1
+    assert ctx.verify_batch(cms, msgs).tolist() == [orc.verify(cms[i], msgs[i]) for i in range(count)] == [1] * count
+    assert ctx.verify_batch(cms, bad).tolist() == [orc.verify(cms[i], bad[i]) for i in range(count)]
+    broken = cms.copy()
+    broken[0, 0] = 0; broken[1, 7] = ctx.q; broken[2, 0] += 8
+    assert ctx.verify_batch(broken, msgs).tolist()[:4] == [-1, -1, -1, 1]
+    # single-call path, malformed containers (commitment.cpp:66-75)
+    lib = capi.load()
+    c0 = api.Commitment.new(ctx, msgs[0], 77)
+    words = c0.as_bytes().copy()
+    for mutate in (lambda w: w.__setitem__(0, 0), lambda w: w.__setitem__(3, ctx.q)):
+        w = words.copy(); mutate(w)
+        fake = capi.LweCommitment(w.ctypes.data_as(capi.u64p), w.size)
+        assert lib.lwe_verify_opening(ctx.as_ptr(), C.byref(fake), msgs[0].ctypes.data_as(capi.u64p), 5, None) == -1
+    short = capi.LweCommitment(words.ctypes.data_as(capi.u64p), 100)
+    assert lib.lwe_verify_opening(ctx.as_ptr(), C.byref(short), msgs[0].ctypes.data_as(capi.u64p), 5, None) == -1
+    # linear combination: device result == oracle result, word for word
+    cs = [api.Commitment.new(ctx, msgs[i], int(seeds[i])) for i in range(4)]
+    coeffs = [2, 3, ctx.p + 5, 0]
+    comb = api.Commitment.linear_combine(ctx, cs, coeffs)
+    want = orc.linear_combine([c.as_bytes() for c in cs], coeffs)
+    assert np.array_equal(comb.as_bytes(), want)
+    # NULL entries are skipped (commitment.cpp:248-250); all-NULL -> NULL
+    ptrs = (capi.LweCommitmentP * 3)(cs[0].as_ffi_ptr(), None, cs[1].as_ffi_ptr())
+    cf = np.array([2, 99, 3], dtype=np.uint64)
+    r = lib.lwe_linear_combine(ctx.as_ptr(), ptrs, cf.ctypes.data_as(capi.u64p), 3)
+    assert r
+    got = np.ctypeslib.as_array(r.contents.data, shape=(r.contents.len,)).copy()
+    lib.lwe_commitment_free(r)
+    assert np.array_equal(got, orc.linear_combine([cs[0].as_bytes(), None, cs[1].as_bytes()], [2, 99, 3]))
+    nulls = (capi.LweCommitmentP * 2)(None, None)
+    assert not lib.lwe_linear_combine(ctx.as_ptr(), nulls, cf.ctypes.data_as(capi.u64p), 2)
+    assert not lib.lwe_linear_combine(ctx.as_ptr(), ptrs, cf.ctypes.data_as(capi.u64p), 0)
+    ctx.close()
+
+
+def test_homomorphism_at_scale(gpu, rng):
+    """Size-independent property at a BASELINE batch size: verify(sum c_i C_i) == sum c_i m_i (mod p)."""
+    ctx = mk()
+    count = 512
+    msgs = rng.integers(0, ctx.p, size=(count, 64), dtype=np.uint64)
+    seeds = sharding.global_seeds(0xC0FFEE, 0, count)
+    cms = ctx.commit_batch(msgs, seeds)
+    assert (cms[:, 0] == 2 * 4096 * 8).all() and (cms[:, 1:] < np.uint64(ctx.q)).all()
+    assert ctx.verify_batch(cms, msgs).tolist() == [1] * count
+    # fold pairs with small coefficients on the host (the homomorphism itself), verify on the device
+    a, b = cms[0::2, 1:].astype(object), cms[1::2, 1:].astype(object)
+    folded = np.empty((count // 2, ctx.words), dtype=np.uint64)
+    folded[:, 0] = cms[0, 0]
+    folded[:, 1:] = ((2 * a + 3 * b) % ctx.q).astype(np.uint64)
+    exp = ((2 * msgs[0::2].astype(object) + 3 * msgs[1::2].astype(object)) % ctx.p).astype(np.uint64)
+    assert ctx.verify_batch(folded, exp).tolist() == [1] * (count // 2)
+    ctx.close()
+
+
+def test_sharded_batch_is_bit_identical(gpu, rng):
+    """contiguous slices + global-index seeds -> same bits for any number of ranks."""
+    ctx = mk(1024, 2)
+    count = 24
+    msgs = rng.integers(0, ctx.p, size=(count, 1024), dtype=np.uint64)
+    full = ctx.commit_batch(msgs, sharding.global_seeds(0xC0FFEE, 0, count))
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            a, b = sharding.shard_range(count, r, world)
+            parts.append(ctx.commit_batch(msgs[a:b], sharding.global_seeds(0xC0FFEE, a, b)))
+        assert np.array_equal(sharding.gather_slices(parts), full)
+    ctx.close()
+
+
+def test_device_pointer_commit(gpu, rng):
+    import torch
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    count = 5
+    msgs = rng.integers(0, 2**63, size=(count, 4096), dtype=np.int64)
+    seeds = np.arange(21, 21 + count, dtype=np.int64)
+    dm, ds = torch.from_numpy(msgs).cuda(), torch.from_numpy(seeds).cuda()
+    out = torch.zeros((count, ctx.words), dtype=torch.int64, device="cuda")
+    ctx.commit_batch_device(dm.data_ptr(), 4096, ds.data_ptr(), count, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint64), orc.commit_batch(msgs.view(np.uint64), seeds.view(np.uint64)))
+    ctx.close()
+
+
+def test_context_create_rules(gpu):
+    lib = capi.load()
+    for bad in (dict(n=0), dict(n=8), dict(n=3000), dict(k=0), dict(k=17), dict(sigma=0.0), dict(sigma=float("nan"))):
+        with pytest.raises(api.LambdaSnarkError):
+            api.LweContext(api.Params(**{**dict(n=4096, k=2, q=Q0, sigma=3.19), **bad}), validate=False)
+    assert not lib.lwe_context_create_seeded(None, SEED32)
+    # the reference ignores `modulus` (commitment.cpp:108-111): an unusable one falls back to the built-in prime
+    ctx = api.LweContext(api.Params(n=4096, k=2, q=17592186044423, sigma=3.19), seed32=SEED32)
+    assert ctx.q == Q0 and ctx.modulus() == 17592186044423
+    ctx.close()
+    # two OS-seeded contexts have different keys
+    a = api.LweContext(api.Params()); b = api.LweContext(api.Params())
+    assert not np.array_equal(a.matrix(), b.matrix())
+    a.close(); b.close()
+
+
+# ---------------------------------------------------------------------- sampler
+def test_sample_gaussian_seeded_matches_oracle(gpu):
+    for sigma, length in ((3.2, 4099), (3.19, 1), (1.0, 33), (10.0, 1000), (40.0, 257)):
+        got = api.sample_gaussian(length, sigma, seed32=SEED32)
+        assert np.array_equal(got, O.sample_gaussian_seeded(length, sigma, SEED32)), (sigma, length)
+
+
+def test_sample_gaussian_reference_tests(gpu):
+    lib = capi.load()                                              # cpp-core/tests/test_utils.cpp:26-70
+    buf = np.zeros(16, dtype=np.uint64)
+    assert lib.sample_gaussian(None, 16, 3.2) == -1
+    assert lib.sample_gaussian(buf.ctypes.data_as(capi.u64p), 0, 3.2) == -1
+    assert lib.sample_gaussian(buf.ctypes.data_as(capi.u64p), 16, 0.0) == -1
+    assert lib.sample_gaussian(buf.ctypes.data_as(capi.u64p), 16, float("inf")) == -1
+    x = api.sample_gaussian(4096, 3.2).astype(np.float64)
+    assert abs(x.mean()) < 0.5 and abs(x.std(ddof=1) - 3.2) < 0.8
+    pos, neg = int((x > 0).sum()), int((x < 0).sum())
+    assert pos > 1024 and neg > 1024 and abs(pos - neg) < 4096 // 5
+    assert not np.array_equal(api.sample_gaussian(64, 3.2), api.sample_gaussian(64, 3.2))   # fresh entropy per call
