@@ -180,6 +180,16 @@ typedef struct {
     uint32_t     n_cols;
 } SparseMatrix;
 
+/* r1cs.h:62-69 -- named in lambda-snark-sys's bindgen allowlist (build.rs:201) */
+typedef struct {
+    SparseMatrix A;
+    SparseMatrix B;
+    SparseMatrix C;
+    uint32_t n_vars;
+    uint32_t n_public_inputs;
+    uint32_t n_constraints;
+} R1CSConstraintSystem;
+
 typedef struct {
     uint64_t* values;
     size_t    len;

@@ -69,7 +69,10 @@ class NttContext:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            _lib().ntt_context_free(self._h)
+            try:
+                _lib().ntt_context_free(self._h)
+            except TypeError:        # interpreter shutdown: module globals already cleared
+                pass
             self._h = None
 
     __del__ = close
@@ -192,7 +195,10 @@ class LweContext:
 
     def close(self) -> None:
         if getattr(self, "_h", None):
-            _lib().lwe_context_free(self._h)
+            try:
+                _lib().lwe_context_free(self._h)
+            except TypeError:
+                pass
             self._h = None
 
     __del__ = close
@@ -297,7 +303,10 @@ class Commitment:
 
     def close(self) -> None:
         if getattr(self, "_inner", None):
-            _lib().lwe_commitment_free(self._inner)
+            try:
+                _lib().lwe_commitment_free(self._inner)
+            except TypeError:
+                pass
             self._inner = None
 
     __del__ = close

@@ -48,12 +48,21 @@ __device__ __forceinline__ u64 mullo2_acc(u64 x, u64 w, u64 y, u64 z) {
 // two cross products, so it undershoots floor(x*ws/2^64) by at most 2; the
 // exact Shoup remainder is < 2q, hence the result is in [0, 4q).
 // 9 IMAD + 2 ALU.
+//
+// Measured on B200 (tools/imad_microbench.cu): IMAD / IMAD.WIDE issue at 64
+// lanes/clk/SM, IMAD.HI at 32.  The two cross products are therefore taken as
+// full-rate mul.wide results whose high registers are added on the ALU pipe
+// (one 3-input IADD3 + one IADD3.X) instead of two half-rate mul.hi.
 __device__ __forceinline__ u64 mulred4(u64 x, u64 w, u64 ws, u64 nq) {
     const u32 x0 = lo32(x), x1 = hi32(x);
     const u32 s0 = lo32(ws), s1 = hi32(ws);
-    const u32 a = __umulhi(x1, s0);
-    const u32 b = __umulhi(x0, s1);
-    const u64 qh = mad_wide(x1, s1, (u64)a) + (u64)b;
+    const u64 ta = mul_wide(x1, s0);
+    const u64 tb = mul_wide(x0, s1);
+    // the 33-bit sum of the two high halves is formed first so that it is born
+    // as a register pair and can ride in IMAD.WIDE's 64-bit addend without the
+    // zero-extension moves ptxas otherwise inserts (they land on the IMAD pipe)
+    const u64 ab = (u64)hi32(ta) + (u64)hi32(tb);
+    const u64 qh = mad_wide(x1, s1, ab);
     return mullo2_acc(x, w, qh, nq);
 }
 
@@ -72,7 +81,7 @@ __device__ __forceinline__ u64 csub(u64 x, u64 m) {
 // v < 2^7 * q  ->  [0, q).   3 IMAD + shifts + one conditional subtract.
 __device__ __forceinline__ u64 reduce_small(u64 v, const ModParams& mp) {
     const u32 vs = (u32)(v >> mp.red_sh);
-    const u32 est = __umulhi(vs, mp.red_c);           // floor(v/q) - 1 <= est <= floor(v/q)
+    const u32 est = hi32(mul_wide(vs, mp.red_c));     // floor(v/q) - 1 <= est <= floor(v/q)
     u64 acc = mad_wide(est, lo32(mp.nq), v);          // v - est*q  (mod 2^64)
     const u32 h = mad_lo(est, hi32(mp.nq), hi32(acc));
     return csub(pack64(lo32(acc), h), mp.q);

@@ -3,13 +3,17 @@
 // One CTA per commitment.  Everything between the message / seed coming in and
 // t = A*s + e + Delta*m going out stays on chip:
 //   phase 1  sample s_0..s_{k-1} (u64 residues) and e_0..e_{k-1} (int8) into
-//            shared memory: ChaCha keystream + constant-time CDT (K7 inlined)
-//   phase 2  forward NTT of all k secret polynomials, in shared memory
-//   phase 3  per output row i: acc = sum_j A-hat[i][j] o s-hat[j] (Shoup MAC,
-//            A-hat read once per commitment from L2), inverse NTT in shared
-//            memory, then + e_i (+ Delta*m on the last row) fused into the
-//            coalesced store of the LweCommitment container
-// HBM traffic per commitment: message in (8n) + container out (8kn + 8).
+//            shared memory: ChaCha keystream + constant-time CDT (K7 inlined;
+//            the CDT is searched with warp shuffles, see cdt_magnitude_shfl)
+//   phase 2  forward NTT of all k secret polynomials, one multi-polynomial tile
+//   phase 3  NTT-domain mat-vec IN PLACE: s-hat[.][x] <- A-hat[.][.][x] * s-hat[.][x]
+//            (Shoup MACs; A-hat read once per commitment from L2)
+//   phase 4  inverse NTT of the k rows, same tile
+//   phase 5  + e_i (+ Delta*m on the last row) fused into the coalesced store of
+//            the LweCommitment container
+// Shared memory: k*n*8 (residues) + k*n (errors) = 72 KiB at n=4096, k=2, so
+// three CTAs share an SM.  HBM traffic per commitment: message in (8n) +
+// container out (8kn + 8).
 //
 // Replaces Encryptor::encrypt_symmetric + BatchEncoder::encode +
 // ciphertext_to_commitment of the reference (cpp-core/src/commitment.cpp:44-60,
@@ -36,26 +40,38 @@ struct FusedParams {
     u32 msg_used;             // min(msg_len, n)
 };
 
+template <int LOGN, int K>
+constexpr size_t fused_smem() { return ((size_t)K << LOGN) * sizeof(u64) + ((size_t)K << LOGN); }
+
+template <int LOGN, int K>
+constexpr int fused_min_blocks() {
+    return fused_smem<LOGN, K>() <= 75 * 1024 ? 3 : (fused_smem<LOGN, K>() <= 113 * 1024 ? 2 : 1);
+}
+
 template <int LOGN, int K, int NCH8>
-__global__ void __launch_bounds__(kNttThreads)
+__global__ void __launch_bounds__(kNttThreads, fused_min_blocks<LOGN, K>())
 fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CdtParam cdt) {
     constexpr u32 n = 1u << LOGN;
+    static_assert((n >> 4) % 32 == 0, "whole warps must take part in the shuffle search");
     extern __shared__ __align__(16) u64 sm[];
-    u64* S = sm;                                   // [K][n], swizzled
-    u64* W = sm + (size_t)K * n;                   // [n],    swizzled
-    signed char* E = reinterpret_cast<signed char*>(W + n);   // [K][n]
+    u64* S = sm;                                                     // [K][n], swizzled
+    signed char* E = reinterpret_cast<signed char*>(sm + (size_t)K * n);   // [K][n]
     const ModParams& mp = fp.mp;
     const size_t b = blockIdx.x;
     const u64 seed = fp.seeds[b];
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
+    const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
 
     // ---- phase 1: randomness (DESIGN.md 3.3 layout, same as sample_se_kernel)
     for (u32 tau = threadIdx.x; tau < (n >> 4); tau += kNttThreads) {
         u32 sg[16];
         chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
-#pragma unroll
+        static_assert(K <= 4, "sign words 0..3 only");
+#pragma unroll 1
         for (u32 P = 0; P < 2 * K; P++) {
-            const u32 sbits = sg[P >> 1] >> ((P & 1) * 16);
+            const u32 wsel = P >> 1;
+            const u32 sw = wsel == 0 ? sg[0] : (wsel == 1 ? sg[1] : (wsel == 2 ? sg[2] : sg[3]));
+            const u32 sbits = sw >> ((P & 1) * 16);
 #pragma unroll
             for (u32 h = 0; h < 2; h++) {
                 u32 x[16];
@@ -63,7 +79,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
 #pragma unroll
                 for (u32 w = 0; w < 8; w++) {
                     const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
-                    const u32 mag = cdt_magnitude<NCH8>(cdt, u);
+                    const u32 mag = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
                     const u32 j = 8 * h + w;
                     const u32 sign = (sbits >> j) & 1u;
                     if (P < K) {
@@ -80,36 +96,42 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     // ---- phase 2: s-hat = NTT(s), all K polynomials as one multi-polynomial tile
     tile_forward<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
 
-    // ---- phase 3: rows of t
-    u64* o = fp.out + b * (1 + (size_t)K * n);
-    if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
-    const u64* msg = fp.msgs + b * (size_t)fp.msg_len;
-#pragma unroll 1
-    for (u32 i = 0; i < (u32)K; i++) {
-        for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
+    // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
+    for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
+        u64 sv[K];
+#pragma unroll
+        for (u32 j = 0; j < (u32)K; j++) sv[j] = S[swz((j << LOGN) + x)];
+#pragma unroll
+        for (u32 i = 0; i < (u32)K; i++) {
             u64 acc = 0;
 #pragma unroll
             for (u32 j = 0; j < (u32)K; j++) {
                 const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
-                acc += mulred4(S[swz((j << LOGN) + x)], a.x, a.y, mp.nq);     // each term < 4q
+                acc += mulred4(sv[j], a.x, a.y, mp.nq);                       // each term < 4q
             }
-            W[swz(x)] = reduce_small(acc, mp);                                 // 4Kq <= 64q < 2^7 q
+            S[swz((i << LOGN) + x)] = reduce_small(acc, mp);                   // 4Kq <= 16q < 2^7 q
         }
-        __syncthreads();
-        tile_inverse<LOGN, LOGN, true>(W, fp.tbl, mp, n, 0u);
-        const signed char* Ei = E + ((size_t)i << LOGN);
-        for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
-            const int ev = Ei[x];
-            u64 v = W[swz(x)] + (ev < 0 ? mp.q - (u64)(-ev) : (u64)ev);       // < 2q
-            if (i == (u32)K - 1 && x < fp.msg_used) {
-                u64 m = msg[x];
-                if (__builtin_expect(m >= fp.p, 0)) m %= fp.p;
-                v += fp.delta * m;                                             // delta*m <= q-1
-                v = csub(v, mp.q);
-            }
-            o[1 + ((size_t)i << LOGN) + x] = csub(v, mp.q);
+    }
+    __syncthreads();
+
+    // ---- phase 4: rows of A*s back to coefficients
+    tile_inverse<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
+
+    // ---- phase 5: + e (+ Delta*m), container store
+    u64* o = fp.out + b * (1 + (size_t)K * n);
+    if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
+    const u64* msg = fp.msgs + b * (size_t)fp.msg_len;
+#pragma unroll 4
+    for (u32 idx = threadIdx.x; idx < (u32)K * n; idx += kNttThreads) {
+        const int ev = E[idx];
+        u64 v = S[swz(idx)] + (ev < 0 ? mp.q - (u64)(-ev) : (u64)ev);         // < 2q
+        const u32 x = idx - ((u32)(K - 1) << LOGN);                           // wraps for earlier rows
+        if (idx >= ((u32)(K - 1) << LOGN) && x < fp.msg_used) {
+            u64 m = __ldcs(msg + x);
+            if (__builtin_expect(m >= fp.p, 0)) m %= fp.p;
+            v = csub(v + fp.delta * m, mp.q);                                  // delta*m <= q-1
         }
-        __syncthreads();      // W is rewritten by the next row
+        __stcs(o + 1 + idx, csub(v, mp.q));
     }
 }
 
@@ -125,9 +147,6 @@ static bool build_cdt_param(const LweContext* c, CdtParam& out) {
     return true;
 }
 
-template <int LOGN, int K>
-static constexpr size_t fused_smem() { return ((size_t)(K + 1) << LOGN) * sizeof(u64) + ((size_t)K << LOGN); }
-
 static bool fused_shape_ok(uint32_t logn, uint32_t k) {
     if (logn == 12) return k >= 1 && k <= 4;
     if (logn == 10 || logn == 11 || logn == 13) return k == 2;
@@ -137,21 +156,20 @@ static bool fused_shape_ok(uint32_t logn, uint32_t k) {
 bool fused_commit_supported(const LweContext* c) {
     CdtParam tmp;
     return fused_shape_ok(c->logn, c->k) && c->ntt->mp.lazy_fwd && c->ntt->mp.lazy_inv &&
-           build_cdt_param(c, tmp) && (size_t)c->k * 4 <= 64;
+           build_cdt_param(c, tmp);
 }
 
-// A2 is built lazily from d_A the first time the fused path runs
+// (a, floor(a * 2^64 / q)) pairs of A-hat for the fused kernel's Shoup MACs
 __global__ void shoup_table_kernel(u64 q, const u64* __restrict__ A, size_t total, ulonglong2* __restrict__ A2) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const u64 a = A[i];
-    // floor(a * 2^64 / q) by long division of (a : 0) by q, 64 steps of shift-subtract
+    // long division of (a : 0) by q, 64 shift-subtract steps (q < 2^61, no overflow)
     u64 rem = a % q, quo = 0;
     for (int bit = 0; bit < 64; bit++) {
-        const bool carry = rem >> 63;
         rem <<= 1;
         quo <<= 1;
-        if (carry || rem >= q) { rem -= q; quo |= 1; }
+        if (rem >= q) { rem -= q; quo |= 1; }
     }
     A2[i] = make_ulonglong2(a, quo);
 }
@@ -167,7 +185,7 @@ bool fused_prepare(LweContext* mc, cudaStream_t s) {
 }
 
 template <int LOGN, int K>
-static bool launch_fused(const LweContext* c, const FusedParams& fp, const CdtParam& cdt, size_t count, cudaStream_t s) {
+static bool launch_fused(const FusedParams& fp, const CdtParam& cdt, size_t count, cudaStream_t s) {
     constexpr size_t smem = fused_smem<LOGN, K>();
     const int nch8 = (int)((cdt.count + 7) / 8);
     auto run = [&](auto kernel) -> bool {
@@ -177,7 +195,6 @@ static bool launch_fused(const LweContext* c, const FusedParams& fp, const CdtPa
         kernel<<<(unsigned)count, kNttThreads, smem, s>>>(fp, cdt);
         return cuda_ok(cudaGetLastError(), "fused_commit_kernel launch");
     };
-    (void)c;
     if (nch8 <= 5) return run(fused_commit_kernel<LOGN, K, 5>);
     return run(fused_commit_kernel<LOGN, K, 8>);
 }
@@ -186,6 +203,7 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
                          size_t count, u64* d_out, cudaStream_t s) {
     if (count == 0) return true;
     if (count > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    if (msg_len > 0xffffffffull) { set_error("msg_len too large"); return false; }
     CdtParam cdt;
     if (!build_cdt_param(c, cdt)) { set_error("fused path: CDT too large"); return false; }
     if (!c->d_A2) { set_error("fused path: context not prepared"); return false; }
@@ -201,15 +219,14 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     fp.out = d_out;
     fp.msg_len = (u32)msg_len;
     fp.msg_used = (u32)std::min<size_t>(msg_len, c->n);
-    if (msg_len > 0xffffffffull) { set_error("msg_len too large"); return false; }
     switch (c->logn * 16 + c->k) {
-        case 12 * 16 + 1: return launch_fused<12, 1>(c, fp, cdt, count, s);
-        case 12 * 16 + 2: return launch_fused<12, 2>(c, fp, cdt, count, s);
-        case 12 * 16 + 3: return launch_fused<12, 3>(c, fp, cdt, count, s);
-        case 12 * 16 + 4: return launch_fused<12, 4>(c, fp, cdt, count, s);
-        case 10 * 16 + 2: return launch_fused<10, 2>(c, fp, cdt, count, s);
-        case 11 * 16 + 2: return launch_fused<11, 2>(c, fp, cdt, count, s);
-        case 13 * 16 + 2: return launch_fused<13, 2>(c, fp, cdt, count, s);
+        case 12 * 16 + 1: return launch_fused<12, 1>(fp, cdt, count, s);
+        case 12 * 16 + 2: return launch_fused<12, 2>(fp, cdt, count, s);
+        case 12 * 16 + 3: return launch_fused<12, 3>(fp, cdt, count, s);
+        case 12 * 16 + 4: return launch_fused<12, 4>(fp, cdt, count, s);
+        case 10 * 16 + 2: return launch_fused<10, 2>(fp, cdt, count, s);
+        case 11 * 16 + 2: return launch_fused<11, 2>(fp, cdt, count, s);
+        case 13 * 16 + 2: return launch_fused<13, 2>(fp, cdt, count, s);
         default: set_error("fused path: unsupported (n, k)"); return false;
     }
 }

@@ -28,7 +28,7 @@ imad_peak_kernel(unsigned iters, unsigned seed, unsigned long long* sink) {
 #pragma unroll
             for (int c = 0; c < kChains; c++) {
                 if (WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
-                else      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[c]) : "r"(a), "r"(b));
+                else      asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[c]) : "r"(a), "r"(b));   // d = d*a + b
             }
         }
     }

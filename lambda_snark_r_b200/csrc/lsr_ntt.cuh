@@ -161,7 +161,7 @@ template <> struct plan<13> { static constexpr int N = 4; static constexpr int R
 template <> struct plan<14> { static constexpr int N = 4; static constexpr int R[4] = {4, 3, 3, 4}; };
 
 // ---------------------------------------------------------------------------
-// One pass over a tile held in shared memory.
+// One pass over a tile.
 //   LOGN  : log2 of the full transform size
 //   S     : first forward stage covered by this pass (global numbering)
 //   R     : stages in the pass
@@ -170,9 +170,23 @@ template <> struct plan<14> { static constexpr int N = 4; static constexpr int R
 //   items : work items in the tile = tile_elems >> R
 //   tb    : index of the tile's block within its polynomial (0 when LT==LOGN)
 //           (for multi-polynomial tiles, LT == LOGN and tb == 0)
+//   IN/OUT: where the pass reads / writes its coefficients.  IO_GLOBAL fuses
+//           the HBM load (store) of the tile into the first (last) pass whose
+//           thread->coefficient map is coalesced, so the tile crosses shared
+//           memory one time less.  All global loads of a work item are issued
+//           before any is consumed (16 independent requests per thread).
 // ---------------------------------------------------------------------------
-template <int LOGN, int LT, int S, int R, bool LAZY, bool INVERSE, bool FINAL>
-__device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const NttTables& tb_,
+enum : int { IO_SMEM = 0, IO_GLOBAL = 1 };
+
+struct TileIo {
+    u64* g;        // tile base in global memory (IO_GLOBAL only)
+    u32 valid;     // coefficients of the tile that exist (multiple of 2^LT)
+    u32 sanitize;  // reduce out-of-range inputs on load
+    u64 limit;     // sanitiser threshold
+};
+
+template <int LOGN, int LT, int S, int R, bool LAZY, bool INVERSE, bool FINAL, int IN, int OUT>
+__device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io, const NttTables& tb_,
                                           const ModParams& mp, u32 items, u32 tb) {
     constexpr int LG = LOGN - S - R;          // log2 of the element stride g
     constexpr u32 g = 1u << LG;
@@ -186,9 +200,19 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const NttTables&
         const u32 c = w & (g - 1u);
         const u32 base = (poly << LT) + (blk << (LG + R)) + c;
         const u32 T0 = (1u << S) + (tb << SL) + blk;
+        const bool live = (IN == IO_GLOBAL || OUT == IO_GLOBAL) ? ((poly << LT) < io.valid) : true;
         u64 v[1 << R];
+        if constexpr (IN == IO_GLOBAL) {
 #pragma unroll
-        for (int j = 0; j < (1 << R); j++) v[j] = sm[swz(base + ((u32)j << LG))];
+            for (int j = 0; j < (1 << R); j++) v[j] = live ? __ldcs(io.g + base + ((u32)j << LG)) : 0ull;
+            if (io.sanitize) {
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++) v[j] = sm[swz(base + ((u32)j << LG))];
+        }
         if constexpr (!INVERSE) {
             fwd_network<R, LAZY>(v, tw, T0, mp);
             if (FINAL) {
@@ -200,53 +224,72 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const NttTables&
             static_assert(!INVERSE || !FINAL || S == 0, "final inverse pass must contain stage 0");
             inv_network<R, LAZY, FINAL>(v, tw, T0, sigma0, tb_.n_inv, mp);
         }
+        if constexpr (OUT == IO_GLOBAL) {
+            if (live) {
 #pragma unroll
-        for (int j = 0; j < (1 << R); j++) sm[swz(base + ((u32)j << LG))] = v[j];
+                for (int j = 0; j < (1 << R); j++) __stcs(io.g + base + ((u32)j << LG), v[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < (1 << R); j++) sm[swz(base + ((u32)j << LG))] = v[j];
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
-// All passes of a tile, shared memory to shared memory, with a barrier after
-// each pass.  tile_elems = coefficients resident in `sm` (multiple of 2^LT).
+// All passes of a tile with a barrier after each pass that wrote shared memory.
+// tile_elems = coefficients of the tile (multiple of 2^LT).
 // Forward: stages LOGN-LT .. LOGN-1 (always ends with the final reduction).
 // Inverse: the same stages in reverse; FINAL (n^-1 + correction) iff LT==LOGN.
-// Caller must have synchronised after filling `sm`.
+// GIO = false: shared memory in, shared memory out (caller synchronised after
+//              filling `sm`; used by the fused commitment kernel).
+// GIO = true : forward reads its first pass from global memory and leaves the
+//              result in shared memory (global when the plan has one pass);
+//              inverse expects the tile in shared memory (global when one
+//              pass) and writes its last pass to global memory.
 // ---------------------------------------------------------------------------
-template <int LOGN, int LT, bool LAZY, int I>
-__device__ __forceinline__ void tile_forward_from(u64* sm, const NttTables& t, const ModParams& mp,
-                                                  u32 tile_elems, u32 tb) {
+template <int LOGN, int LT, bool LAZY, bool GIO, int I>
+__device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, const NttTables& t,
+                                                  const ModParams& mp, u32 tile_elems, u32 tb) {
     using P = plan<LT>;
     if constexpr (I < P::N) {
         constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
-        tile_pass<LOGN, LT, S, R, LAZY, false, (I == P::N - 1)>(sm, t, mp, tile_elems >> R, tb);
-        __syncthreads();
-        tile_forward_from<LOGN, LT, LAZY, I + 1>(sm, t, mp, tile_elems, tb);
+        constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
+        constexpr int OUT = (GIO && P::N == 1) ? IO_GLOBAL : IO_SMEM;
+        tile_pass<LOGN, LT, S, R, LAZY, false, (I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
+        if constexpr (OUT == IO_SMEM) __syncthreads();
+        tile_forward_from<LOGN, LT, LAZY, GIO, I + 1>(sm, io, t, mp, tile_elems, tb);
     }
 }
 
-template <int LOGN, int LT, bool LAZY, int I>
-__device__ __forceinline__ void tile_inverse_from(u64* sm, const NttTables& t, const ModParams& mp,
-                                                  u32 tile_elems, u32 tb) {
+template <int LOGN, int LT, bool LAZY, bool GIO, int I>
+__device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, const NttTables& t,
+                                                  const ModParams& mp, u32 tile_elems, u32 tb) {
     using P = plan<LT>;
     if constexpr (I >= 0) {
         constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
-        tile_pass<LOGN, LT, S, R, LAZY, true, (I == 0 && LT == LOGN)>(sm, t, mp, tile_elems >> R, tb);
-        __syncthreads();
-        tile_inverse_from<LOGN, LT, LAZY, I - 1>(sm, t, mp, tile_elems, tb);
+        constexpr int IN = (GIO && P::N == 1) ? IO_GLOBAL : IO_SMEM;
+        constexpr int OUT = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
+        tile_pass<LOGN, LT, S, R, LAZY, true, (I == 0 && LT == LOGN), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
+        if constexpr (OUT == IO_SMEM) __syncthreads();
+        tile_inverse_from<LOGN, LT, LAZY, GIO, I - 1>(sm, io, t, mp, tile_elems, tb);
     }
 }
 
+// shared-memory-only forms (fused commitment kernel)
 template <int LOGN, int LT, bool LAZY>
 __device__ __forceinline__ void tile_forward(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
-    tile_forward_from<LOGN, LT, LAZY, 0>(sm, t, mp, tile_elems, tb);
+    const TileIo io{nullptr, tile_elems, 0u, 0ull};
+    tile_forward_from<LOGN, LT, LAZY, false, 0>(sm, io, t, mp, tile_elems, tb);
 }
 template <int LOGN, int LT, bool LAZY>
 __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
-    tile_inverse_from<LOGN, LT, LAZY, plan<LT>::N - 1>(sm, t, mp, tile_elems, tb);
+    const TileIo io{nullptr, tile_elems, 0u, 0ull};
+    tile_inverse_from<LOGN, LT, LAZY, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb);
 }
 
 // ---------------------------------------------------------------------------
@@ -257,32 +300,54 @@ __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const 
 // LT <  LOGN: a tile is one 2^LT block of a polynomial (big-n second kernel
 //             forward / first kernel inverse); values are already lazy, so the
 //             forward direction must not sanitise.
+// Forward: HBM -> registers (first pass, coalesced) ... last pass -> shared
+//          memory -> coalesced store.  Inverse: coalesced load -> shared memory
+//          -> first pass ... last pass (coalesced map) -> HBM.
 // ---------------------------------------------------------------------------
+template <int LT>
+constexpr int ntt_min_blocks() { return LT <= 12 ? 3 : (LT == 13 ? 2 : 1); }
+
 template <int LOGN, int LT, bool LAZY, bool INVERSE>
-__global__ void __launch_bounds__(kNttThreads)
+__global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
 ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
     constexpr u32 TILE = 1u << TL;
+    constexpr u32 PER_THREAD = TILE / kNttThreads;
+    constexpr bool ONE_PASS = plan<LT>::N == 1;
     const size_t tile0 = (size_t)blockIdx.x << TL;
     const u32 valid = (u32)((total_elems - tile0) < TILE ? (total_elems - tile0) : TILE);
     u64* __restrict__ g = data + tile0;
     const u32 tb = (LT < LOGN) ? (blockIdx.x & ((1u << (LOGN - LT)) - 1u)) : 0u;
     const bool clean = (!INVERSE && LT < LOGN);   // already-lazy values: no sanitiser
-    const u64 limit = INVERSE ? mp.q2 : mp.q4;
+    const TileIo io{g, valid, clean ? 0u : 1u, INVERSE ? mp.q2 : mp.q4};
 
-    for (u32 i = threadIdx.x; i < TILE; i += kNttThreads) {
-        u64 x = 0;
-        if (i < valid) {
-            x = g[i];
-            if (!clean) x = sanitize(x, limit, mp);
+    if constexpr (!INVERSE) {
+        tile_forward_from<LOGN, LT, LAZY, true, 0>(sm, io, tbl, mp, TILE, tb);
+        if constexpr (!ONE_PASS) {
+#pragma unroll 4
+            for (u32 k = 0; k < PER_THREAD; k++) {
+                const u32 i = threadIdx.x + k * kNttThreads;
+                if (i < valid) __stcs(g + i, sm[swz(i)]);
+            }
         }
-        sm[swz(i)] = x;
+    } else {
+        if constexpr (!ONE_PASS) {
+            u64 x[PER_THREAD];
+#pragma unroll
+            for (u32 k = 0; k < PER_THREAD; k++) {
+                const u32 i = threadIdx.x + k * kNttThreads;
+                x[k] = i < valid ? __ldcs(g + i) : 0ull;
+            }
+#pragma unroll
+            for (u32 k = 0; k < PER_THREAD; k++) {
+                const u32 i = threadIdx.x + k * kNttThreads;
+                sm[swz(i)] = sanitize(x[k], io.limit, mp);
+            }
+            __syncthreads();
+        }
+        tile_inverse_from<LOGN, LT, LAZY, true, plan<LT>::N - 1>(sm, io, tbl, mp, TILE, tb);
     }
-    __syncthreads();
-    if (!INVERSE) tile_forward<LOGN, LT, LAZY>(sm, tbl, mp, TILE, tb);
-    else          tile_inverse<LOGN, LT, LAZY>(sm, tbl, mp, TILE, tb);
-    for (u32 i = threadIdx.x; i < valid; i += kNttThreads) g[i] = sm[swz(i)];
 }
 
 // ---------------------------------------------------------------------------

@@ -64,6 +64,31 @@ __device__ __forceinline__ u32 cdt_magnitude(const CdtParam& t, u64 u) {
     return below;
 }
 
+// Same count, ~3x fewer instructions: entries 0..30 live one per lane
+// (lane_entry = cdf[lane], lane 31 unused) and are searched with a 5-step
+// branch-free binary search whose probes are warp shuffles -- no memory access
+// and no branch depends on u, so the constant-time property of the linear scan
+// is kept.  Entries 31.. (mass < 2^-60 for sigma = 3.19) are scanned linearly
+// from the constant bank.  Exactly equal to cdt_magnitude because the table is
+// non-decreasing: #{k : cdf[k] < u} = #{k < 31 : ...} + #{k >= 31 : ...}.
+// Must be called by all 32 lanes of a warp.
+template <int NCH8>
+__device__ __forceinline__ u32 cdt_magnitude_shfl(const CdtParam& t, u64 lane_entry, u64 u) {
+    const u32 e_lo = (u32)lane_entry, e_hi = (u32)(lane_entry >> 32);
+    u32 pos = (t.cdf[15] < u) ? 16u : 0u;          // first probe is the same for every lane
+#pragma unroll
+    for (u32 step = 8; step >= 1; step >>= 1) {
+        const u32 probe = pos + step - 1u;
+        const u32 v_lo = __shfl_sync(0xffffffffu, e_lo, probe);
+        const u32 v_hi = __shfl_sync(0xffffffffu, e_hi, probe);
+        const u64 v = ((u64)v_hi << 32) | v_lo;
+        pos += (v < u) ? step : 0u;
+    }
+#pragma unroll
+    for (int k = 31; k < NCH8 * 8; k++) pos += (u32)(t.cdf[k] < u);
+    return pos;
+}
+
 // table in global memory, any size
 __device__ __forceinline__ u32 cdt_magnitude_global(const u64* __restrict__ cdf, u32 count, u64 u) {
     u32 below = 0;
