@@ -48,10 +48,17 @@ struct ModParams {
 //                sequentially from index 1; re-indexed so both directions
 //                address twiddles the same way); inv[1] is pre-multiplied by
 //                n^-1 (SEAL folds the scalar into the last stage the same way)
+//   fwd_last / inv_last: the twiddles of the unit-stride radix-16 pass (forward
+//                stages logn-4 .. logn-1), transposed to [15][n/16] so that work
+//                item w reads entry [(2^r - 1 + t)][w]: coalesced across a warp
 struct NttTables {
     const ulonglong2* fwd;
     const ulonglong2* inv;
+    const ulonglong2* fwd_last;
+    const ulonglong2* inv_last;
     ulonglong2 n_inv;   // (n^-1, shoup)
+    ulonglong2 head_fwd[16];   // fwd[0..15] / inv[0..15] by value: the twiddles of the
+    ulonglong2 head_inv[16];   // first forward pass are uniform over the whole grid
 };
 
 }  // namespace lsr

@@ -47,6 +47,8 @@ struct NttContext {
     lsr::NttTables tables{};          // device pointers
     ulonglong2* d_fwd = nullptr;
     ulonglong2* d_inv = nullptr;
+    ulonglong2* d_fwd_last = nullptr;
+    ulonglong2* d_inv_last = nullptr;
     cudaStream_t stream = nullptr;    // used by the host-pointer entry points
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};

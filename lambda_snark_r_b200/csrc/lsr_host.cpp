@@ -152,6 +152,22 @@ bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
     }
     out.n_inv.x = n_inv;
     out.n_inv.y = shoup_quotient(n_inv, q);
+    // transposed copy of the unit-stride radix-16 pass (forward stages logn-4 .. logn-1):
+    // work item w, stage r, group t  <-  heap entry ((2^(logn-4) + w) << r) + t
+    out.fwd_last.clear(); out.inv_last.clear();
+    if (logn > 4) {
+        const uint32_t items = n >> 4, first = 1u << (logn - 4);
+        out.fwd_last.assign((size_t)15 * items, ulonglong2{0, 0});
+        out.inv_last.assign((size_t)15 * items, ulonglong2{0, 0});
+        for (uint32_t w = 0; w < items; ++w)
+            for (uint32_t r = 0; r < 4; ++r)
+                for (uint32_t t = 0; t < (1u << r); ++t) {
+                    const size_t dst = (size_t)((1u << r) - 1 + t) * items + w;
+                    const size_t src = ((size_t)(first + w) << r) + t;
+                    out.fwd_last[dst] = out.fwd[src];
+                    out.inv_last[dst] = out.inv[src];
+                }
+    }
     return true;
 }
 

@@ -28,6 +28,7 @@ struct NttHostTables {
     u64 psi = 0;
     std::vector<ulonglong2> fwd;   // [n], index m+g
     std::vector<ulonglong2> inv;   // [n], index m+g, inv[1] scaled by n^-1
+    std::vector<ulonglong2> fwd_last, inv_last;   // [15][n/16] transposed last-pass twiddles (logn > 4)
     ulonglong2 n_inv{0, 0};
 };
 bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out);

@@ -165,11 +165,24 @@ NttContext* ntt_create(u64 q, uint32_t n) {
               cuda_ok(cudaMemcpy(c->d_fwd, ht.fwd.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles") &&
               cuda_ok(cudaMemcpy(c->d_inv, ht.inv.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles") &&
               cuda_ok(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (ok && !ht.fwd_last.empty()) {
+        const size_t lb = sizeof(ulonglong2) * ht.fwd_last.size();
+        ok = cuda_ok(cudaMalloc(&c->d_fwd_last, lb), "cudaMalloc(twiddles)") &&
+             cuda_ok(cudaMalloc(&c->d_inv_last, lb), "cudaMalloc(twiddles)") &&
+             cuda_ok(cudaMemcpy(c->d_fwd_last, ht.fwd_last.data(), lb, cudaMemcpyHostToDevice), "upload twiddles") &&
+             cuda_ok(cudaMemcpy(c->d_inv_last, ht.inv_last.data(), lb, cudaMemcpyHostToDevice), "upload twiddles");
+    }
     for (int i = 0; ok && i < 2; ++i)
         ok = cuda_ok(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
     if (!ok) { ntt_destroy(c); return nullptr; }
     c->tables.fwd = c->d_fwd;
     c->tables.inv = c->d_inv;
+    for (uint32_t i = 0; i < 16; ++i) {
+        c->tables.head_fwd[i] = i < n ? ht.fwd[i] : ulonglong2{0, 0};
+        c->tables.head_inv[i] = i < n ? ht.inv[i] : ulonglong2{0, 0};
+    }
+    c->tables.fwd_last = c->d_fwd_last;
+    c->tables.inv_last = c->d_inv_last;
     c->tables.n_inv = ht.n_inv;
     return c;
 }
@@ -180,6 +193,8 @@ void ntt_destroy(NttContext* c) {
     for (auto& s : c->scratch) s.release();
     if (c->d_fwd) cudaFree(c->d_fwd);
     if (c->d_inv) cudaFree(c->d_inv);
+    if (c->d_fwd_last) cudaFree(c->d_fwd_last);
+    if (c->d_inv_last) cudaFree(c->d_inv_last);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->copy_streams) if (s) cudaStreamDestroy(s);
     delete c;

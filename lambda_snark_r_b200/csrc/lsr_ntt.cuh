@@ -36,14 +36,30 @@ __device__ __forceinline__ ulonglong2 ld_tw(const ulonglong2* p) {
 // One forward stage r of a radix-2^R pass; recursion over r keeps every loop
 // bound a template constant (plain nested `#pragma unroll` loops were being
 // re-rolled by nvcc, which sent v[] to local memory).
-template <int R, int r, bool LAZY>
+//
+// Twiddle addressing.  LL = false: heap layout, entry (T0 << r) + t.  LL = true
+// ("last-pass layout", unit-stride pass where every work item has its own 2^R-1
+// twiddles): entry ((2^r - 1 + t) * stride + T0) of a table transposed on the
+// host so that the 32 lanes of a warp read 32 consecutive 16-byte pairs -- 4
+// L1 wavefronts per load instead of up to 32.  T0 is then the work-item index.
+template <bool LL>
+__device__ __forceinline__ u32 tw_index(u32 T0, int r, int t, u32 stride) {
+    return LL ? ((u32)((1 << r) - 1 + t) * stride + T0) : ((T0 << r) + (u32)t);
+}
+
+// HEAD: the pass starts at forward stage 0 of a whole polynomial, so T0 == 1 and
+// the entries (1 << r) + t are the same for every thread of the grid: they are
+// read from `head`, a by-value kernel parameter (constant bank), and reach the
+// IMADs as uniform operands -- no load, no register, one RF read less each.
+template <int R, int r, bool LAZY, bool LL, bool HEAD>
 __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
-                                          u32 T0, const ModParams& mp) {
+                                          const ulonglong2* __restrict__ head,
+                                          u32 T0, u32 stride, const ModParams& mp) {
     if constexpr (r < R) {
         constexpr int half = 1 << (R - 1 - r);
 #pragma unroll
         for (int t = 0; t < (1 << r); t++) {
-            const ulonglong2 w = ld_tw(tw + ((T0 << r) + t));
+            const ulonglong2 w = HEAD ? head[(1 << r) + t] : ld_tw(tw + tw_index<LL>(T0, r, t, stride));
 #pragma unroll
             for (int jl = 0; jl < half; jl++) {
                 const int j = (t << (R - r)) + jl;
@@ -61,14 +77,15 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        fwd_stage<R, r + 1, LAZY>(v, tw, T0, mp);
+        fwd_stage<R, r + 1, LAZY, LL, HEAD>(v, tw, head, T0, stride, mp);
     }
 }
 
-template <int R, bool LAZY>
+template <int R, bool LAZY, bool LL = false, bool HEAD = false>
 __device__ __forceinline__ void fwd_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
-                                            u32 T0, const ModParams& mp) {
-    fwd_stage<R, 0, LAZY>(v, tw, T0, mp);
+                                            u32 T0, const ModParams& mp, u32 stride = 0,
+                                            const ulonglong2* __restrict__ head = nullptr) {
+    fwd_stage<R, 0, LAZY, LL, HEAD>(v, tw, head, T0, stride, mp);
 }
 
 // last inverse stage (m = 1): scalar n^-1 folded in (SEAL transform_from_rev
@@ -92,9 +109,10 @@ __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglo
 // sigma0 = number of inverse stages already done before this pass (growth
 // bound: a value entering inverse stage sigma is < 4q * 2^sigma on the lazy
 // path).  FINAL: the pass ends with the m = 1 stage (forward stage 0).
-template <int R, int r, bool LAZY, bool FINAL>
+template <int R, int r, bool LAZY, bool FINAL, bool LL, bool HEAD>
 __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
-                                          u32 T0, int sigma0, const ulonglong2 n_inv,
+                                          const ulonglong2* __restrict__ head,
+                                          u32 T0, u32 stride, int sigma0, const ulonglong2 n_inv,
                                           const ModParams& mp) {
     if constexpr (r < R) {
         constexpr int half = 1 << r;
@@ -102,7 +120,7 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
         const u64 C = mp.q4 << (sigma0 + r);
 #pragma unroll
         for (int t = 0; t < (1 << fr); t++) {
-            const ulonglong2 w = ld_tw(tw + ((T0 << fr) + t));
+            const ulonglong2 w = HEAD ? head[(1 << fr) + t] : ld_tw(tw + tw_index<LL>(T0, fr, t, stride));
 #pragma unroll
             for (int jl = 0; jl < half; jl++) {
                 const int j = (t << (r + 1)) + jl;
@@ -121,15 +139,16 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        inv_stage<R, r + 1, LAZY, FINAL>(v, tw, T0, sigma0, n_inv, mp);
+        inv_stage<R, r + 1, LAZY, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
     }
 }
 
-template <int R, bool LAZY, bool FINAL>
+template <int R, bool LAZY, bool FINAL, bool LL = false, bool HEAD = false>
 __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                             u32 T0, int sigma0, const ulonglong2 n_inv,
-                                            const ModParams& mp) {
-    inv_stage<R, 0, LAZY, FINAL>(v, tw, T0, sigma0, n_inv, mp);
+                                            const ModParams& mp, u32 stride = 0,
+                                            const ulonglong2* __restrict__ head = nullptr) {
+    inv_stage<R, 0, LAZY, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
 }
 
 template <bool LAZY>
@@ -192,29 +211,39 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
     constexpr u32 g = 1u << LG;
     constexpr int SL = S - (LOGN - LT);       // stage index local to the block
     static_assert(LG >= 0 && SL >= 0, "bad pass");
-    const ulonglong2* __restrict__ tw = INVERSE ? tb_.inv : tb_.fwd;
+    // unit-stride radix-16 pass of a multi-pass plan: per-work-item twiddles, transposed table
+    constexpr bool LL = (LG == 0) && (R == 4) && (LT > 4);
+    constexpr bool HEAD = (S == 0) && (LT == LOGN) && !LL;     // twiddles 1 .. 2^R - 1, grid-uniform
+    constexpr u32 ll_stride = 1u << (LOGN - R);
+    const ulonglong2* __restrict__ tw = LL ? (INVERSE ? tb_.inv_last : tb_.fwd_last) : (INVERSE ? tb_.inv : tb_.fwd);
     for (u32 W = threadIdx.x; W < items; W += blockDim.x) {
         const u32 poly = W >> (LT - R);                   // polynomial slot within the tile
         const u32 w = W & ((1u << (LT - R)) - 1u);
         const u32 blk = w >> LG;
         const u32 c = w & (g - 1u);
         const u32 base = (poly << LT) + (blk << (LG + R)) + c;
-        const u32 T0 = (1u << S) + (tb << SL) + blk;
+        const u32 T0 = LL ? ((tb << (LT - R)) + w) : ((1u << S) + (tb << SL) + blk);
         const bool live = (IN == IO_GLOBAL || OUT == IO_GLOBAL) ? ((poly << LT) < io.valid) : true;
         u64 v[1 << R];
         if constexpr (IN == IO_GLOBAL) {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = live ? __ldcs(io.g + base + ((u32)j << LG)) : 0ull;
             if (io.sanitize) {
+                // every element <= the OR of all: one test per work item, slow path only if it can matter
+                u64 any = 0;
 #pragma unroll
-                for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
+                for (int j = 0; j < (1 << R); j++) any |= v[j];
+                if (__builtin_expect(any >= io.limit, 0)) {
+#pragma unroll
+                    for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
+                }
             }
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = sm[swz(base + ((u32)j << LG))];
         }
         if constexpr (!INVERSE) {
-            fwd_network<R, LAZY>(v, tw, T0, mp);
+            fwd_network<R, LAZY, LL, HEAD>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
             if (FINAL) {
 #pragma unroll
                 for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<LAZY>(v[j], mp);
@@ -222,7 +251,7 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         } else {
             constexpr int sigma0 = LOGN - S - R;          // inverse stages already done
             static_assert(!INVERSE || !FINAL || S == 0, "final inverse pass must contain stage 0");
-            inv_network<R, LAZY, FINAL>(v, tw, T0, sigma0, tb_.n_inv, mp);
+            inv_network<R, LAZY, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
         }
         if constexpr (OUT == IO_GLOBAL) {
             if (live) {
