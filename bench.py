@@ -114,6 +114,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs ignore it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_commit_rate(target_s: float, threads: int | None = None):
     """Oracle C port (kind "port"), all host threads, bounded sample of the same workload."""
     from oracle import oracle as O
@@ -123,7 +131,7 @@ def cpu_commit_rate(target_s: float, threads: int | None = None):
     except Exception:
         native = False
     ctx = O.OracleLwe(Q_MOD, N_RING, K_RANK, SIGMA, CTX_SEED, native=native)
-    threads = threads or O.max_threads()
+    threads = threads or host_threads()
     rng = np.random.Generator(np.random.PCG64(0x5EED))
 
     def run(count):
@@ -150,7 +158,7 @@ def cpu_ntt_rate(target_s: float, threads: int | None = None):
     except Exception:
         native = False
     ctx = O.OracleNtt(Q_MOD, N_RING, native=native)
-    threads = threads or O.max_threads()
+    threads = threads or host_threads()
     rng = np.random.Generator(np.random.PCG64(0x5EED))
     calib = threads * 64
     x = rng.integers(0, Q_MOD, size=(calib, N_RING), dtype=np.uint64)
@@ -216,6 +224,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     api.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream().cuda_stream
@@ -312,9 +321,14 @@ def run_gpu(args):
                   "GBps_in_per_rank": (world - 1) * GB_ * words * 8 / (gms * 1e-3) / 1e9}
 
     # ---- integer roofline denominator (measured on this GPU)
-    imad_wide = C.c_double(0); mhz = C.c_double(0)
-    capi.load().lsr_measure_imad_peak(1, C.byref(imad_wide), C.byref(mhz))
-    imad_peak = imad_wide.value
+    imad_wide = C.c_double(0); imad_lo = C.c_double(0); mhz = C.c_double(0)
+    capi.load().lsr_measure_imad_peak(0, C.byref(imad_lo), C.byref(mhz))     # IMAD (32-bit result): 64 lanes/clk/SM
+    capi.load().lsr_measure_imad_peak(1, C.byref(imad_wide), None)           # IMAD.WIDE (64-bit result): 32 lanes/clk/SM
+    imad_peak = imad_lo.value
+    # a Shoup modmul on 2-limb residues needs 5 full 32x32->64 products + 4 low products; with IMAD.WIDE at half
+    # rate that is 14 issue slots of the IMAD pipe, not the 10 the SURVEY normalisation assumes
+    wide_cost = imad_lo.value / imad_wide.value if imad_wide.value else 2.0
+    slots_per_modmul = 5 * wide_cost + 4
 
     if rank != 0:
         if world > 1:
@@ -333,7 +347,8 @@ def run_gpu(args):
         return {"value": rate, "unit": "NTT/s", "ms_per_step": ms,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                              "imad_achieved_gimad_s": gimad, "imad_peak_gimad_s": imad_peak,
-                             "imad_frac": gimad / imad_peak if imad_peak else None}}
+                             "imad_frac": gimad / imad_peak if imad_peak else None,
+                             "imad_frac_wide_aware": gimad * slots_per_modmul / IMAD_PER_MODMUL / imad_peak if imad_peak else None}}
 
     # CPU baseline: bounded sample of the same workload on this box's host cores
     cpu_rate, cpu_threads, cpu_count, cpu_dt, native = cpu_commit_rate(args.cpu_seconds)
@@ -353,8 +368,10 @@ def run_gpu(args):
             "binding_bound": "imad (integer multiply pipe), not hbm",
             "imad_achieved_gimad_s": commit_imad, "imad_peak_gimad_s": imad_peak,
             "imad_frac": commit_imad / imad_peak if imad_peak else None,
-            "imad_peak_source": f"lsr_measure_imad_peak on this GPU: dependency-free mad.wide.u32, {imad_wide.value:.0f} GIMAD/s "
-                                f"= 64 lanes/clk/SM at {mhz.value:.0f} MHz",
+            "imad_peak_source": f"lsr_measure_imad_peak on this GPU: IMAD {imad_lo.value:.0f} GIMAD/s (= 64 lanes/clk/SM at "
+                                f"{mhz.value:.0f} MHz), IMAD.WIDE {imad_wide.value:.0f} GIMAD/s",
+            "imad_slots_per_modmul_measured": slots_per_modmul,
+            "imad_frac_wide_aware": B * MODMUL_COMMIT * slots_per_modmul / (ms_step * 1e-3) / 1e9 / imad_peak if imad_peak else None,
             "imad_model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d); sampler not counted",
         },
         "cpu_baseline": {"value": cpu_rate, "unit": "commitments/s", "cores": cpu_threads, "kind": "port",

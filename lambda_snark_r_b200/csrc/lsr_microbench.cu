@@ -14,28 +14,37 @@ namespace lsr {
 constexpr int kChains = 8;     // independent accumulators per thread (latency 4, issue every 2)
 constexpr int kInner = 64;
 
+// Every multiplicand is produced by the previous instruction of a neighbouring
+// chain, so ptxas can neither hoist a product out of the loop nor split the
+// multiply-add (it does both with loop-invariant operands: an earlier version of
+// this kernel ended up timing 64-bit adds).  WIDE: IMAD.WIDE d64 = a*b (full
+// 64-bit product, the form the NTT butterflies use); else IMAD d = a*b + d.
 template <bool WIDE>
 __global__ void __launch_bounds__(256)
-imad_peak_kernel(unsigned iters, unsigned seed, unsigned long long* sink) {
-    unsigned a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 1u;
-    unsigned long long acc[kChains];
-    unsigned lo[kChains];
+imad_peak_kernel(unsigned iters, unsigned seed, unsigned long long* sink, int flag) {
+    unsigned b[kChains], d[kChains];
+    unsigned long long D[kChains];
 #pragma unroll
-    for (int c = 0; c < kChains; c++) { acc[c] = a + c; lo[c] = b + c; }
+    for (int c = 0; c < kChains; c++) {
+        b[c] = (blockIdx.x * 40503u + threadIdx.x * 2654435761u + c * 1315423911u + seed) | 1u;
+        d[c] = b[c] * 7u + c;
+        D[c] = ((unsigned long long)d[c] << 32) | b[c];
+    }
     for (unsigned it = 0; it < iters; it++) {
 #pragma unroll
         for (int r = 0; r < kInner; r++) {
 #pragma unroll
             for (int c = 0; c < kChains; c++) {
-                if (WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
-                else      asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(lo[c]) : "r"(a), "r"(b));   // d = d*a + b
+                const int n = (c + 1) % kChains;
+                if (WIDE) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(D[c]) : "r"((unsigned)(D[n] >> 32)), "r"(b[c]));
+                else      asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(d[c]) : "r"(d[n]), "r"(b[c]));
             }
         }
     }
     unsigned long long s = 0;
 #pragma unroll
-    for (int c = 0; c < kChains; c++) s += acc[c] + lo[c];
-    if (s == 0x123456789abcdefULL) *sink = s;     // never true in practice; defeats DCE
+    for (int c = 0; c < kChains; c++) s += D[c] + d[c];
+    if (flag) sink[threadIdx.x] = s;
 }
 
 }  // namespace lsr
@@ -48,7 +57,7 @@ extern "C" int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_m
     cudaDeviceProp prop;
     if (!cuda_ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return -1;
     unsigned long long* sink = nullptr;
-    if (!cuda_ok(cudaMalloc(&sink, sizeof(*sink)), "cudaMalloc")) return -1;
+    if (!cuda_ok(cudaMalloc(&sink, 256 * sizeof(*sink)), "cudaMalloc")) return -1;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -57,8 +66,8 @@ extern "C" int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_m
     double best = 0.0;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0);
-        if (wide) imad_peak_kernel<true><<<blocks, 256>>>(iters, rep, sink);
-        else      imad_peak_kernel<false><<<blocks, 256>>>(iters, rep, sink);
+        if (wide) imad_peak_kernel<true><<<blocks, 256>>>(iters, rep, sink, 0);
+        else      imad_peak_kernel<false><<<blocks, 256>>>(iters, rep, sink, 0);
         cudaEventRecord(e1);
         if (!cuda_ok(cudaEventSynchronize(e1), "imad_peak_kernel")) { cudaFree(sink); return -1; }
         float ms = 0.f;
