@@ -404,7 +404,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16384, help="commitments per GPU per step")
     ap.add_argument("--ntt-batch", type=int, default=16384, help="polynomials per GPU per NTT step")
-    ap.add_argument("--e2e-batch", type=int, default=4096)
+    ap.add_argument("--e2e-batch", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -282,6 +282,13 @@ int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words,
 int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
                                const uint8_t seed32[32]) LSR_NOEXCEPT;
 
+/* Test hook: CDT magnitude #{k : cdf[k] < u[i]} evaluated on the device for caller-chosen
+ * u (boundary cases the keystream never reaches).  variant 0 = linear scan of the table in
+ * global memory (generic path), 1 = unrolled scan of the by-value table, 2 = warp-shuffle
+ * binary search (fused kernel).  HOST memory.                                        */
+int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out,
+                             int variant) LSR_NOEXCEPT;
+
 /* s, e of the commitment (context, seed): two's-complement, each [k][n];
  * test hook for the fused sampler.  HOST memory.                            */
 int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LSR_NOEXCEPT;

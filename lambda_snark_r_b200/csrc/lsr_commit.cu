@@ -321,9 +321,10 @@ bool lwe_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, c
     return generic_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream);
 }
 
-// Host path: chunks alternate between two streams (H2D msgs+seeds -> kernels ->
-// D2H commitments).  The generic path's S scratch is shared, so with the
-// generic path the two streams are serialised through one stream instead.
+// Host path: chunks of 256 commitments rotate over three streams, each running
+// H2D (messages + seeds) -> kernel(s) -> D2H (containers) in order, so the D2H
+// copy engine -- the bound: 64 KiB out per commitment -- never idles.  The
+// generic path shares one S scratch buffer and therefore stays on one stream.
 bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const u64* seeds,
                      size_t count, u64* out) {
     if (count == 0) return true;
@@ -331,9 +332,10 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
     if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
     const size_t words = lwe_words(c);
     const size_t eff_len = std::max<size_t>(msg_len, 1);
-    const size_t chunk = std::min<size_t>(count, 512);
+    const size_t chunk = std::min<size_t>(count, 256);
     const bool fused = fused_commit_supported(c) && c->commit_path != 1;
-    const int nbuf = (fused && count > chunk) ? 2 : 1;
+    const int nbuf = (fused && count > chunk) ? 3 : 1;
+    cudaStream_t streams[3] = {c->ntt->copy_streams[0], c->ntt->copy_streams[1], c->ntt->stream};
     for (int b = 0; b < nbuf; b++) {
         if (!c->scratch[1 + 3 * b].reserve(chunk * eff_len * sizeof(u64))) return false;
         if (!c->scratch[2 + 3 * b].reserve(chunk * sizeof(u64))) return false;
@@ -343,7 +345,7 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
     int b = 0;
     for (size_t done = 0; ok && done < count; done += chunk) {
         const size_t cnt = std::min(chunk, count - done);
-        cudaStream_t s = nbuf == 1 ? c->ntt->stream : c->ntt->copy_streams[b];
+        cudaStream_t s = nbuf == 1 ? c->ntt->stream : streams[b];
         u64* dm = static_cast<u64*>(c->scratch[1 + 3 * b].ptr);
         u64* ds = static_cast<u64*>(c->scratch[2 + 3 * b].ptr);
         u64* dout = static_cast<u64*>(c->scratch[3 + 3 * b].ptr);
@@ -351,10 +353,10 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
         ok = ok && cuda_ok(cudaMemcpyAsync(ds, seeds + done, cnt * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D seeds") &&
              lwe_commit_launch(c, dm, msg_len, ds, cnt, dout, s) &&
              cuda_ok(cudaMemcpyAsync(out + done * words, dout, cnt * words * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H");
-        if (nbuf == 2) b ^= 1;
+        if (nbuf > 1) b = (b + 1) % nbuf;
     }
-    if (nbuf == 1) ok = cuda_ok(cudaStreamSynchronize(c->ntt->stream), "sync") && ok;
-    else for (int i = 0; i < 2; i++) ok = cuda_ok(cudaStreamSynchronize(c->ntt->copy_streams[i]), "sync") && ok;
+    for (int i = 0; i < (nbuf == 1 ? 1 : 3); i++)
+        ok = cuda_ok(cudaStreamSynchronize(nbuf == 1 ? c->ntt->stream : streams[i]), "sync") && ok;
     return ok;
 }
 

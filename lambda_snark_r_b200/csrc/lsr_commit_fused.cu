@@ -19,6 +19,7 @@
 // ciphertext_to_commitment of the reference (cpp-core/src/commitment.cpp:44-60,
 // 152-156).
 #include <algorithm>
+#include <cstdlib>
 
 #include "lsr_engine.h"
 #include "lsr_ntt.cuh"
@@ -38,6 +39,7 @@ struct FusedParams {
     u64* out;                 // [count][1 + K*n]
     u32 msg_len;              // true stride of msgs
     u32 msg_used;             // min(msg_len, n)
+    u32 skip;                 // PROFILING ONLY (env LSR_FUSED_SKIP): bit i set = phase i+1 not executed; results are garbage
 };
 
 template <int LOGN, int K>
@@ -47,6 +49,26 @@ template <int LOGN, int K>
 constexpr int fused_min_blocks() {
     return fused_smem<LOGN, K>() <= 75 * 1024 ? 3 : (fused_smem<LOGN, K>() <= 113 * 1024 ? 2 : 1);
 }
+
+// value (canonical row coefficient) -> + e_i[x] (+ Delta * (m[x] mod p) on row K-1), reduced
+template <int LOGN, int K>
+struct CommitEpilogue {
+    const signed char* E;
+    const u64* msg;
+    u64 q, delta, p;
+    u32 msg_used;
+    __device__ __forceinline__ u64 operator()(u32 idx, u64 v) const {
+        const int ev = E[idx];
+        v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                // < 2q
+        const u32 x = idx - ((u32)(K - 1) << LOGN);                            // wraps for earlier rows
+        if (idx >= ((u32)(K - 1) << LOGN) && x < msg_used) {
+            u64 m = __ldcs(msg + x);
+            if (__builtin_expect(m >= p, 0)) m %= p;
+            v = csub(v + delta * m, q);                                        // delta*m <= q-1
+        }
+        return csub(v, q);
+    }
+};
 
 template <int LOGN, int K, int NCH8>
 __global__ void __launch_bounds__(kNttThreads, fused_min_blocks<LOGN, K>())
@@ -63,7 +85,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
 
     // ---- phase 1: randomness (DESIGN.md 3.3 layout, same as sample_se_kernel)
-    for (u32 tau = threadIdx.x; tau < (n >> 4); tau += kNttThreads) {
+    for (u32 tau = threadIdx.x; tau < ((fp.skip & 1u) ? 0u : (n >> 4)); tau += kNttThreads) {
         u32 sg[16];
         chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
         static_assert(K <= 4, "sign words 0..3 only");
@@ -94,10 +116,10 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     __syncthreads();
 
     // ---- phase 2: s-hat = NTT(s), all K polynomials as one multi-polynomial tile
-    tile_forward<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
+    if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
 
     // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
-    for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
+    for (u32 x = threadIdx.x; x < ((fp.skip & 4u) ? 0u : n); x += kNttThreads) {
         u64 sv[K];
 #pragma unroll
         for (u32 j = 0; j < (u32)K; j++) sv[j] = S[swz((j << LOGN) + x)];
@@ -114,24 +136,14 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     }
     __syncthreads();
 
-    // ---- phase 4: rows of A*s back to coefficients
-    tile_inverse<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
-
-    // ---- phase 5: + e (+ Delta*m), container store
+    // ---- phase 4+5: rows of A*s back to coefficients; the last inverse pass (coalesced
+    // thread -> coefficient map) adds e (and Delta*m on the last row) in registers and
+    // stores the LweCommitment container straight to HBM
     u64* o = fp.out + b * (1 + (size_t)K * n);
     if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
-    const u64* msg = fp.msgs + b * (size_t)fp.msg_len;
-#pragma unroll 4
-    for (u32 idx = threadIdx.x; idx < (u32)K * n; idx += kNttThreads) {
-        const int ev = E[idx];
-        u64 v = S[swz(idx)] + (ev < 0 ? mp.q - (u64)(-ev) : (u64)ev);         // < 2q
-        const u32 x = idx - ((u32)(K - 1) << LOGN);                           // wraps for earlier rows
-        if (idx >= ((u32)(K - 1) << LOGN) && x < fp.msg_used) {
-            u64 m = __ldcs(msg + x);
-            if (__builtin_expect(m >= fp.p, 0)) m %= fp.p;
-            v = csub(v + fp.delta * m, mp.q);                                  // delta*m <= q-1
-        }
-        __stcs(o + 1 + idx, csub(v, mp.q));
+    if (!(fp.skip & 8u)) {
+        const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.msg_used};
+        tile_inverse_to_global<LOGN, LOGN, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
     }
 }
 
@@ -142,9 +154,50 @@ static bool build_cdt_param(const LweContext* c, CdtParam& out) {
     if (used > (size_t)kCdtInline) return false;
     if (c->cdf.size() - 1 > 127) return false;                // e held as int8
     out.count = (u32)used;
-    out.pad = 0;
     for (int i = 0; i < kCdtInline; i++) out.cdf[i] = (size_t)i < used ? c->cdf[i] : ~0ull;
+    out.pad = 1;
+    for (int i = 31; i < kCdtInline; i++) if ((out.cdf[i] >> 32) != 0xffffffffull) out.pad = 0;
     return true;
+}
+
+// Test hook: evaluates the three CDT searches on caller-supplied u values so that the
+// boundary cases (u = cdf[k] - 1, cdf[k], cdf[k] + 1, including the 2^-60-probability tail
+// the keystream never reaches in a test) can be compared with the reference's linear scan.
+template <int NCH8>
+__global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64* __restrict__ cdf_full, u32 cdf_n,
+                                 const u64* __restrict__ u, size_t count, u32* __restrict__ out, int variant) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // count is padded to a multiple of 32
+    const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const u64 x = i < count ? u[i] : 0;
+    u32 r;
+    if (variant == 0) r = cdt_magnitude_global(cdf_full, cdf_n, x);
+    else if (variant == 1) r = cdt_magnitude<NCH8>(cdt, x);
+    else r = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, x);
+    if (i < count) out[i] = r;
+}
+
+bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant) {
+    LweContext fake;
+    fake.cdf = host::build_cdt(sigma);
+    if (fake.cdf.empty()) return false;
+    CdtParam cdt;
+    const bool inline_ok = build_cdt_param(&fake, cdt);
+    if (variant != 0 && !inline_ok) { set_error("CDT does not fit the inline table"); return false; }
+    if (!cuda_ok(cudaSetDevice(current_device_choice()), "cudaSetDevice")) return false;
+    u64 *d_u = nullptr, *d_cdf = nullptr;
+    u32* d_out = nullptr;
+    bool ok = cuda_ok(cudaMalloc(&d_u, count * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&d_out, count * 4), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&d_cdf, fake.cdf.size() * 8), "cudaMalloc") &&
+              cuda_ok(cudaMemcpy(d_u, u, count * 8, cudaMemcpyHostToDevice), "H2D") &&
+              cuda_ok(cudaMemcpy(d_cdf, fake.cdf.data(), fake.cdf.size() * 8, cudaMemcpyHostToDevice), "H2D");
+    if (ok) {
+        const unsigned blocks = (unsigned)((count + 127) / 128);
+        if (!inline_ok || (cdt.count + 7) / 8 <= 5) cdt_probe_kernel<5><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant);
+        else cdt_probe_kernel<8><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant);
+        ok = cuda_ok(cudaGetLastError(), "cdt_probe_kernel") && cuda_ok(cudaMemcpy(out, d_out, count * 4, cudaMemcpyDeviceToHost), "D2H");
+    }
+    cudaFree(d_u); cudaFree(d_out); cudaFree(d_cdf);
+    return ok;
 }
 
 static bool fused_shape_ok(uint32_t logn, uint32_t k) {
@@ -219,6 +272,8 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     fp.out = d_out;
     fp.msg_len = (u32)msg_len;
     fp.msg_used = (u32)std::min<size_t>(msg_len, c->n);
+    const char* skip = std::getenv("LSR_FUSED_SKIP");
+    fp.skip = skip ? (u32)std::strtoul(skip, nullptr, 0) : 0u;
     switch (c->logn * 16 + c->k) {
         case 12 * 16 + 1: return launch_fused<12, 1>(fp, cdt, count, s);
         case 12 * 16 + 2: return launch_fused<12, 2>(fp, cdt, count, s);

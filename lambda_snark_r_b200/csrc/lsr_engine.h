@@ -74,7 +74,7 @@ struct LweContext {
     lsr::u64* d_cdf = nullptr;        // [cdf.size()]
     int commit_path = 0;              // 0 auto, 1 generic, 2 fused
     mutable std::mutex mu;
-    mutable lsr::DeviceScratch scratch[8];
+    mutable lsr::DeviceScratch scratch[10];
 };
 
 namespace lsr {
@@ -97,6 +97,7 @@ bool lwe_lincomb_host(const LweContext* ctx, const u64* payloads, const u64* coe
 bool lwe_sample_se_host(const LweContext* ctx, u64 seed, int64_t* s, int64_t* e);
 bool sample_gaussian_host(u64* out, size_t len, double sigma, const uint8_t seed32[32]);
 bool fused_commit_supported(const LweContext* ctx);
+bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant);
 
 NttContext* ntt_create(u64 q, uint32_t n);
 void ntt_destroy(NttContext* ctx);

@@ -92,12 +92,14 @@ static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_
     return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
 }
 
-// n <= 2^14: one kernel, the polynomial never leaves shared memory.
-// n >  2^14: column kernel (first LOGN-12 stages) + tile kernel on 4096-blocks.
+// n <= 2^13: one kernel, the polynomial never leaves shared memory.
+// n >= 2^14: column kernel (first LOGN-12 stages) + tile kernel on 4096-blocks.
+// (n = 2^14 fits one CTA's shared memory, but at one 8-warp CTA per SM it ran at
+// 625 G butterflies/s against 800 for the two-kernel path: profiles/r01_ntt_sweep.json)
 template <int LOGN, bool INV>
 static bool launch_transform(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
     const size_t total = batch << LOGN;
-    if constexpr (LOGN <= 14) {
+    if constexpr (LOGN <= 13) {
         return launch_tile<LOGN, LOGN, INV>(c, d, total, s);
     } else {
         constexpr int S = LOGN - 12;
@@ -108,6 +110,10 @@ static bool launch_transform(const NttContext* c, u64* d, size_t batch, cudaStre
 
 template <bool INV>
 static bool dispatch(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    if (reinterpret_cast<uintptr_t>(d) & 15u) {     // unit-stride passes use 16-byte global accesses
+        set_error("device polynomial buffer must be 16-byte aligned");
+        return false;
+    }
     switch (c->logn) {
         case 1: return launch_transform<1, INV>(c, d, batch, s);
         case 2: return launch_transform<2, INV>(c, d, batch, s);

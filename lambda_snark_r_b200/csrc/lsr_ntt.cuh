@@ -13,7 +13,22 @@
 // touch shared memory.  The XOR swizzle below makes every pass of the plans
 // chosen in plan_for() bank-conflict free.
 #pragma once
+#include <type_traits>
+
 #include "lsr_arith.cuh"
+
+// Unit-stride pass talking to HBM directly with 16-byte accesses instead of restaging
+// through shared memory.  Measured at n = 4096 (tools/ntt_variant_bench.cu): the forward
+// store gains 3 % (36.6 vs 35.4 M NTT/s), the inverse load loses 3 % (33.4 vs 34.5).
+#ifndef LSR_NTT_DIRECT_OUT
+#define LSR_NTT_DIRECT_OUT 1
+#endif
+#ifndef LSR_NTT_DIRECT_IN
+#define LSR_NTT_DIRECT_IN 0
+#endif
+#ifndef LSR_NTT_MINB      // tools/ntt_variant_bench.cu overrides this to explore occupancy
+#define LSR_NTT_MINB 3
+#endif
 
 namespace lsr {
 
@@ -204,9 +219,14 @@ struct TileIo {
     u64 limit;     // sanitiser threshold
 };
 
-template <int LOGN, int LT, int S, int R, bool LAZY, bool INVERSE, bool FINAL, int IN, int OUT>
+// Epilogue hook for the pass that stores to global memory: value = epi(tile index, value).
+struct NoEpilogue {
+    __device__ __forceinline__ u64 operator()(u32, u64 v) const { return v; }
+};
+
+template <int LOGN, int LT, int S, int R, bool LAZY, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io, const NttTables& tb_,
-                                          const ModParams& mp, u32 items, u32 tb) {
+                                          const ModParams& mp, u32 items, u32 tb, const Epi& epi = Epi()) {
     constexpr int LG = LOGN - S - R;          // log2 of the element stride g
     constexpr u32 g = 1u << LG;
     constexpr int SL = S - (LOGN - LT);       // stage index local to the block
@@ -225,7 +245,24 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         const u32 T0 = LL ? ((tb << (LT - R)) + w) : ((1u << S) + (tb << SL) + blk);
         const bool live = (IN == IO_GLOBAL || OUT == IO_GLOBAL) ? ((poly << LT) < io.valid) : true;
         u64 v[1 << R];
-        if constexpr (IN == IO_GLOBAL) {
+        if constexpr (IN == IO_GLOBAL && LG == 0 && R >= 1) {
+            // unit-stride pass: each thread owns 2^R consecutive coefficients -> 16-byte accesses
+            const ulonglong2* __restrict__ gp = reinterpret_cast<const ulonglong2*>(io.g + base);
+#pragma unroll
+            for (int j = 0; j < (1 << R); j += 2) {
+                const ulonglong2 t2 = live ? __ldcs(gp + (j >> 1)) : make_ulonglong2(0ull, 0ull);
+                v[j] = t2.x; v[j + 1] = t2.y;
+            }
+            if (io.sanitize) {
+                u64 any = 0;
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) any |= v[j];
+                if (__builtin_expect(any >= io.limit, 0)) {
+#pragma unroll
+                    for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
+                }
+            }
+        } else if constexpr (IN == IO_GLOBAL) {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = live ? __ldcs(io.g + base + ((u32)j << LG)) : 0ull;
             if (io.sanitize) {
@@ -253,10 +290,19 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
             static_assert(!INVERSE || !FINAL || S == 0, "final inverse pass must contain stage 0");
             inv_network<R, LAZY, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
         }
-        if constexpr (OUT == IO_GLOBAL) {
+        if constexpr (OUT == IO_GLOBAL && LG == 0 && R >= 1 && std::is_same<Epi, NoEpilogue>::value) {
+            if (live) {
+                ulonglong2* __restrict__ gp = reinterpret_cast<ulonglong2*>(io.g + base);
+#pragma unroll
+                for (int j = 0; j < (1 << R); j += 2) __stcs(gp + (j >> 1), make_ulonglong2(v[j], v[j + 1]));
+            }
+        } else if constexpr (OUT == IO_GLOBAL) {
             if (live) {
 #pragma unroll
-                for (int j = 0; j < (1 << R); j++) __stcs(io.g + base + ((u32)j << LG), v[j]);
+                for (int j = 0; j < (1 << R); j++) {
+                    const u32 idx = base + ((u32)j << LG);
+                    __stcs(io.g + idx, epi(idx, v[j]));
+                }
             }
         } else {
 #pragma unroll
@@ -285,25 +331,26 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
-        constexpr int OUT = (GIO && P::N == 1) ? IO_GLOBAL : IO_SMEM;
+        constexpr int OUT = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_OUT && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
         tile_pass<LOGN, LT, S, R, LAZY, false, (I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
         if constexpr (OUT == IO_SMEM) __syncthreads();
         tile_forward_from<LOGN, LT, LAZY, GIO, I + 1>(sm, io, t, mp, tile_elems, tb);
     }
 }
 
-template <int LOGN, int LT, bool LAZY, bool GIO, int I>
+template <int LOGN, int LT, bool LAZY, bool GIO, int I, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, const NttTables& t,
-                                                  const ModParams& mp, u32 tile_elems, u32 tb) {
+                                                  const ModParams& mp, u32 tile_elems, u32 tb,
+                                                  const Epi& epi = Epi()) {
     using P = plan<LT>;
     if constexpr (I >= 0) {
         constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
-        constexpr int IN = (GIO && P::N == 1) ? IO_GLOBAL : IO_SMEM;
+        constexpr int IN = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_IN && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LOGN, LT, S, R, LAZY, true, (I == 0 && LT == LOGN), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
+        tile_pass<LOGN, LT, S, R, LAZY, true, (I == 0 && LT == LOGN), IN, OUT, Epi>(sm, io, t, mp, tile_elems >> R, tb, epi);
         if constexpr (OUT == IO_SMEM) __syncthreads();
-        tile_inverse_from<LOGN, LT, LAZY, GIO, I - 1>(sm, io, t, mp, tile_elems, tb);
+        tile_inverse_from<LOGN, LT, LAZY, GIO, I - 1, Epi>(sm, io, t, mp, tile_elems, tb, epi);
     }
 }
 
@@ -321,6 +368,16 @@ __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const 
     tile_inverse_from<LOGN, LT, LAZY, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb);
 }
 
+// shared memory in, last pass straight to global memory through an epilogue
+// (fused commitment kernel: + e, + Delta*m, container store); needs a multi-pass plan
+template <int LOGN, int LT, bool LAZY, typename Epi>
+__device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const NttTables& t, const ModParams& mp,
+                                                       u32 tile_elems, const Epi& epi) {
+    static_assert(plan<LT>::N > 1, "single-pass plans read from global memory");
+    const TileIo io{g, tile_elems, 0u, 0ull};
+    tile_inverse_from<LOGN, LT, LAZY, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, epi);
+}
+
 // ---------------------------------------------------------------------------
 // K1 / K2: batched transform, one tile (>= 4096 coefficients) per CTA.
 //   data        : [batch][n] contiguous u64, transformed in place
@@ -334,7 +391,7 @@ __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const 
 //          -> first pass ... last pass (coalesced map) -> HBM.
 // ---------------------------------------------------------------------------
 template <int LT>
-constexpr int ntt_min_blocks() { return LT <= 12 ? 3 : (LT == 13 ? 2 : 1); }
+constexpr int ntt_min_blocks() { return LT <= 12 ? LSR_NTT_MINB : (LT == 13 ? 2 : 1); }
 
 template <int LOGN, int LT, bool LAZY, bool INVERSE>
 __global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
@@ -353,7 +410,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 
     if constexpr (!INVERSE) {
         tile_forward_from<LOGN, LT, LAZY, true, 0>(sm, io, tbl, mp, TILE, tb);
-        if constexpr (!ONE_PASS) {
+        if constexpr (!ONE_PASS && !LSR_NTT_DIRECT_OUT) {
 #pragma unroll 4
             for (u32 k = 0; k < PER_THREAD; k++) {
                 const u32 i = threadIdx.x + k * kNttThreads;
@@ -361,7 +418,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
             }
         }
     } else {
-        if constexpr (!ONE_PASS) {
+        if constexpr (!ONE_PASS && !LSR_NTT_DIRECT_IN) {
             u64 x[PER_THREAD];
 #pragma unroll
             for (u32 k = 0; k < PER_THREAD; k++) {

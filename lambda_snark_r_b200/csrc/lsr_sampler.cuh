@@ -51,7 +51,7 @@ __device__ __forceinline__ void chacha_block(const ChaChaKey& key, u32 w12, u32 
 constexpr int kCdtInline = 64;
 struct CdtParam {
     u32 count;                 // entries in use (<= kCdtInline); trailing 2^64-1 entries trimmed
-    u32 pad;
+    u32 pad;                   // 1 if every entry with index >= 31 has high word 0xffffffff (32-bit tail scan)
     u64 cdf[kCdtInline];       // unused entries = 2^64-1 (never "below u")
 };
 
@@ -84,8 +84,19 @@ __device__ __forceinline__ u32 cdt_magnitude_shfl(const CdtParam& t, u64 lane_en
         const u64 v = ((u64)v_hi << 32) | v_lo;
         pos += (v < u) ? step : 0u;
     }
+    if (t.pad) {
+        // every entry from 31 on has an all-ones high word (true for sigma = 3.19: 1 - cdf[31] < 2^-32), so
+        // cdf[k] < u  <=>  u_hi == 0xffffffff and cdf_lo[k] < u_lo: 32-bit compares, one gate at the end.
+        // t.pad is a property of the table (uniform over the grid), not of u.
+        const u32 u_lo = (u32)u, u_hi = (u32)(u >> 32);
+        u32 tail = 0;
 #pragma unroll
-    for (int k = 31; k < NCH8 * 8; k++) pos += (u32)(t.cdf[k] < u);
+        for (int k = 31; k < NCH8 * 8; k++) tail += (u32)((u32)t.cdf[k] < u_lo);
+        pos += (u_hi == 0xffffffffu) ? tail : 0u;
+    } else {
+#pragma unroll
+        for (int k = 31; k < NCH8 * 8; k++) pos += (u32)(t.cdf[k] < u);
+    }
     return pos;
 }
 

@@ -326,3 +326,24 @@ def test_sample_gaussian_reference_tests(gpu):
     pos, neg = int((x > 0).sum()), int((x < 0).sum())
     assert pos > 1024 and neg > 1024 and abs(pos - neg) < 4096 // 5
     assert not np.array_equal(api.sample_gaussian(64, 3.2), api.sample_gaussian(64, 3.2))   # fresh entropy per call
+
+
+def test_cdt_search_variants_on_boundaries(gpu, rng):
+    """Every device CDT search against the reference's linear scan (oracle, itself pinned to utils.cpp) on the
+    boundary values of the table -- including the all-ones-high-word tail that random keystreams never reach."""
+    lib = capi.load()
+    for sigma in (3.19, 3.2, 1.0, 5.0):
+        cdf = O.cdt_build(sigma)
+        us = [0, 1, 2**64 - 1, 2**64 - 2, 2**63, 0xFFFFFFFF00000000, 0xFFFFFFFEFFFFFFFF, 0xFFFFFFFF00000001]
+        for v in cdf:
+            us += [(int(v) + d) % 2**64 for d in (-2, -1, 0, 1, 2)]
+        us += [int(x) for x in rng.integers(0, 2**64, 500, dtype=np.uint64)]
+        us += [int(x) | 0xFFFFFFFF00000000 for x in rng.integers(0, 2**32, 500, dtype=np.uint64)]   # tail region
+        u = np.array(us, dtype=np.uint64)
+        want = np.array([abs(O.cdt_sample(cdf, int(x), 0)) for x in u], dtype=np.uint32)
+        for variant in (0, 1, 2):
+            out = np.zeros(u.size, dtype=np.uint32)
+            rc = lib.lsr_cdt_magnitude_device(sigma, u.ctypes.data_as(capi.u64p), u.size,
+                                              out.ctypes.data_as(C.POINTER(C.c_uint32)), variant)
+            assert rc == 0, (sigma, variant)
+            assert np.array_equal(out, want), (sigma, variant, np.nonzero(out != want)[0][:5])
