@@ -253,6 +253,16 @@ size_t   lsr_lwe_commitment_words(const LweContext* ctx) LSR_NOEXCEPT; /* 1 + k*
 /* copies A-hat ([k][k][n], NTT domain) to host memory; for cross-checks */
 int      lsr_lwe_copy_matrix(const LweContext* ctx, uint64_t* out) LSR_NOEXCEPT;
 
+/* Arithmetic of the NTT butterflies (NttContext, and the NttContext inside an
+ * LweContext): 0 auto -- FP64-pipe butterflies (exact modular products by
+ * error-free fma multiplication) when q < 2^45, else u64 Shoup butterflies;
+ * 1 u64 arithmetic only; 2 require FP64 (-1 if q >= 2^45).  Results are
+ * bit-identical either way; the switch exists for cross-checks and benchmarks.
+ * lsr_ntt_arith returns the policy in effect (1 or 2).                        */
+int lsr_ntt_set_arith(NttContext* ctx, int arith) LSR_NOEXCEPT;
+int lsr_ntt_arith(const NttContext* ctx) LSR_NOEXCEPT;
+int lsr_lwe_set_arith(LweContext* ctx, int arith) LSR_NOEXCEPT;
+
 /* Path selection for lwe_commit_batch*: 0 auto, 1 force the generic
  * multi-kernel path, 2 force the fused kernel (-1 at call time if it does
  * not support the context's (n, k, sigma)).                                 */

@@ -85,6 +85,16 @@ class NttContext:
     def root(self) -> int:
         return int(_lib().lsr_ntt_root(self._h))
 
+    def set_arith(self, arith: int) -> None:
+        """0 auto, 1 u64 butterflies only, 2 require the FP64-pipe butterflies (q < 2^45)."""
+        if _lib().lsr_ntt_set_arith(self._h, arith) != 0:
+            raise LambdaSnarkError("lsr_ntt_set_arith failed")
+
+    @property
+    def arith(self) -> int:
+        """Policy in effect: 1 = u64 Shoup butterflies, 2 = FP64 butterflies."""
+        return int(_lib().lsr_ntt_arith(self._h))
+
     # single-polynomial drop-in calls (in place on a copy)
     def forward(self, coeffs) -> np.ndarray:
         a = _u64(coeffs).copy()
@@ -202,6 +212,11 @@ class LweContext:
             self._h = None
 
     __del__ = close
+
+    def set_arith(self, arith: int) -> None:
+        """Arithmetic of the NTT butterflies inside the commitment kernels (see NttContext.set_arith)."""
+        if _lib().lsr_lwe_set_arith(self._h, arith) != 0:
+            raise LambdaSnarkError("lsr_lwe_set_arith failed")
 
     def set_commit_path(self, path: int) -> None:
         if _lib().lsr_lwe_set_commit_path(self._h, path) != 0:

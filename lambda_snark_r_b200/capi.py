@@ -90,6 +90,9 @@ SIGNATURES = {
     "lsr_lwe_commitment_words": (C.c_size_t, [C.c_void_p]),
     "lsr_lwe_copy_matrix": (C.c_int, [C.c_void_p, u64p]),
     "lsr_lwe_set_commit_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
+    "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
+    "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lwe_commit_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lsr_lwe_commit_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                C.c_void_p, C.c_void_p]),

@@ -195,6 +195,23 @@ int lsr_lwe_set_commit_path(LweContext* ctx, int path) LSR_NOEXCEPT {
     return 0;
 }
 
+int lsr_ntt_set_arith(NttContext* ctx, int arith) LSR_NOEXCEPT {
+    if (!ctx || arith < 0 || arith > 2) return -1;
+    if (arith == 2 && !ctx->mp.f64_ok) return -1;         // FP64 butterflies are exact only for q < 2^45
+    ctx->arith = arith == 2 ? 0 : arith;                  // 0 (auto) already picks FP64 whenever it is exact
+    return 0;
+}
+
+int lsr_ntt_arith(const NttContext* ctx) LSR_NOEXCEPT {
+    if (!ctx) return -1;
+    return (ctx->arith != 1 && ctx->mp.f64_ok) ? 2 : 1;
+}
+
+int lsr_lwe_set_arith(LweContext* ctx, int arith) LSR_NOEXCEPT {
+    if (!ctx) return -1;
+    return lsr_ntt_set_arith(ctx->ntt, arith);
+}
+
 LweCommitment* lwe_commit(LweContext* ctx, const uint64_t* message, size_t msg_len, uint64_t seed) LSR_NOEXCEPT {
     LSR_TRY
     if (!ctx || !message) return nullptr;                 // commitment.cpp:144

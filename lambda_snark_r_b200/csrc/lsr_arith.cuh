@@ -123,6 +123,52 @@ __device__ __forceinline__ u64 sanitize(u64 x, u64 limit, const ModParams& mp) {
     return x;
 }
 
+// ---------------------------------------------------------------------------
+// POL_F64: residues as doubles.  Every value is an integer-valued double with
+// |x| < 2^51; products are formed exactly with the fma error-free
+// transformation, so the results are exact integers mod q whatever the
+// rounding of the quotient estimate does -- the estimate only decides which
+// representative comes out.  Nothing here is approximate.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double as_d(u64 x) { return __longlong_as_double((long long)x); }
+__device__ __forceinline__ u64 as_u(double x) { return (u64)__double_as_longlong(x); }
+
+constexpr double kRintMagic = 6755399441055744.0;   // 1.5 * 2^52: (v + M) - M = rint(v) for |v| < 2^51
+constexpr double kTwo52 = 4503599627370496.0;
+constexpr u64 kTwo52Bits = 0x4330000000000000ull;   // bit pattern of 2^52
+
+// x * w - c * q with c = rint(x * wq), wq = RN(w / q), 0 <= w < q < 2^45, |x| < 2^51.
+//   c  : (x*wq + M) is computed exactly and rounded to the unit grid, so |c - x*wq| <= 1/2 and
+//        |c - x*w/q| <= 1/2 + |x| 2^-53
+//   h,l: h + l = x*w exactly (l = fma(x, w, -h) is the rounding error of the product)
+//   r  : h is an integer (a product of integers, rounded to a coarser grid when >= 2^53) and
+//        |h - c*q| < 2^53, so the fma is exact; r + l = x*w - c*q is an integer below q in
+//        magnitude, exact again.
+// Result: balanced representative, |result| <= q (1/2 + |x| 2^-53) <= 0.75 q.   6 FP64 instructions.
+__device__ __forceinline__ double mulmod_f(double x, double w, double wq, double q) {
+    const double c = __dadd_rn(__fma_rn(x, wq, kRintMagic), -kRintMagic);
+    const double h = __dmul_rn(x, w);
+    const double l = __fma_rn(x, w, -h);
+    const double r = __fma_rn(-c, q, h);
+    return __dadd_rn(r, l);
+}
+
+// |x| < 2^51  ->  balanced representative, |result| <= q (1/2 + |x| 2^-53).   3 FP64 instructions.
+__device__ __forceinline__ double reduce_f(double x, double invq, double q) {
+    const double c = __dadd_rn(__fma_rn(x, invq, kRintMagic), -kRintMagic);
+    return __fma_rn(-c, q, x);
+}
+
+// integer x < 2^52 -> double, without the (quarter-rate) conversion instruction
+__device__ __forceinline__ double u64_to_f(u64 x) { return __dadd_rn(as_d(x | kTwo52Bits), -kTwo52); }
+
+// integer-valued r in (-q, q) -> canonical residue in [0, q) as u64.  The comparison (not the
+// sign bit) decides, so a negative zero cannot come out as q.
+__device__ __forceinline__ u64 f_to_canonical(double r, const ModParams& mp) {
+    const double off = r < 0.0 ? mp.q52 : kTwo52;
+    return as_u(__dadd_rn(r, off)) & 0x000fffffffffffffull;
+}
+
 // modular add/sub on canonical residues
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }

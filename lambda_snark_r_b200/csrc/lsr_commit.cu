@@ -273,6 +273,7 @@ void lwe_destroy(LweContext* c) {
     if (c->d_zh) { cudaMemset(c->d_zh, 0, (size_t)std::max<uint32_t>(c->k - 1, 1) * c->n * sizeof(u64)); cudaFree(c->d_zh); }
     if (c->d_A) cudaFree(c->d_A);
     if (c->d_A2) cudaFree(c->d_A2);
+    if (c->d_A2f) cudaFree(c->d_A2f);
     if (c->d_cdf) cudaFree(c->d_cdf);
     for (auto& s : c->scratch) s.release();
     ntt_destroy(c->ntt);

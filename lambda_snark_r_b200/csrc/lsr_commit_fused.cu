@@ -31,7 +31,7 @@ struct FusedParams {
     ModParams mp;
     NttTables tbl;
     ChaChaKey key;
-    const ulonglong2* A2;     // [K][K][n]  (a, floor(a*2^64/q)), NTT domain
+    const ulonglong2* A2;     // [K][K][n]  NTT domain; (a, floor(a*2^64/q)), or for POL_F64 the doubles (a, a/q)
     u64 delta;
     u64 p;
     const u64* msgs;          // [count][msg_len]
@@ -70,7 +70,7 @@ struct CommitEpilogue {
     }
 };
 
-template <int LOGN, int K, int NCH8>
+template <int LOGN, int K, int NCH8, int POL>
 __global__ void __launch_bounds__(kNttThreads, fused_min_blocks<LOGN, K>())
 fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CdtParam cdt) {
     constexpr u32 n = 1u << LOGN;
@@ -105,7 +105,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
                     const u32 j = 8 * h + w;
                     const u32 sign = (sbits >> j) & 1u;
                     if (P < K) {
-                        S[swz((P << LOGN) + 16u * tau + j)] = signed_residue(mag, sign, mp.q);
+                        S[swz((P << LOGN) + 16u * tau + j)] =
+                            POL == POL_F64 ? as_u((double)(int)signed_value(mag, sign)) : signed_residue(mag, sign, mp.q);
                     } else {
                         E[((P - K) << LOGN) + 16u * tau + j] = (signed char)signed_value(mag, sign);
                     }
@@ -116,7 +117,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     __syncthreads();
 
     // ---- phase 2: s-hat = NTT(s), all K polynomials as one multi-polynomial tile
-    if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, true>(S, fp.tbl, mp, (u32)K * n, 0u);
+    // (POL_F64: evaluations stay unreduced, |s-hat| < (1 + 0.75 logn) q; the mat-vec product reduces)
+    if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, POL>(S, fp.tbl, mp, (u32)K * n, 0u);
 
     // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
     for (u32 x = threadIdx.x; x < ((fp.skip & 4u) ? 0u : n); x += kNttThreads) {
@@ -125,13 +127,23 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         for (u32 j = 0; j < (u32)K; j++) sv[j] = S[swz((j << LOGN) + x)];
 #pragma unroll
         for (u32 i = 0; i < (u32)K; i++) {
-            u64 acc = 0;
+            if (POL == POL_F64) {
+                double acc = 0.0;
 #pragma unroll
-            for (u32 j = 0; j < (u32)K; j++) {
-                const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
-                acc += mulred4(sv[j], a.x, a.y, mp.nq);                       // each term < 4q
+                for (u32 j = 0; j < (u32)K; j++) {
+                    const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
+                    acc = __dadd_rn(acc, mulmod_f(as_d(sv[j]), as_d(a.x), as_d(a.y), mp.qd));   // each term <= 0.75 q
+                }
+                S[swz((i << LOGN) + x)] = as_u(acc);                           // |acc| <= 0.75 K q <= 3 q
+            } else {
+                u64 acc = 0;
+#pragma unroll
+                for (u32 j = 0; j < (u32)K; j++) {
+                    const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
+                    acc += mulred4(sv[j], a.x, a.y, mp.nq);                   // each term < 4q
+                }
+                S[swz((i << LOGN) + x)] = reduce_small(acc, mp);               // 4Kq <= 16q < 2^7 q
             }
-            S[swz((i << LOGN) + x)] = reduce_small(acc, mp);                   // 4Kq <= 16q < 2^7 q
         }
     }
     __syncthreads();
@@ -143,7 +155,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
     if (!(fp.skip & 8u)) {
         const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.msg_used};
-        tile_inverse_to_global<LOGN, LOGN, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
+        tile_inverse_to_global<LOGN, LOGN, POL>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
     }
 }
 
@@ -208,8 +220,8 @@ static bool fused_shape_ok(uint32_t logn, uint32_t k) {
 
 bool fused_commit_supported(const LweContext* c) {
     CdtParam tmp;
-    return fused_shape_ok(c->logn, c->k) && c->ntt->mp.lazy_fwd && c->ntt->mp.lazy_inv &&
-           build_cdt_param(c, tmp);
+    const bool arith_ok = (c->ntt->mp.lazy_fwd && c->ntt->mp.lazy_inv) || (c->ntt->mp.f64_ok && c->ntt->arith != 1);
+    return fused_shape_ok(c->logn, c->k) && arith_ok && build_cdt_param(c, tmp);
 }
 
 // (a, floor(a * 2^64 / q)) pairs of A-hat for the fused kernel's Shoup MACs
@@ -227,18 +239,32 @@ __global__ void shoup_table_kernel(u64 q, const u64* __restrict__ A, size_t tota
     A2[i] = make_ulonglong2(a, quo);
 }
 
+// (a, a / q) as doubles for the POL_F64 mat-vec (a < 2^45 converts exactly; IEEE division)
+__global__ void f64_table_kernel(double qd, const u64* __restrict__ A, size_t total, ulonglong2* __restrict__ A2f) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double a = (double)A[i];
+    A2f[i] = make_ulonglong2(as_u(a), as_u(__ddiv_rn(a, qd)));
+}
+
 // called once from lwe_create (context set-up), so launches never race on it
 bool fused_prepare(LweContext* mc, cudaStream_t s) {
     const LweContext* c = mc;
-    if (c->d_A2 || !fused_commit_supported(c)) return true;
+    if (c->d_A2 || !fused_shape_ok(c->logn, c->k)) return true;
     const size_t total = (size_t)c->k * c->k * c->n;
     if (!cuda_ok(cudaMalloc(&mc->d_A2, total * sizeof(ulonglong2)), "cudaMalloc(A2)")) { mc->d_A2 = nullptr; return false; }
     shoup_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->q, c->d_A, total, mc->d_A2);
-    return cuda_ok(cudaGetLastError(), "shoup_table_kernel");
+    if (!cuda_ok(cudaGetLastError(), "shoup_table_kernel")) return false;
+    if (c->ntt->mp.f64_ok) {
+        if (!cuda_ok(cudaMalloc(&mc->d_A2f, total * sizeof(ulonglong2)), "cudaMalloc(A2f)")) { mc->d_A2f = nullptr; return false; }
+        f64_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->ntt->mp.qd, c->d_A, total, mc->d_A2f);
+        if (!cuda_ok(cudaGetLastError(), "f64_table_kernel")) return false;
+    }
+    return true;
 }
 
-template <int LOGN, int K>
-static bool launch_fused(const FusedParams& fp, const CdtParam& cdt, size_t count, cudaStream_t s) {
+template <int LOGN, int K, int POL>
+static bool launch_fused_pol(const FusedParams& fp, const CdtParam& cdt, size_t count, cudaStream_t s) {
     constexpr size_t smem = fused_smem<LOGN, K>();
     const int nch8 = (int)((cdt.count + 7) / 8);
     auto run = [&](auto kernel) -> bool {
@@ -248,8 +274,14 @@ static bool launch_fused(const FusedParams& fp, const CdtParam& cdt, size_t coun
         kernel<<<(unsigned)count, kNttThreads, smem, s>>>(fp, cdt);
         return cuda_ok(cudaGetLastError(), "fused_commit_kernel launch");
     };
-    if (nch8 <= 5) return run(fused_commit_kernel<LOGN, K, 5>);
-    return run(fused_commit_kernel<LOGN, K, 8>);
+    if (nch8 <= 5) return run(fused_commit_kernel<LOGN, K, 5, POL>);
+    return run(fused_commit_kernel<LOGN, K, 8, POL>);
+}
+
+template <int LOGN, int K>
+static bool launch_fused(const FusedParams& fp, const CdtParam& cdt, size_t count, cudaStream_t s, bool f64) {
+    if (f64) return launch_fused_pol<LOGN, K, POL_F64>(fp, cdt, count, s);
+    return launch_fused_pol<LOGN, K, POL_LAZY>(fp, cdt, count, s);
 }
 
 bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
@@ -260,11 +292,13 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     CdtParam cdt;
     if (!build_cdt_param(c, cdt)) { set_error("fused path: CDT too large"); return false; }
     if (!c->d_A2) { set_error("fused path: context not prepared"); return false; }
+    const bool f64 = c->ntt->mp.f64_ok && c->ntt->arith != 1;
+    if (f64 && !c->d_A2f) { set_error("fused path: context not prepared"); return false; }
     FusedParams fp;
     fp.mp = c->ntt->mp;
-    fp.tbl = c->ntt->tables;
+    fp.tbl = f64 ? c->ntt->tables_f : c->ntt->tables;
     for (int i = 0; i < 8; i++) fp.key.k[i] = c->key[i];
-    fp.A2 = c->d_A2;
+    fp.A2 = f64 ? c->d_A2f : c->d_A2;
     fp.delta = c->delta;
     fp.p = c->p;
     fp.msgs = d_msgs;
@@ -275,13 +309,13 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     const char* skip = std::getenv("LSR_FUSED_SKIP");
     fp.skip = skip ? (u32)std::strtoul(skip, nullptr, 0) : 0u;
     switch (c->logn * 16 + c->k) {
-        case 12 * 16 + 1: return launch_fused<12, 1>(fp, cdt, count, s);
-        case 12 * 16 + 2: return launch_fused<12, 2>(fp, cdt, count, s);
-        case 12 * 16 + 3: return launch_fused<12, 3>(fp, cdt, count, s);
-        case 12 * 16 + 4: return launch_fused<12, 4>(fp, cdt, count, s);
-        case 10 * 16 + 2: return launch_fused<10, 2>(fp, cdt, count, s);
-        case 11 * 16 + 2: return launch_fused<11, 2>(fp, cdt, count, s);
-        case 13 * 16 + 2: return launch_fused<13, 2>(fp, cdt, count, s);
+        case 12 * 16 + 1: return launch_fused<12, 1>(fp, cdt, count, s, f64);
+        case 12 * 16 + 2: return launch_fused<12, 2>(fp, cdt, count, s, f64);
+        case 12 * 16 + 3: return launch_fused<12, 3>(fp, cdt, count, s, f64);
+        case 12 * 16 + 4: return launch_fused<12, 4>(fp, cdt, count, s, f64);
+        case 10 * 16 + 2: return launch_fused<10, 2>(fp, cdt, count, s, f64);
+        case 11 * 16 + 2: return launch_fused<11, 2>(fp, cdt, count, s, f64);
+        case 13 * 16 + 2: return launch_fused<13, 2>(fp, cdt, count, s, f64);
         default: set_error("fused path: unsupported (n, k)"); return false;
     }
 }

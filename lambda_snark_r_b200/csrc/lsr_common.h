@@ -39,7 +39,21 @@ struct ModParams {
     u32 red_c;
     u32 lazy_fwd;  // (4 + 4 logn) q < 2^63
     u32 lazy_inv;  // 2^(logn+2) q < 2^63
+    u32 f64_ok;    // q < 2^45: the FP64-pipe butterfly is exact
+    u32 pad_;
+    double qd;     // (double)q
+    double invq;   // RN(1 / q)
+    double q52;    // q + 2^52
 };
+
+// Arithmetic policy of the NTT kernels (template parameter POL):
+//   POL_GUARD  SEAL's Harvey butterfly on u64, any q < 2^61
+//   POL_LAZY   u64 residues, truncated Shoup product, no reduction inside the butterfly
+//   POL_F64    residues held as doubles (balanced representatives), exact modular product by
+//              fma error-free multiplication; q < 2^45.  The FP64 pipe of B200 issues 64
+//              lanes/clk/SM and a butterfly costs 8 of its instructions, against 5 half-rate
+//              IMAD.WIDE + 4 IMAD + 8 ALU for POL_LAZY: measured 2.0x (tools/fp64_microbench.cu)
+enum : int { POL_GUARD = 0, POL_LAZY = 1, POL_F64 = 2 };
 
 // Device twiddle tables, both indexed [m + group] for the stage with m groups
 // (m = 1, 2, 4, ..., n/2): .x = w, .y = floor(w * 2^64 / q).
@@ -51,6 +65,8 @@ struct ModParams {
 //   fwd_last / inv_last: the twiddles of the unit-stride radix-16 pass (forward
 //                stages logn-4 .. logn-1), transposed to [15][n/16] so that work
 //                item w reads entry [(2^r - 1 + t)][w]: coalesced across a warp
+// For POL_F64 a second instance of this struct holds the same tables as bit patterns of
+// doubles: .x = (double)w, .y = RN(w / q).
 struct NttTables {
     const ulonglong2* fwd;
     const ulonglong2* inv;

@@ -49,6 +49,12 @@ struct NttContext {
     ulonglong2* d_inv = nullptr;
     ulonglong2* d_fwd_last = nullptr;
     ulonglong2* d_inv_last = nullptr;
+    lsr::NttTables tables_f{};        // POL_F64 tables (doubles), valid iff mp.f64_ok
+    ulonglong2* d_f_fwd = nullptr;
+    ulonglong2* d_f_inv = nullptr;
+    ulonglong2* d_f_fwd_last = nullptr;
+    ulonglong2* d_f_inv_last = nullptr;
+    int arith = 0;                    // 0 auto (FP64 butterflies when exact), 1 integer only
     cudaStream_t stream = nullptr;    // used by the host-pointer entry points
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -70,6 +76,7 @@ struct LweContext {
     NttContext* ntt = nullptr;        // owned
     lsr::u64* d_A = nullptr;          // [k][k][n] residues, NTT domain
     ulonglong2* d_A2 = nullptr;       // same with Shoup quotients, fused-kernel layout
+    ulonglong2* d_A2f = nullptr;      // same as doubles (a, a/q), fused kernel with FP64 butterflies
     lsr::u64* d_zh = nullptr;         // [k-1][n]
     lsr::u64* d_cdf = nullptr;        // [cdf.size()]
     int commit_path = 0;              // 0 auto, 1 generic, 2 fused

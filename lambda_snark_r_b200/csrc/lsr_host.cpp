@@ -109,6 +109,10 @@ ModParams make_mod_params(u64 q, uint32_t logn) {
     const u128 lim = (u128)1 << 63;
     mp.lazy_fwd = ((u128)(4 + 4 * logn) * q < lim) ? 1u : 0u;
     mp.lazy_inv = (((u128)q << (logn + 2)) < lim) ? 1u : 0u;
+    mp.f64_ok = (q < ((u64)1 << 45)) ? 1u : 0u;
+    mp.qd = (double)q;
+    mp.invq = 1.0 / (double)q;
+    mp.q52 = (double)q + 4503599627370496.0;
     return mp;
 }
 

@@ -60,6 +60,13 @@ static bool ensure_smem(K kernel, size_t smem) {
                    "cudaFuncSetAttribute(smem)");
 }
 
+// Arithmetic policy of a transform: FP64 butterflies whenever they are exact for the modulus
+// (q < 2^45, unless the context was pinned to integer arithmetic), else the u64 paths.
+static int policy_of(const NttContext* c, bool inverse) {
+    if (c->arith != 1 && c->mp.f64_ok) return POL_F64;
+    return (inverse ? c->mp.lazy_inv : c->mp.lazy_fwd) ? POL_LAZY : POL_GUARD;
+}
+
 template <int LOGN, int LT, bool INV>
 static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s) {
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
@@ -67,13 +74,17 @@ static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t 
     const size_t tiles = (total + ((size_t)1 << TL) - 1) >> TL;
     if (tiles == 0) return true;
     if (tiles > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
-    const bool lazy = INV ? c->mp.lazy_inv : c->mp.lazy_fwd;
-    if (lazy) {
-        auto k = ntt_tile_kernel<LOGN, LT, true, INV>;
+    const int pol = policy_of(c, INV);
+    if (pol == POL_F64) {
+        auto k = ntt_tile_kernel<LOGN, LT, POL_F64, INV>;
+        if (!ensure_smem(k, smem)) return false;
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables_f, d, total);
+    } else if (pol == POL_LAZY) {
+        auto k = ntt_tile_kernel<LOGN, LT, POL_LAZY, INV>;
         if (!ensure_smem(k, smem)) return false;
         k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
     } else {
-        auto k = ntt_tile_kernel<LOGN, LT, false, INV>;
+        auto k = ntt_tile_kernel<LOGN, LT, POL_GUARD, INV>;
         if (!ensure_smem(k, smem)) return false;
         k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
     }
@@ -86,9 +97,10 @@ static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_
     const size_t blocks = (cols + kNttThreads - 1) / kNttThreads;
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
-    const bool lazy = INV ? c->mp.lazy_inv : c->mp.lazy_fwd;
-    if (lazy) ntt_column_kernel<LOGN, S, true, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
-    else      ntt_column_kernel<LOGN, S, false, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    const int pol = policy_of(c, INV);
+    if (pol == POL_F64)       ntt_column_kernel<LOGN, S, POL_F64, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch);
+    else if (pol == POL_LAZY) ntt_column_kernel<LOGN, S, POL_LAZY, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    else                      ntt_column_kernel<LOGN, S, POL_GUARD, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
     return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
 }
 
@@ -153,6 +165,19 @@ bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64
 }
 
 // ------------------------------------------------------------------ life cycle
+static ulonglong2 to_f64_pair(const ulonglong2& e, u64 q) {
+    const double w = (double)e.x, wq = w / (double)q;      // w < 2^45: exact; IEEE division
+    ulonglong2 r;
+    std::memcpy(&r.x, &w, 8);
+    std::memcpy(&r.y, &wq, 8);
+    return r;
+}
+static std::vector<ulonglong2> to_f64_pairs(const std::vector<ulonglong2>& t, u64 q) {
+    std::vector<ulonglong2> r(t.size());
+    for (size_t i = 0; i < t.size(); ++i) r[i] = to_f64_pair(t[i], q);
+    return r;
+}
+
 NttContext* ntt_create(u64 q, uint32_t n) {
     host::NttHostTables ht;
     if (!host::build_ntt_tables(q, n, ht)) {
@@ -180,7 +205,35 @@ NttContext* ntt_create(u64 q, uint32_t n) {
     }
     for (int i = 0; ok && i < 2; ++i)
         ok = cuda_ok(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    // POL_F64 tables: the same entries as (double)w, RN(w / q) bit patterns
+    std::vector<ulonglong2> f_fwd, f_inv, f_fwd_last, f_inv_last;
+    if (ok && c->mp.f64_ok) {
+        f_fwd = to_f64_pairs(ht.fwd, q); f_inv = to_f64_pairs(ht.inv, q);
+        f_fwd_last = to_f64_pairs(ht.fwd_last, q); f_inv_last = to_f64_pairs(ht.inv_last, q);
+        ok = cuda_ok(cudaMalloc(&c->d_f_fwd, bytes), "cudaMalloc(twiddles)") &&
+             cuda_ok(cudaMalloc(&c->d_f_inv, bytes), "cudaMalloc(twiddles)") &&
+             cuda_ok(cudaMemcpy(c->d_f_fwd, f_fwd.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles") &&
+             cuda_ok(cudaMemcpy(c->d_f_inv, f_inv.data(), bytes, cudaMemcpyHostToDevice), "upload twiddles");
+        if (ok && !f_fwd_last.empty()) {
+            const size_t lb = sizeof(ulonglong2) * f_fwd_last.size();
+            ok = cuda_ok(cudaMalloc(&c->d_f_fwd_last, lb), "cudaMalloc(twiddles)") &&
+                 cuda_ok(cudaMalloc(&c->d_f_inv_last, lb), "cudaMalloc(twiddles)") &&
+                 cuda_ok(cudaMemcpy(c->d_f_fwd_last, f_fwd_last.data(), lb, cudaMemcpyHostToDevice), "upload twiddles") &&
+                 cuda_ok(cudaMemcpy(c->d_f_inv_last, f_inv_last.data(), lb, cudaMemcpyHostToDevice), "upload twiddles");
+        }
+    }
     if (!ok) { ntt_destroy(c); return nullptr; }
+    if (c->mp.f64_ok) {
+        c->tables_f.fwd = c->d_f_fwd;
+        c->tables_f.inv = c->d_f_inv;
+        c->tables_f.fwd_last = c->d_f_fwd_last;
+        c->tables_f.inv_last = c->d_f_inv_last;
+        for (uint32_t i = 0; i < 16; ++i) {
+            c->tables_f.head_fwd[i] = i < n ? f_fwd[i] : ulonglong2{0, 0};
+            c->tables_f.head_inv[i] = i < n ? f_inv[i] : ulonglong2{0, 0};
+        }
+        c->tables_f.n_inv = to_f64_pair(ht.n_inv, q);
+    }
     c->tables.fwd = c->d_fwd;
     c->tables.inv = c->d_inv;
     for (uint32_t i = 0; i < 16; ++i) {
@@ -201,6 +254,10 @@ void ntt_destroy(NttContext* c) {
     if (c->d_inv) cudaFree(c->d_inv);
     if (c->d_fwd_last) cudaFree(c->d_fwd_last);
     if (c->d_inv_last) cudaFree(c->d_inv_last);
+    if (c->d_f_fwd) cudaFree(c->d_f_fwd);
+    if (c->d_f_inv) cudaFree(c->d_f_inv);
+    if (c->d_f_fwd_last) cudaFree(c->d_f_fwd_last);
+    if (c->d_f_inv_last) cudaFree(c->d_f_inv_last);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (auto& s : c->copy_streams) if (s) cudaStreamDestroy(s);
     delete c;

@@ -66,7 +66,7 @@ __device__ __forceinline__ u32 tw_index(u32 T0, int r, int t, u32 stride) {
 // the entries (1 << r) + t are the same for every thread of the grid: they are
 // read from `head`, a by-value kernel parameter (constant bank), and reach the
 // IMADs as uniform operands -- no load, no register, one RF read less each.
-template <int R, int r, bool LAZY, bool LL, bool HEAD>
+template <int R, int r, int POL, bool LL, bool HEAD>
 __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                           const ulonglong2* __restrict__ head,
                                           u32 T0, u32 stride, const ModParams& mp) {
@@ -79,7 +79,13 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
             for (int jl = 0; jl < half; jl++) {
                 const int j = (t << (R - r)) + jl;
                 const int jj = j + half;
-                if (LAZY) {
+                if (POL == POL_F64) {
+                    // balanced doubles: |T| <= 0.75 q, growth +0.75 q per stage, no offset needed
+                    const double T = mulmod_f(as_d(v[jj]), as_d(w.x), as_d(w.y), mp.qd);
+                    const double X = as_d(v[j]);
+                    v[j] = as_u(__dadd_rn(X, T));
+                    v[jj] = as_u(__dadd_rn(X, -T));
+                } else if (POL == POL_LAZY) {
                     const u64 T = mulred4(v[jj], w.x, w.y, mp.nq);
                     const u64 X = v[j];
                     v[j] = X + T;
@@ -92,26 +98,30 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        fwd_stage<R, r + 1, LAZY, LL, HEAD>(v, tw, head, T0, stride, mp);
+        fwd_stage<R, r + 1, POL, LL, HEAD>(v, tw, head, T0, stride, mp);
     }
 }
 
-template <int R, bool LAZY, bool LL = false, bool HEAD = false>
+template <int R, int POL, bool LL = false, bool HEAD = false>
 __device__ __forceinline__ void fwd_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                             u32 T0, const ModParams& mp, u32 stride = 0,
                                             const ulonglong2* __restrict__ head = nullptr) {
-    fwd_stage<R, 0, LAZY, LL, HEAD>(v, tw, head, T0, stride, mp);
+    fwd_stage<R, 0, POL, LL, HEAD>(v, tw, head, T0, stride, mp);
 }
 
 // last inverse stage (m = 1): scalar n^-1 folded in (SEAL transform_from_rev
 // with scalar; w_scaled = inv[1] is already multiplied by n^-1), then the
 // final correction to [0, q)
-template <bool LAZY>
+template <int POL>
 __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglong2 w_scaled,
                                                    const ulonglong2 n_inv, int sigma,
                                                    const ModParams& mp) {
     const u64 X = x, Y = y;
-    if (LAZY) {
+    if (POL == POL_F64) {
+        const double Xd = as_d(X), Yd = as_d(Y);
+        x = f_to_canonical(mulmod_f(__dadd_rn(Xd, Yd), as_d(n_inv.x), as_d(n_inv.y), mp.qd), mp);
+        y = f_to_canonical(mulmod_f(__dadd_rn(Xd, -Yd), as_d(w_scaled.x), as_d(w_scaled.y), mp.qd), mp);
+    } else if (POL == POL_LAZY) {
         const u64 C = mp.q4 << sigma;
         x = csub(csub(mulred4(X + Y, n_inv.x, n_inv.y, mp.nq), mp.q2), mp.q);
         y = csub(csub(mulred4(X + C - Y, w_scaled.x, w_scaled.y, mp.nq), mp.q2), mp.q);
@@ -124,7 +134,7 @@ __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglo
 // sigma0 = number of inverse stages already done before this pass (growth
 // bound: a value entering inverse stage sigma is < 4q * 2^sigma on the lazy
 // path).  FINAL: the pass ends with the m = 1 stage (forward stage 0).
-template <int R, int r, bool LAZY, bool FINAL, bool LL, bool HEAD>
+template <int R, int r, int POL, bool FINAL, bool LL, bool HEAD>
 __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                           const ulonglong2* __restrict__ head,
                                           u32 T0, u32 stride, int sigma0, const ulonglong2 n_inv,
@@ -141,10 +151,14 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                 const int j = (t << (r + 1)) + jl;
                 const int jj = j + half;
                 if constexpr (FINAL && r == R - 1) {
-                    inv_last_butterfly<LAZY>(v[j], v[jj], w, n_inv, sigma0 + r, mp);
+                    inv_last_butterfly<POL>(v[j], v[jj], w, n_inv, sigma0 + r, mp);
                 } else {
                     const u64 X = v[j], Y = v[jj];
-                    if (LAZY) {
+                    if (POL == POL_F64) {
+                        const double Xd = as_d(X), Yd = as_d(Y);
+                        v[j] = as_u(__dadd_rn(Xd, Yd));
+                        v[jj] = as_u(mulmod_f(__dadd_rn(Xd, -Yd), as_d(w.x), as_d(w.y), mp.qd));
+                    } else if (POL == POL_LAZY) {
                         v[j] = X + Y;
                         v[jj] = mulred4(X + C - Y, w.x, w.y, mp.nq);
                     } else {
@@ -154,22 +168,41 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        inv_stage<R, r + 1, LAZY, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
+        inv_stage<R, r + 1, POL, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
     }
 }
 
-template <int R, bool LAZY, bool FINAL, bool LL = false, bool HEAD = false>
+// POL_F64 growth control.  In a GS pass element j is a product at stage r iff bit r of j is
+// set, and a sum (doubling) otherwise: leaving the pass, element 0 is bounded by 2^R b (b = bound
+// of the inputs) and element j != 0 by 2^(R-1-h) P, h = highest set bit of j, P = 0.75 q the
+// bound of a product.  Reducing the 2^(R-2) elements with the largest bounds (j < 2^(R-2)) leaves
+// every element <= 2P = 1.5 q, so the next pass (R <= 5) sees |X - Y| <= 2^R * 1.5 q <= 48 q
+// < 2^51 for q < 2^45.  Cost: 3 FP64 instructions on a quarter of the elements per pass.
+template <int R, int POL, bool FINAL, bool LL = false, bool HEAD = false>
 __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                             u32 T0, int sigma0, const ulonglong2 n_inv,
                                             const ModParams& mp, u32 stride = 0,
                                             const ulonglong2* __restrict__ head = nullptr) {
-    inv_stage<R, 0, LAZY, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
+    inv_stage<R, 0, POL, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
+    if constexpr (POL == POL_F64 && !FINAL) {
+        constexpr int NRED = R >= 2 ? (1 << (R - 2)) : 1;
+#pragma unroll
+        for (int j = 0; j < NRED; j++) v[j] = as_u(reduce_f(as_d(v[j]), mp.invq, mp.qd));
+    }
 }
 
-template <bool LAZY>
+template <int POL>
 __device__ __forceinline__ u64 fwd_final(u64 v, const ModParams& mp) {
-    if (LAZY) return reduce_small(v, mp);
+    if (POL == POL_F64) return f_to_canonical(reduce_f(as_d(v), mp.invq, mp.qd), mp);
+    if (POL == POL_LAZY) return reduce_small(v, mp);
     return csub(csub(v, mp.q2), mp.q);
+}
+
+// raw u64 from the caller -> the policy's working representation
+template <int POL>
+__device__ __forceinline__ u64 to_working(u64 v) {
+    if (POL == POL_F64) return as_u(u64_to_f(v));
+    return v;
 }
 
 // ---------------------------------------------------------------------------
@@ -215,7 +248,8 @@ enum : int { IO_SMEM = 0, IO_GLOBAL = 1 };
 struct TileIo {
     u64* g;        // tile base in global memory (IO_GLOBAL only)
     u32 valid;     // coefficients of the tile that exist (multiple of 2^LT)
-    u32 sanitize;  // reduce out-of-range inputs on load
+    u32 sanitize;  // the tile is raw caller data: reduce out-of-range inputs on load and convert
+                   // to the policy's working representation (POL_F64: doubles)
     u64 limit;     // sanitiser threshold
 };
 
@@ -224,7 +258,7 @@ struct NoEpilogue {
     __device__ __forceinline__ u64 operator()(u32, u64 v) const { return v; }
 };
 
-template <int LOGN, int LT, int S, int R, bool LAZY, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue>
+template <int LOGN, int LT, int S, int R, int POL, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io, const NttTables& tb_,
                                           const ModParams& mp, u32 items, u32 tb, const Epi& epi = Epi()) {
     constexpr int LG = LOGN - S - R;          // log2 of the element stride g
@@ -261,6 +295,8 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
 #pragma unroll
                     for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
                 }
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) v[j] = to_working<POL>(v[j]);
             }
         } else if constexpr (IN == IO_GLOBAL) {
 #pragma unroll
@@ -274,21 +310,23 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
 #pragma unroll
                     for (int j = 0; j < (1 << R); j++) v[j] = sanitize(v[j], io.limit, mp);
                 }
+#pragma unroll
+                for (int j = 0; j < (1 << R); j++) v[j] = to_working<POL>(v[j]);
             }
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = sm[swz(base + ((u32)j << LG))];
         }
         if constexpr (!INVERSE) {
-            fwd_network<R, LAZY, LL, HEAD>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
+            fwd_network<R, POL, LL, HEAD>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
             if (FINAL) {
 #pragma unroll
-                for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<LAZY>(v[j], mp);
+                for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<POL>(v[j], mp);
             }
         } else {
             constexpr int sigma0 = LOGN - S - R;          // inverse stages already done
             static_assert(!INVERSE || !FINAL || S == 0, "final inverse pass must contain stage 0");
-            inv_network<R, LAZY, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
+            inv_network<R, POL, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
         }
         if constexpr (OUT == IO_GLOBAL && LG == 0 && R >= 1 && std::is_same<Epi, NoEpilogue>::value) {
             if (live) {
@@ -323,7 +361,7 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
 //              inverse expects the tile in shared memory (global when one
 //              pass) and writes its last pass to global memory.
 // ---------------------------------------------------------------------------
-template <int LOGN, int LT, bool LAZY, bool GIO, int I>
+template <int LOGN, int LT, int POL, bool GIO, int I, bool FIN = true>
 __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, const NttTables& t,
                                                   const ModParams& mp, u32 tile_elems, u32 tb) {
     using P = plan<LT>;
@@ -332,13 +370,13 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_OUT && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LOGN, LT, S, R, LAZY, false, (I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
+        tile_pass<LOGN, LT, S, R, POL, false, (FIN && I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
         if constexpr (OUT == IO_SMEM) __syncthreads();
-        tile_forward_from<LOGN, LT, LAZY, GIO, I + 1>(sm, io, t, mp, tile_elems, tb);
+        tile_forward_from<LOGN, LT, POL, GIO, I + 1, FIN>(sm, io, t, mp, tile_elems, tb);
     }
 }
 
-template <int LOGN, int LT, bool LAZY, bool GIO, int I, typename Epi = NoEpilogue>
+template <int LOGN, int LT, int POL, bool GIO, int I, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, const NttTables& t,
                                                   const ModParams& mp, u32 tile_elems, u32 tb,
                                                   const Epi& epi = Epi()) {
@@ -348,34 +386,36 @@ __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, con
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_IN && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LOGN, LT, S, R, LAZY, true, (I == 0 && LT == LOGN), IN, OUT, Epi>(sm, io, t, mp, tile_elems >> R, tb, epi);
+        tile_pass<LOGN, LT, S, R, POL, true, (I == 0 && LT == LOGN), IN, OUT, Epi>(sm, io, t, mp, tile_elems >> R, tb, epi);
         if constexpr (OUT == IO_SMEM) __syncthreads();
-        tile_inverse_from<LOGN, LT, LAZY, GIO, I - 1, Epi>(sm, io, t, mp, tile_elems, tb, epi);
+        tile_inverse_from<LOGN, LT, POL, GIO, I - 1, Epi>(sm, io, t, mp, tile_elems, tb, epi);
     }
 }
 
-// shared-memory-only forms (fused commitment kernel)
-template <int LOGN, int LT, bool LAZY>
+// shared-memory-only forms (fused commitment kernel).  Values in shared memory are in the
+// policy's working representation.  POL_F64 forward leaves the evaluations unreduced (bounded by
+// (b + 0.75 logn) q for inputs bounded by b q): the consumer multiplies them, which reduces.
+template <int LOGN, int LT, int POL>
 __device__ __forceinline__ void tile_forward(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
     const TileIo io{nullptr, tile_elems, 0u, 0ull};
-    tile_forward_from<LOGN, LT, LAZY, false, 0>(sm, io, t, mp, tile_elems, tb);
+    tile_forward_from<LOGN, LT, POL, false, 0, POL != POL_F64>(sm, io, t, mp, tile_elems, tb);
 }
-template <int LOGN, int LT, bool LAZY>
+template <int LOGN, int LT, int POL>
 __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
     const TileIo io{nullptr, tile_elems, 0u, 0ull};
-    tile_inverse_from<LOGN, LT, LAZY, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb);
+    tile_inverse_from<LOGN, LT, POL, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb);
 }
 
 // shared memory in, last pass straight to global memory through an epilogue
 // (fused commitment kernel: + e, + Delta*m, container store); needs a multi-pass plan
-template <int LOGN, int LT, bool LAZY, typename Epi>
+template <int LOGN, int LT, int POL, typename Epi>
 __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const NttTables& t, const ModParams& mp,
                                                        u32 tile_elems, const Epi& epi) {
     static_assert(plan<LT>::N > 1, "single-pass plans read from global memory");
     const TileIo io{g, tile_elems, 0u, 0ull};
-    tile_inverse_from<LOGN, LT, LAZY, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, epi);
+    tile_inverse_from<LOGN, LT, POL, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, epi);
 }
 
 // ---------------------------------------------------------------------------
@@ -393,7 +433,7 @@ __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const Nt
 template <int LT>
 constexpr int ntt_min_blocks() { return LT <= 12 ? LSR_NTT_MINB : (LT == 13 ? 2 : 1); }
 
-template <int LOGN, int LT, bool LAZY, bool INVERSE>
+template <int LOGN, int LT, int POL, bool INVERSE>
 __global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
 ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems) {
     extern __shared__ __align__(16) u64 sm[];
@@ -409,7 +449,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
     const TileIo io{g, valid, clean ? 0u : 1u, INVERSE ? mp.q2 : mp.q4};
 
     if constexpr (!INVERSE) {
-        tile_forward_from<LOGN, LT, LAZY, true, 0>(sm, io, tbl, mp, TILE, tb);
+        tile_forward_from<LOGN, LT, POL, true, 0>(sm, io, tbl, mp, TILE, tb);
         if constexpr (!ONE_PASS && !LSR_NTT_DIRECT_OUT) {
 #pragma unroll 4
             for (u32 k = 0; k < PER_THREAD; k++) {
@@ -428,11 +468,11 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 #pragma unroll
             for (u32 k = 0; k < PER_THREAD; k++) {
                 const u32 i = threadIdx.x + k * kNttThreads;
-                sm[swz(i)] = sanitize(x[k], io.limit, mp);
+                sm[swz(i)] = to_working<POL>(sanitize(x[k], io.limit, mp));
             }
             __syncthreads();
         }
-        tile_inverse_from<LOGN, LT, LAZY, true, plan<LT>::N - 1>(sm, io, tbl, mp, TILE, tb);
+        tile_inverse_from<LOGN, LT, POL, true, plan<LT>::N - 1>(sm, io, tbl, mp, TILE, tb);
     }
 }
 
@@ -442,7 +482,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 // coefficients of one column, straight from / to global memory (coalesced
 // across threads), no shared memory.
 // ---------------------------------------------------------------------------
-template <int LOGN, int S, bool LAZY, bool INVERSE>
+template <int LOGN, int S, int POL, bool INVERSE>
 __global__ void __launch_bounds__(kNttThreads)
 ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch) {
     constexpr int LG = LOGN - S;
@@ -455,12 +495,12 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
     u64 v[1 << S];
     if (!INVERSE) {
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) v[j] = sanitize(g[(size_t)j << LG], mp.q4, mp);
-        fwd_network<S, LAZY>(v, tbl.fwd, 1u, mp);
+        for (int j = 0; j < (1 << S); j++) v[j] = to_working<POL>(sanitize(g[(size_t)j << LG], mp.q4, mp));
+        fwd_network<S, POL>(v, tbl.fwd, 1u, mp);
     } else {
 #pragma unroll
         for (int j = 0; j < (1 << S); j++) v[j] = g[(size_t)j << LG];
-        inv_network<S, LAZY, true>(v, tbl.inv, 1u, LG, tbl.n_inv, mp);
+        inv_network<S, POL, true>(v, tbl.inv, 1u, LG, tbl.n_inv, mp);
     }
 #pragma unroll
     for (int j = 0; j < (1 << S); j++) g[(size_t)j << LG] = v[j];

@@ -22,6 +22,7 @@ Q1 = 17592180539393            # 44-bit, 2-adicity 18
 Q60 = 1152921504606584833      # 60-bit, 2-adicity 18 (guarded Harvey path)
 Q50 = 1125899902124033         # 50-bit
 Q31 = 2146959361               # 31-bit
+Q45 = 35184365273089           # largest prime < 2^45 with 2^18 | q-1: worst case for the FP64 butterflies
 
 
 def pytest_configure(config):

@@ -153,19 +153,23 @@ def test_commit_matches_oracle_on_both_paths(gpu, rng, n, k, q):
     msgs[1, :] = ctx.p - 1
     seeds = sharding.global_seeds(0xC0FFEE, 0, count)
     want = orc.commit_batch(msgs, seeds)
-    ran = 0
-    for path in (1, 2):
-        ctx.set_commit_path(path)
-        try:
-            got = ctx.commit_batch(msgs, seeds)
-        except api.LambdaSnarkError:
-            assert path == 2          # the fused kernel covers a subset of shapes; the generic path covers all
-            continue
-        assert np.array_equal(got, want), f"path {path}"
-        ran += 1
-    assert ran >= 1
-    if (n, k, q) == (4096, 2, Q0):
-        assert ran == 2               # the headline configuration must run fused
+    for arith in ((0, 1) if q < 2**45 else (0,)):     # FP64 butterflies (auto) and u64 butterflies
+        ctx.set_arith(arith)
+        ran = 0
+        for path in (1, 2):
+            ctx.set_commit_path(path)
+            try:
+                got = ctx.commit_batch(msgs, seeds)
+            except api.LambdaSnarkError:
+                assert path == 2          # the fused kernel covers a subset of shapes; the generic path covers all
+                continue
+            assert np.array_equal(got, want), f"path {path} arith {arith}"
+            ran += 1
+        assert ran >= 1
+        if (n, k, q) == (4096, 2, Q0):
+            assert ran == 2               # the headline configuration must run fused
+        ctx.set_commit_path(0)
+        assert ctx.verify_batch(got, msgs % np.uint64(ctx.p)).tolist() == [1] * count, f"arith {arith}"
     ctx.close()
 
 

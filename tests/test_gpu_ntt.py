@@ -7,7 +7,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from conftest import Q0, Q1, Q31, Q50, Q60, uniform
+from conftest import Q0, Q1, Q31, Q45, Q50, Q60, uniform
 from lambda_snark_r_b200 import api, capi
 from oracle import oracle as O
 
@@ -74,7 +74,8 @@ def test_survey_kats_on_device(gpu):
 # ------------------------------------------------------------ parity sweeps
 SWEEP = [(12289, 256), (257, 2), (Q0, 2), (Q0, 4), (Q0, 8), (Q0, 16), (Q0, 32), (Q0, 64), (Q0, 128), (Q0, 512),
          (Q0, 1024), (Q0, 2048), (Q0, 4096), (Q1, 8192), (Q1, 16384), (Q1, 32768), (Q1, 65536), (Q1, 131072),
-         (Q60, 16), (Q60, 4096), (Q60, 16384), (Q60, 65536), (Q50, 4096), (Q50, 32768), (Q31, 1024), (Q31, 65536)]
+         (Q60, 16), (Q60, 4096), (Q60, 16384), (Q60, 65536), (Q50, 4096), (Q50, 32768), (Q31, 1024), (Q31, 65536),
+         (Q45, 4096), (Q45, 8192), (Q45, 65536)]
 
 
 @pytest.mark.parametrize("q,n", SWEEP)
@@ -91,12 +92,61 @@ def test_forward_inverse_match_oracle(gpu, rng, q, n):
         x[2, :] = 0; x[2, 0] = 1
     if batch > 3:
         x[3, :] = 0; x[3, n - 1] = 1
-    fx = g.forward_batch(x)
-    assert np.array_equal(fx, o.forward(x))
-    assert np.array_equal(g.inverse_batch(fx), x)
     y = uniform(rng, q, (batch, n))
-    assert np.array_equal(g.inverse_batch(y), o.inverse(y))
+    want_f, want_i = o.forward(x), o.inverse(y)
+    # both arithmetic policies where both exist: FP64 butterflies (auto for q < 2^45) and u64 Shoup
+    for arith in ((0, 1) if q < 2**45 else (0,)):
+        g.set_arith(arith)
+        assert g.arith == (2 if (arith == 0 and q < 2**45) else 1)
+        fx = g.forward_batch(x)
+        assert np.array_equal(fx, want_f), f"arith {arith}"
+        assert np.array_equal(g.inverse_batch(fx), x), f"arith {arith}"
+        assert np.array_equal(g.inverse_batch(y), want_i), f"arith {arith}"
     g.close()
+
+
+@pytest.mark.parametrize("q,n", [(Q0, 4096), (Q0, 1024), (Q0, 16), (Q1, 8192), (Q1, 131072), (Q31, 1024), (12289, 256),
+                                 (Q45, 16), (Q45, 4096), (Q45, 16384), (Q45, 131072)])
+def test_fp64_butterflies_on_extreme_inputs(gpu, rng, q, n):
+    """The FP64 policy keeps balanced representatives whose bounds grow with the stage count;
+    these rows push every bound: all q-1, alternating 0 / q-1 in every period, values around q/2,
+    lazy inputs up to 4q-1 (forward) and 2q-1 (inverse), and rows that make one butterfly output
+    sum coherently through all stages (the all-ones evaluation vector)."""
+    g = api.NttContext(q, n)
+    o = O.OracleNtt(q, n)
+    assert g.arith == 2
+    rows = [np.full(n, q - 1, dtype=np.uint64), np.full(n, q // 2, dtype=np.uint64), np.full(n, q // 2 + 1, dtype=np.uint64),
+            np.ones(n, dtype=np.uint64)]
+    for period in (1, 2, 4, 16, 256):
+        if period < n:
+            r = np.zeros(n, dtype=np.uint64); r[(np.arange(n) // period) % 2 == 1] = q - 1
+            rows.append(r)
+    for pos in (0, 1, n // 2, n - 1):
+        r = np.zeros(n, dtype=np.uint64); r[pos] = q - 1
+        rows.append(r)
+    rows += [uniform(rng, q, n) for _ in range(4)]
+    x = np.stack(rows)
+    want_f, want_i = o.forward(x), o.inverse(x)
+    assert np.array_equal(g.forward_batch(x), want_f)
+    assert np.array_equal(g.inverse_batch(x), want_i)
+    assert np.array_equal(g.forward_batch(x + np.uint64(3 * q)), want_f)        # lazy inputs, still below 4q
+    assert np.array_equal(g.inverse_batch(x + np.uint64(q)), want_i)            # below 2q
+    assert np.array_equal(g.inverse_batch(want_f), x)
+    g.set_arith(1)
+    assert np.array_equal(g.forward_batch(x), want_f) and np.array_equal(g.inverse_batch(x), want_i)
+    g.close()
+
+
+def test_arith_policy_selection(gpu):
+    lib = capi.load()
+    for q, n, pol in ((Q0, 4096, 2), (Q31, 1024, 2), (Q50, 4096, 1), (Q60, 4096, 1)):
+        h = lib.ntt_context_create(q, n)
+        assert lib.lsr_ntt_arith(h) == pol
+        assert lib.lsr_ntt_set_arith(h, 2) == (0 if pol == 2 else -1)
+        assert lib.lsr_ntt_set_arith(h, 1) == 0 and lib.lsr_ntt_arith(h) == 1
+        assert lib.lsr_ntt_set_arith(h, 0) == 0 and lib.lsr_ntt_arith(h) == pol
+        assert lib.lsr_ntt_set_arith(h, 3) == -1 and lib.lsr_ntt_set_arith(None, 0) == -1
+        lib.ntt_context_free(h)
 
 
 @pytest.mark.parametrize("q,n", [(Q0, 4096), (Q60, 4096), (Q1, 32768), (12289, 256)])
