@@ -14,8 +14,10 @@ reported beside it under "ntt".
 value      : commitments/s, whole job, inputs resident in HBM (CUDA events)
 e2e        : same metric through the C ABI's host-pointer call lwe_commit_batch
              with pinned HOST buffers, copies inside the timed region
-roofline   : dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json),
-             plus the integer-multiply roofline it is actually bound by
+roofline   : dominant kernel vs the measured HBM peak (MEASURED_PEAKS.json), plus the
+             compute rooflines: the FP64 pipe the butterflies run on (q < 2^45: exact
+             modular products by error-free fma multiplication, 8 FP64 instructions per
+             butterfly) and, for continuity with SURVEY 8d, the IMAD normalisation
 cpu_baseline / --impl reference : the oracle's C port of the same algorithm on
              the host cores (the reference's SEAL path cannot be built here)
 """
@@ -43,6 +45,11 @@ ALG_BYTES_NTT = 16 * N_RING                                       # read + write
 BUTTERFLIES_NTT = (N_RING // 2) * 12
 IMAD_PER_MODMUL = 10                                              # SURVEY 8d normalisation
 MODMUL_COMMIT = 2 * K_RANK * BUTTERFLIES_NTT + K_RANK * (N_RING // 2) + K_RANK * K_RANK * N_RING   # 118784
+FP64_PER_BUTTERFLY = 8                                            # mulmod_f (6) + add + sub, DESIGN.md 4.2
+FP64_PER_MODMUL = 6
+FP64_NTT_FWD = BUTTERFLIES_NTT * FP64_PER_BUTTERFLY
+FP64_NTT_INV = FP64_NTT_FWD + (N_RING // 2) * FP64_PER_MODMUL     # n^-1 folded into the last stage
+FP64_COMMIT = K_RANK * (FP64_NTT_FWD + FP64_NTT_INV) + K_RANK * K_RANK * N_RING * (FP64_PER_MODMUL + 1)
 
 
 def peaks():
@@ -244,6 +251,9 @@ def run_gpu(args):
 
     ctx = api.LweContext(api.Params(n=N_RING, k=K_RANK, q=Q_MOD, sigma=SIGMA), seed32=CTX_SEED)
     ntt = api.NttContext(Q_MOD, N_RING)
+    if args.arith == "u64":          # comparison runs only: pin both contexts to the u64 Shoup butterflies
+        ctx.set_arith(1)
+        ntt.set_arith(1)
     words = ctx.words
     B = args.batch
     # weak scaling: every rank owns B commitments; global index = rank*B + i decides seed and message
@@ -271,7 +281,6 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     ms_total = timed(step, args.warmup, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
@@ -303,6 +312,14 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     e2e_value = world * EB / (e2e_ms * 1e-3)
+    # the timed regions are a few tens of ms each: nvidia-smi samples every 100 ms, so the sampler stays on across all of
+    # them (commit, NTT, e2e) and the loop below keeps the commit kernel running until it has seen >= 10 samples
+    if rank == 0:
+        t_end = time.perf_counter() + 1.2
+        while time.perf_counter() < t_end:
+            step()
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- final gather over NVLink (outside the timed step: no data-path collective in the hot path)
     gather = None
@@ -329,6 +346,10 @@ def run_gpu(args):
     # rate that is 14 issue slots of the IMAD pipe, not the 10 the SURVEY normalisation assumes
     wide_cost = imad_lo.value / imad_wide.value if imad_wide.value else 2.0
     slots_per_modmul = 5 * wide_cost + 4
+    fp64_peak = C.c_double(0)
+    capi.load().lsr_measure_fp64_peak(C.byref(fp64_peak))                     # DFMA/DADD/DMUL: 64 lanes/clk/SM
+    fp64_peak = fp64_peak.value
+    arith = "fp64" if ntt.arith == 2 else "u64"
 
     if rank != 0:
         if world > 1:
@@ -339,16 +360,24 @@ def run_gpu(args):
     tr = traffic_note()
     commit_gbs = B * ALG_BYTES_COMMIT / (ms_step * 1e-3) / 1e9
     commit_imad = B * MODMUL_COMMIT * IMAD_PER_MODMUL / (ms_step * 1e-3) / 1e9
+    commit_fp64 = B * FP64_COMMIT / (ms_step * 1e-3) / 1e9
 
-    def ntt_block(ms, extra_modmul=0):
+    def ntt_block(ms, fp64_inst, extra_modmul=0):
         rate = world * NB / (ms * 1e-3)
+        per_gpu = NB / (ms * 1e-3)
         gbs = NB * ALG_BYTES_NTT / (ms * 1e-3) / 1e9
         gimad = NB * (BUTTERFLIES_NTT + extra_modmul) * IMAD_PER_MODMUL / (ms * 1e-3) / 1e9
+        gfp64 = per_gpu * fp64_inst / 1e9
+        bounds = {"hbm": hbm_peak * 1e9 / ALG_BYTES_NTT, "fp64": fp64_peak * 1e9 / fp64_inst if arith == "fp64" else None,
+                  "imad_survey": imad_peak * 1e9 / ((BUTTERFLIES_NTT + extra_modmul) * IMAD_PER_MODMUL)}
+        live = {k: v for k, v in bounds.items() if v and (k != "imad_survey" or arith != "fp64")}
+        slow = min(live, key=live.get)
         return {"value": rate, "unit": "NTT/s", "ms_per_step": ms,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                             "imad_achieved_gimad_s": gimad, "imad_peak_gimad_s": imad_peak,
-                             "imad_frac": gimad / imad_peak if imad_peak else None,
-                             "imad_frac_wide_aware": gimad * slots_per_modmul / IMAD_PER_MODMUL / imad_peak if imad_peak else None}}
+                             "fp64_achieved_ginst_s": gfp64 if arith == "fp64" else None, "fp64_peak_ginst_s": fp64_peak,
+                             "fp64_frac": gfp64 / fp64_peak if (arith == "fp64" and fp64_peak) else None,
+                             "bounds_ntt_per_s": bounds, "slower_bound": slow, "frac_of_slower_bound": per_gpu / live[slow],
+                             "imad_survey_frac": gimad / imad_peak if imad_peak else None}}
 
     # CPU baseline: bounded sample of the same workload on this box's host cores
     cpu_rate, cpu_threads, cpu_count, cpu_dt, native = cpu_commit_rate(args.cpu_seconds)
@@ -361,18 +390,25 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(B, "hbm-resident"),
         "roofline": {
-            "kernel": "fused_commit_kernel<12,2,5>", "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
+            "kernel": "fused_commit_kernel<12,2,5,%s>" % ("POL_F64" if arith == "fp64" else "POL_LAZY"), "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
             "unit": "GB/s", "frac": commit_gbs / hbm_peak, "peak_source": hbm_src,
             "traffic": (tr.get("fused_commit_bytes_per_commitment") or 0) * B or None,
             "algorithmic_bytes_per_commitment": ALG_BYTES_COMMIT,
-            "binding_bound": "imad (integer multiply pipe), not hbm",
-            "imad_achieved_gimad_s": commit_imad, "imad_peak_gimad_s": imad_peak,
-            "imad_frac": commit_imad / imad_peak if imad_peak else None,
-            "imad_peak_source": f"lsr_measure_imad_peak on this GPU: IMAD {imad_lo.value:.0f} GIMAD/s (= 64 lanes/clk/SM at "
-                                f"{mhz.value:.0f} MHz), IMAD.WIDE {imad_wide.value:.0f} GIMAD/s",
-            "imad_slots_per_modmul_measured": slots_per_modmul,
-            "imad_frac_wide_aware": B * MODMUL_COMMIT * slots_per_modmul / (ms_step * 1e-3) / 1e9 / imad_peak if imad_peak else None,
-            "imad_model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d); sampler not counted",
+            "arith": arith,
+            "binding_bound": "instruction issue: FP64 butterflies (2 issue cycles each, nothing co-issues with them) plus the "
+                             "ChaCha/CDT sampler on the ALU pipe; not hbm",
+            "fp64_achieved_ginst_s": commit_fp64 if arith == "fp64" else None, "fp64_peak_ginst_s": fp64_peak,
+            "fp64_frac": commit_fp64 / fp64_peak if (arith == "fp64" and fp64_peak) else None,
+            "fp64_model": f"{FP64_COMMIT} FP64 instructions/commitment = {K_RANK} fwd + {K_RANK} inv NTT x {FP64_PER_BUTTERFLY}/butterfly"
+                          f" + {K_RANK * K_RANK * N_RING} mat-vec MACs x {FP64_PER_MODMUL + 1}; sampler (ALU pipe) not counted",
+            "fp64_peak_source": "lsr_measure_fp64_peak on this GPU (dependent-free DFMA chains, 64 lanes/clk/SM)",
+            "bounds_commitments_per_s": {"hbm": hbm_peak * 1e9 / ALG_BYTES_COMMIT,
+                                         "fp64": fp64_peak * 1e9 / FP64_COMMIT if fp64_peak else None,
+                                         "imad_survey": imad_peak * 1e9 / (MODMUL_COMMIT * IMAD_PER_MODMUL) if imad_peak else None},
+            "imad_survey_frac": commit_imad / imad_peak if imad_peak else None,
+            "imad_survey_model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d normalisation; with "
+                                 f"arith=fp64 the multiplications run on the FP64 pipe instead); IMAD {imad_lo.value:.0f} GIMAD/s"
+                                 f" (= 64 lanes/clk/SM at {mhz.value:.0f} MHz), IMAD.WIDE {imad_wide.value:.0f} GIMAD/s measured",
         },
         "cpu_baseline": {"value": cpu_rate, "unit": "commitments/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_count} commitments in {cpu_dt:.1f}s, oracle C port, {cpu_threads} OpenMP threads"
@@ -383,7 +419,7 @@ def run_gpu(args):
                 "api": "lwe_commit_batch (C ABI, pinned host buffers)"},
         "gpu_launches": args.steps,
         "clocks": clocks,
-        "ntt": {"batch_per_gpu": NB, "forward": ntt_block(ms_fwd), "inverse": ntt_block(ms_inv, N_RING // 2),
+        "ntt": {"batch_per_gpu": NB, "forward": ntt_block(ms_fwd, FP64_NTT_FWD), "inverse": ntt_block(ms_inv, FP64_NTT_INV, N_RING // 2),
                 "pointwise": {"value": world * NB * N_RING / (ms_mul * 1e-3), "unit": "coefficients/s", "ms_per_step": ms_mul,
                               "roofline": {"bound": "hbm", "achieved": mul_gbs, "peak": hbm_peak, "unit": "GB/s",
                                            "frac": mul_gbs / hbm_peak}}},
@@ -406,6 +442,8 @@ def main():
     ap.add_argument("--ntt-batch", type=int, default=16384, help="polynomials per GPU per NTT step")
     ap.add_argument("--e2e-batch", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--arith", default="auto", choices=["auto", "u64"],
+                    help="auto: FP64-pipe butterflies (exact for q < 2^45); u64: integer Shoup butterflies (comparison)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

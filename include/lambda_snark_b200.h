@@ -220,6 +220,9 @@ const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnosti
  * 10^9 IMAD per second.  sm_mhz_effective (optional) = the SM clock implied by
  * 64 lanes/clk/SM.                                                          */
 int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_mhz_effective) LSR_NOEXCEPT;
+/* Same for the FP64 pipe (DFMA / DADD / DMUL issue rate, 10^9 thread-instructions/s): the
+ * denominator of the FP64-butterfly roofline.                                            */
+int lsr_measure_fp64_peak(double* ginst_per_s) LSR_NOEXCEPT;
 
 /* Introspection used by the tests and the host wrappers. */
 uint64_t lsr_ntt_modulus(const NttContext* ctx) LSR_NOEXCEPT;

@@ -73,6 +73,7 @@ SIGNATURES = {
     "lsr_version": (C.c_char_p, []),
     "lsr_last_error": (C.c_char_p, []),
     "lsr_measure_imad_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "lsr_measure_fp64_peak": (C.c_int, [C.POINTER(C.c_double)]),
     "lsr_ntt_modulus": (C.c_uint64, [C.c_void_p]),
     "lsr_ntt_degree": (C.c_uint32, [C.c_void_p]),
     "lsr_ntt_root": (C.c_uint64, [C.c_void_p]),

@@ -169,6 +169,17 @@ __device__ __forceinline__ u64 f_to_canonical(double r, const ModParams& mp) {
     return as_u(__dadd_rn(r, off)) & 0x000fffffffffffffull;
 }
 
+// m mod p for any u64 m and a small modulus p < 2^21 (the plaintext modulus), pinv = floor((2^64-1)/p):
+// the quotient estimate is at most 2 short, so the 32-bit remainder is below 3p; min(r, r - p) is the
+// branch-free conditional subtract (r - p wraps to a huge value when r < p).
+__device__ __forceinline__ u32 mod_small(u64 m, u32 p, u64 pinv) {
+    const u64 qh = __umul64hi(m, pinv);
+    u32 r = (u32)m - (u32)qh * p;
+    r = min(r, r - p);
+    r = min(r, r - p);
+    return r;
+}
+
 // modular add/sub on canonical residues
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }

@@ -34,6 +34,7 @@ struct FusedParams {
     const ulonglong2* A2;     // [K][K][n]  NTT domain; (a, floor(a*2^64/q)), or for POL_F64 the doubles (a, a/q)
     u64 delta;
     u64 p;
+    u64 pinv;                 // floor((2^64 - 1) / p)
     const u64* msgs;          // [count][msg_len]
     const u64* seeds;         // [count]
     u64* out;                 // [count][1 + K*n]
@@ -55,15 +56,15 @@ template <int LOGN, int K>
 struct CommitEpilogue {
     const signed char* E;
     const u64* msg;
-    u64 q, delta, p;
+    u64 q, delta, p, pinv;
     u32 msg_used;
     __device__ __forceinline__ u64 operator()(u32 idx, u64 v) const {
         const int ev = E[idx];
         v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                // < 2q
         const u32 x = idx - ((u32)(K - 1) << LOGN);                            // wraps for earlier rows
         if (idx >= ((u32)(K - 1) << LOGN) && x < msg_used) {
-            u64 m = __ldcs(msg + x);
-            if (__builtin_expect(m >= p, 0)) m %= p;
+            // messages are field elements in practice (>= p more often than not): Barrett, not a 64-bit division
+            const u64 m = p < (1ull << 21) ? (u64)mod_small(__ldcs(msg + x), (u32)p, pinv) : __ldcs(msg + x) % p;
             v = csub(v + delta * m, q);                                        // delta*m <= q-1
         }
         return csub(v, q);
@@ -83,6 +84,14 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const u64 seed = fp.seeds[b];
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
     const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+
+    // the message is consumed by the last pass only: pull it towards L2 now (one 128-byte line per thread)
+    // so that the epilogue's loads do not wait on HBM
+    {
+        const u64* m = fp.msgs + b * (size_t)fp.msg_len;
+        for (u32 x = threadIdx.x * 16u; x < fp.msg_used; x += kNttThreads * 16u)
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(m + x));
+    }
 
     // ---- phase 1: randomness (DESIGN.md 3.3 layout, same as sample_se_kernel)
     for (u32 tau = threadIdx.x; tau < ((fp.skip & 1u) ? 0u : (n >> 4)); tau += kNttThreads) {
@@ -154,7 +163,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     u64* o = fp.out + b * (1 + (size_t)K * n);
     if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
     if (!(fp.skip & 8u)) {
-        const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.msg_used};
+        const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used};
         tile_inverse_to_global<LOGN, LOGN, POL>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
     }
 }
@@ -301,6 +310,7 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     fp.A2 = f64 ? c->d_A2f : c->d_A2;
     fp.delta = c->delta;
     fp.p = c->p;
+    fp.pinv = ~0ull / c->p;
     fp.msgs = d_msgs;
     fp.seeds = d_seeds;
     fp.out = d_out;

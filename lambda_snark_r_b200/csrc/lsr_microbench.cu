@@ -47,7 +47,66 @@ imad_peak_kernel(unsigned iters, unsigned seed, unsigned long long* sink, int fl
     if (flag) sink[threadIdx.x] = s;
 }
 
+// FP64 pipe (the POL_F64 butterflies live on it): chains of fma.rn.f64 whose multiplicand is the
+// previous result of a neighbouring chain.  DADD and DMUL issue at the same rate as DFMA
+// (tools/fp64_microbench.cu), so one number serves as the denominator for all three.
+__global__ void __launch_bounds__(256)
+fp64_peak_kernel(unsigned iters, unsigned seed, double* sink, int flag) {
+    double a[kChains], b[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; c++) {
+        a[c] = 1.0 + 1e-9 * (double)(threadIdx.x + c + seed);
+        b[c] = 1.0 - 1e-9 * (double)(blockIdx.x + c);
+    }
+    for (unsigned it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < kInner; r++) {
+#pragma unroll
+            for (int c = 0; c < kChains; c++) {
+                const int n = (c + 1) % kChains;
+                asm volatile("fma.rn.f64 %0, %1, %2, %0;" : "+d"(a[c]) : "d"(a[n]), "d"(b[c]));
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int c = 0; c < kChains; c++) s += a[c];
+    if (flag) sink[threadIdx.x] = s;
+}
+
 }  // namespace lsr
+
+extern "C" int lsr_measure_fp64_peak(double* ginst_per_s) LSR_NOEXCEPT {
+    using namespace lsr;
+    if (!ginst_per_s) return -1;
+    int dev = current_device_choice();
+    if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return -1;
+    cudaDeviceProp prop;
+    if (!cuda_ok(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties")) return -1;
+    double* sink = nullptr;
+    if (!cuda_ok(cudaMalloc(&sink, 256 * sizeof(*sink)), "cudaMalloc")) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const unsigned blocks = prop.multiProcessorCount * 8;
+    const unsigned iters = 1000;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, 256>>>(iters, rep, sink, 0);
+        cudaEventRecord(e1);
+        if (!cuda_ok(cudaEventSynchronize(e1), "fp64_peak_kernel")) { cudaFree(sink); return -1; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)blocks * 256.0 * iters * kInner * kChains / (ms * 1e-3) / 1e9;
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *ginst_per_s = best;
+    return 0;
+}
 
 extern "C" int lsr_measure_imad_peak(int wide, double* gimad_per_s, double* sm_mhz_effective) LSR_NOEXCEPT {
     using namespace lsr;

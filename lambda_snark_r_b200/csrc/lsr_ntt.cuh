@@ -18,8 +18,11 @@
 #include "lsr_arith.cuh"
 
 // Unit-stride pass talking to HBM directly with 16-byte accesses instead of restaging
-// through shared memory.  Measured at n = 4096 (tools/ntt_variant_bench.cu): the forward
-// store gains 3 % (36.6 vs 35.4 M NTT/s), the inverse load loses 3 % (33.4 vs 34.5).
+// through shared memory.  Measured at n = 4096 (tools/ntt_variant_bench.cu) with the u64
+// butterflies, which are bound by the integer pipes: the forward store gains 3 % (36.6 vs 35.4
+// M NTT/s), the inverse load loses 3 % (33.4 vs 34.5).  With the FP64 butterflies the L1 data
+// pipe is the scarcer resource and the direct store (each lane writes its own 128-byte line,
+// 32 lines per instruction) costs 17 %: 48.4 vs 58.7 M NTT/s, so POL_F64 always restages.
 #ifndef LSR_NTT_DIRECT_OUT
 #define LSR_NTT_DIRECT_OUT 1
 #endif
@@ -32,14 +35,21 @@
 
 namespace lsr {
 
-constexpr int kNttThreads = 256;
+#ifndef LSR_NTT_THREADS   // tools/ntt_variant_bench.cu overrides this
+#define LSR_NTT_THREADS 256
+#endif
+constexpr int kNttThreads = LSR_NTT_THREADS;
 constexpr int kTileLogMin = 12;   // a CTA always works on >= 4096 coefficients
 
 // shared-memory swizzle: bits 0-3 ^= bits 4-7
 __device__ __forceinline__ u32 swz(u32 i) { return i ^ ((i >> 4) & 15u); }
 
 __device__ __forceinline__ ulonglong2 ld_tw(const ulonglong2* p) {
+#ifdef LSR_DIAG_NOTW    // tools/ntt_variant_bench.cu only: what would the kernel do if twiddle loads were free? (wrong results)
+    return make_ulonglong2(0x40c81c8000000000ull /* 12345.0 */, 0x3d081c8000000000ull /* ~7e-13 */);
+#else
     return __ldg(p);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -245,6 +255,9 @@ template <> struct plan<14> { static constexpr int N = 4; static constexpr int R
 // ---------------------------------------------------------------------------
 enum : int { IO_SMEM = 0, IO_GLOBAL = 1 };
 
+template <int POL>
+__host__ __device__ constexpr bool ntt_direct_out() { return LSR_NTT_DIRECT_OUT && POL != POL_F64; }
+
 struct TileIo {
     u64* g;        // tile base in global memory (IO_GLOBAL only)
     u32 valid;     // coefficients of the tile that exist (multiple of 2^LT)
@@ -369,7 +382,7 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
-        constexpr int OUT = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_OUT && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
+        constexpr int OUT = (GIO && (P::N == 1 || (ntt_direct_out<POL>() && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
         tile_pass<LOGN, LT, S, R, POL, false, (FIN && I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
         if constexpr (OUT == IO_SMEM) __syncthreads();
         tile_forward_from<LOGN, LT, POL, GIO, I + 1, FIN>(sm, io, t, mp, tile_elems, tb);
@@ -450,7 +463,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 
     if constexpr (!INVERSE) {
         tile_forward_from<LOGN, LT, POL, true, 0>(sm, io, tbl, mp, TILE, tb);
-        if constexpr (!ONE_PASS && !LSR_NTT_DIRECT_OUT) {
+        if constexpr (!ONE_PASS && !ntt_direct_out<POL>()) {
 #pragma unroll 4
             for (u32 k = 0; k < PER_THREAD; k++) {
                 const u32 i = threadIdx.x + k * kNttThreads;

@@ -75,24 +75,36 @@ __device__ __forceinline__ u32 cdt_magnitude(const CdtParam& t, u64 u) {
 template <int NCH8>
 __device__ __forceinline__ u32 cdt_magnitude_shfl(const CdtParam& t, u64 lane_entry, u64 u) {
     const u32 e_lo = (u32)lane_entry, e_hi = (u32)(lane_entry >> 32);
-    u32 pos = (t.cdf[15] < u) ? 16u : 0u;          // first probe is the same for every lane
+    // the search tracks the next probe index directly: probe' = probe + (below ? step/2 : -step/2)
+    // is one select between two immediates and one add, against select + add + add for pos / probe
+    u32 probe = (t.cdf[15] < u) ? 23u : 7u;        // first probe (entry 15) is the same for every lane
 #pragma unroll
-    for (u32 step = 8; step >= 1; step >>= 1) {
-        const u32 probe = pos + step - 1u;
+    for (int step = 8; step >= 2; step >>= 1) {
         const u32 v_lo = __shfl_sync(0xffffffffu, e_lo, probe);
         const u32 v_hi = __shfl_sync(0xffffffffu, e_hi, probe);
         const u64 v = ((u64)v_hi << 32) | v_lo;
-        pos += (v < u) ? step : 0u;
+        probe += (v < u) ? (u32)(step / 2) : (u32)(-(step / 2));
+    }
+    u32 pos;
+    {
+        const u32 v_lo = __shfl_sync(0xffffffffu, e_lo, probe);
+        const u32 v_hi = __shfl_sync(0xffffffffu, e_hi, probe);
+        const u64 v = ((u64)v_hi << 32) | v_lo;
+        pos = probe + ((v < u) ? 1u : 0u);         // #{k < 31 : cdf[k] < u}
     }
     if (t.pad) {
         // every entry from 31 on has an all-ones high word (true for sigma = 3.19: 1 - cdf[31] < 2^-32), so
-        // cdf[k] < u  <=>  u_hi == 0xffffffff and cdf_lo[k] < u_lo: 32-bit compares, one gate at the end.
+        // cdf[k] < u  <=>  u_hi == 0xffffffff and cdf_lo[k] < u_lo.  Each 32-bit comparison is the borrow of a
+        // subtraction, accumulated with subc: two instructions per entry, one gate at the end.
         // t.pad is a property of the table (uniform over the grid), not of u.
         const u32 u_lo = (u32)u, u_hi = (u32)(u >> 32);
-        u32 tail = 0;
+        u32 neg = 0;                                // minus the number of tail entries below u_lo
 #pragma unroll
-        for (int k = 31; k < NCH8 * 8; k++) tail += (u32)((u32)t.cdf[k] < u_lo);
-        pos += (u_hi == 0xffffffffu) ? tail : 0u;
+        for (int k = 31; k < NCH8 * 8; k++) {
+            u32 scratch;
+            asm("{sub.cc.u32 %1, %2, %3; subc.u32 %0, %0, 0;}" : "+r"(neg), "=r"(scratch) : "r"((u32)t.cdf[k]), "r"(u_lo));
+        }
+        pos += (u_hi == 0xffffffffu) ? (0u - neg) : 0u;
     } else {
 #pragma unroll
         for (int k = 31; k < NCH8 * 8; k++) pos += (u32)(t.cdf[k] < u);
