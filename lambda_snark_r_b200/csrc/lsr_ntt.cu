@@ -108,6 +108,9 @@ static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_
 // n >= 2^14: column kernel (first LOGN-12 stages) + tile kernel on 4096-blocks.
 // (n = 2^14 fits one CTA's shared memory, but at one 8-warp CTA per SM it ran at
 // 625 G butterflies/s against 800 for the two-kernel path: profiles/r01_ntt_sweep.json)
+// (Issuing the two kernels in L2-sized batch chunks so the second finds the first one's output on chip
+// was measured and rejected: 16/32/64 MB chunks ran at 0.60/0.77/0.85 of the whole-batch rate -- the
+// small dependent launches cost more in tails than the second HBM round trip does.)
 template <int LOGN, bool INV>
 static bool launch_transform(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
     const size_t total = batch << LOGN;

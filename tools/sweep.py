@@ -16,11 +16,14 @@ api.set_device(0)
 s = torch.cuda.current_stream().cuda_stream
 hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
 rows = []
-for logn in range(10, 17):
+import os
+LOGNS = [int(x) for x in os.environ.get("LSR_SWEEP_LOGN", "10,11,12,13,14,15,16").split(",")]
+BATCHES = [int(x) for x in os.environ.get("LSR_SWEEP_BATCH", "1,16,256,4096,65536").split(",")]
+for logn in LOGNS:
     n = 1 << logn
     q = Q0 if n <= 4096 else Q1
     ctx = api.NttContext(q, n)
-    for batch in (1, 16, 256, 4096, 65536):
+    for batch in BATCHES:
         if batch * n * 8 > (4 << 30):
             batch = (4 << 30) // (n * 8)
         d = torch.randint(0, q, (batch, n), device="cuda", dtype=torch.int64)
