@@ -231,7 +231,10 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     api.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version at INFO/VERSION)
+        # stdout carries the one JSON line: NCCL's own log (it prints its version banner at NCCL_DEBUG >= VERSION) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream().cuda_stream
