@@ -256,6 +256,33 @@ size_t   lsr_lwe_commitment_words(const LweContext* ctx) LSR_NOEXCEPT; /* 1 + k*
 /* copies A-hat ([k][k][n], NTT domain) to host memory; for cross-checks */
 int      lsr_lwe_copy_matrix(const LweContext* ctx, uint64_t* out) LSR_NOEXCEPT;
 
+/* ---- Quotient pipeline of the prover.  These have no counterpart in the reference's C
+ * ABI: they replace Rust code (rust-api/lambda-snark/src/ntt.rs, r1cs.rs) that a maintainer would
+ * bind through lambda-snark-sys.
+ *
+ * Cyclic transform over X^n - 1, natural order in and out: ntt_forward / ntt_inverse of ntt.rs:117-201
+ * (coefficients -> [f(omega^0), ..., f(omega^(n-1))]).  q: a prime < 2^61 with n | q-1, or Goldilocks
+ * 2^64 - 2^32 + 1 (lambda-snark-core/src/lib.rs:58 NTT_MODULUS).  omega = 0 picks the reference's root:
+ * NTT_PRIMITIVE_ROOT^(2^32/n) (lib.rs:78, ntt.rs:214-221), 3^((q-1)/n) for 17592169062401
+ * (r1cs.rs:534-547), the minimal primitive n-th root otherwise.  The context is an ordinary NttContext
+ * (ntt_context_free releases it; ntt_forward_batch on it returns the bit-reversed order).               */
+uint64_t    lsr_reference_root_of_unity(uint64_t q, uint32_t n) LSR_NOEXCEPT;
+NttContext* lsr_cyclic_ntt_context_create(uint64_t q, uint32_t n, uint64_t omega) LSR_NOEXCEPT;
+int lsr_cyclic_ntt_forward(const NttContext* ctx, uint64_t* coeffs, size_t batch) LSR_NOEXCEPT;
+int lsr_cyclic_ntt_inverse(const NttContext* ctx, uint64_t* evals, size_t batch) LSR_NOEXCEPT;
+
+/* Quotient polynomial Q(X) = (A_z(X) B_z(X) - C_z(X)) / (X^m - 1) of the R1CS instance behind `r1cs`
+ * (lambda_snark_r1cs_create), A_z, B_z, C_z interpolated over H = {omega^j}: compute_quotient_poly on
+ * its NTT path (r1cs.rs:474-503, :746-793, :995-1065).  m = number of constraints, a power of two
+ * <= 2^16; matrix values and witness words are reduced as unsigned words (sparse_matrix.rs:279).
+ * One witness: `out` receives the coefficients with trailing zeros removed (*out_len >= 1, out_cap >= m);
+ * LAMBDA_SNARK_ERR_CRYPTO_FAILED when the witness does not satisfy the constraints.
+ * Batch: witnesses [count][witness_len] -> out [count][m] zero-padded, status[count] (0 ok, 1 unsatisfied). */
+LambdaSnarkError lsr_r1cs_quotient(void* r1cs, const uint64_t* witness, size_t witness_len, uint64_t omega,
+                                   uint64_t* out, size_t out_cap, size_t* out_len) LSR_NOEXCEPT;
+int lsr_r1cs_quotient_batch(void* r1cs, const uint64_t* witnesses, size_t witness_len, size_t count,
+                            uint64_t omega, uint64_t* out, int* status) LSR_NOEXCEPT;
+
 /* Arithmetic of the NTT butterflies (NttContext, and the NttContext inside an
  * LweContext): 0 auto -- FP64-pipe butterflies (exact modular products by
  * error-free fma multiplication) when q < 2^45, else u64 Shoup butterflies;

@@ -152,6 +152,90 @@ class NttContext:
 
 
 # ------------------------------------------------------------------- commitment
+class CyclicNtt(NttContext):
+    """Cyclic transform over X^n - 1, natural order in and out: ntt_forward / ntt_inverse of
+    rust-api/lambda-snark/src/ntt.rs:117-201.  omega = 0 picks the reference's root of unity."""
+
+    def __init__(self, q: int, n: int, omega: int = 0):
+        self._h = _lib().lsr_cyclic_ntt_context_create(q, n, omega)
+        if not self._h:
+            raise LambdaSnarkError(f"lsr_cyclic_ntt_context_create({q}, {n}, {omega}) returned NULL")
+        self.q, self.n = q, n
+
+    def forward_natural(self, polys) -> np.ndarray:
+        a = np.ascontiguousarray(_u64(polys)).copy()
+        if _lib().lsr_cyclic_ntt_forward(self._h, _p(a), a.size // self.n) != 0:
+            raise LambdaSnarkError("lsr_cyclic_ntt_forward returned -1")
+        return a
+
+    def inverse_natural(self, evals) -> np.ndarray:
+        a = np.ascontiguousarray(_u64(evals)).copy()
+        if _lib().lsr_cyclic_ntt_inverse(self._h, _p(a), a.size // self.n) != 0:
+            raise LambdaSnarkError("lsr_cyclic_ntt_inverse returned -1")
+        return a
+
+
+def reference_root_of_unity(q: int, n: int) -> int:
+    return int(_lib().lsr_reference_root_of_unity(q, n))
+
+
+class R1CS:
+    """lambda_snark_r1cs_* handle (lambda-snark-core/src/r1cs.rs:121-141) plus the GPU quotient pipeline
+    that replaces R1CS::compute_quotient_poly (lambda-snark/src/r1cs.rs:474-503) on its NTT path.
+    Matrices are lists of (row, col, value)."""
+
+    def __init__(self, rows: int, cols: int, A, B, C, modulus: int):
+        from .capi import SparseEntry, SparseMatrix
+        import ctypes as C_
+        self._keep = []
+        mats = []
+        for entries in (A, B, C):
+            arr = (SparseEntry * max(len(entries), 1))()
+            for i, (r, c, v) in enumerate(entries):
+                arr[i].row, arr[i].col, arr[i].value = r, c, v % (1 << 64)
+            self._keep.append(arr)
+            mats.append(SparseMatrix(C_.cast(arr, C_.POINTER(SparseEntry)), len(entries), rows, cols))
+        h = C_.c_void_p()
+        rc = _lib().lambda_snark_r1cs_create(C_.byref(mats[0]), C_.byref(mats[1]), C_.byref(mats[2]), modulus, C_.byref(h))
+        if rc != 0:
+            raise LambdaSnarkError(f"lambda_snark_r1cs_create failed with code {rc}")
+        self._h = h
+        self.rows, self.cols, self.modulus = rows, cols, modulus
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            try:
+                _lib().lambda_snark_r1cs_free(self._h)
+            except TypeError:
+                pass
+            self._h = None
+
+    __del__ = close
+
+    def quotient(self, witness, omega: int = 0) -> np.ndarray:
+        """compute_quotient_poly: coefficients with trailing zeros removed; raises if the witness is invalid."""
+        import ctypes as C_
+        w = np.ascontiguousarray(_u64(witness))
+        out = np.zeros(max(self.rows, 1), dtype=np.uint64)
+        n = C_.c_size_t(0)
+        rc = _lib().lsr_r1cs_quotient(self._h, _p(w), w.size, omega, _p(out), out.size, C_.byref(n))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_r1cs_quotient failed with code {rc}: {last_error()}")
+        return out[: n.value].copy()
+
+    def quotient_batch(self, witnesses, omega: int = 0):
+        """witnesses [count][cols] -> (Q [count][m] zero-padded, status [count])."""
+        import ctypes as C_
+        w = np.ascontiguousarray(_u64(witnesses)).reshape(-1, self.cols)
+        out = np.zeros((w.shape[0], self.rows), dtype=np.uint64)
+        status = np.zeros(w.shape[0], dtype=np.int32)
+        rc = _lib().lsr_r1cs_quotient_batch(self._h, _p(w), self.cols, w.shape[0], omega, _p(out),
+                                            status.ctypes.data_as(C_.POINTER(C_.c_int)))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_r1cs_quotient_batch failed with code {rc}: {last_error()}")
+        return out, status
+
+
 @dataclass
 class Params:
     """lambda-snark-core Params/Profile::RingB (lambda-snark-core/src/lib.rs:129-196)."""

@@ -91,6 +91,12 @@ SIGNATURES = {
     "lsr_lwe_commitment_words": (C.c_size_t, [C.c_void_p]),
     "lsr_lwe_copy_matrix": (C.c_int, [C.c_void_p, u64p]),
     "lsr_lwe_set_commit_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "lsr_reference_root_of_unity": (C.c_uint64, [C.c_uint64, C.c_uint32]),
+    "lsr_cyclic_ntt_context_create": (C.c_void_p, [C.c_uint64, C.c_uint32, C.c_uint64]),
+    "lsr_cyclic_ntt_forward": (C.c_int, [C.c_void_p, u64p, C.c_size_t]),
+    "lsr_cyclic_ntt_inverse": (C.c_int, [C.c_void_p, u64p, C.c_size_t]),
+    "lsr_r1cs_quotient": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "lsr_r1cs_quotient_batch": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.POINTER(C.c_int)]),
     "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
     "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),

@@ -12,6 +12,12 @@
 
 #include "lambda_snark_b200.h"
 #include "lsr_engine.h"
+#include "lsr_r1cs.h"
+
+namespace lsr {
+u64 reference_root_of_unity(u64 q, uint32_t n);
+int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status);
+}
 
 using lsr::u64;
 
@@ -112,6 +118,61 @@ int ntt_inverse_batch(const NttContext* ctx, uint64_t* evals, size_t batch) LSR_
     if (!ctx || !evals) return -1;
     return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(evals), batch, true) ? 0 : -1;
     LSR_CATCH(-1)
+}
+
+/* ------------------------------------------- cyclic transforms + quotient (N1) */
+uint64_t lsr_reference_root_of_unity(uint64_t q, uint32_t n) LSR_NOEXCEPT {
+    LSR_TRY
+    return lsr::reference_root_of_unity(q, n);
+    LSR_CATCH(0)
+}
+
+NttContext* lsr_cyclic_ntt_context_create(uint64_t q, uint32_t n, uint64_t omega) LSR_NOEXCEPT {
+    LSR_TRY
+    if (omega == 0) omega = lsr::reference_root_of_unity(q, n);
+    return lsr::ntt_create_cyclic(q, n, omega);
+    LSR_CATCH(nullptr)
+}
+
+int lsr_cyclic_ntt_forward(const NttContext* ctx, uint64_t* coeffs, size_t batch) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !coeffs || !ctx->cyclic) return -1;
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(coeffs), batch, false, true) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_cyclic_ntt_inverse(const NttContext* ctx, uint64_t* evals, size_t batch) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !evals || !ctx->cyclic) return -1;
+    return lsr::ntt_transform_host(ctx, reinterpret_cast<u64*>(evals), batch, true, true) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_r1cs_quotient_batch(void* r1cs, const uint64_t* witnesses, size_t witness_len, size_t count, uint64_t omega,
+                            uint64_t* out, int* status) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!r1cs || !witnesses || !out || !status) return LAMBDA_SNARK_ERR_NULL_PTR;
+    lsr::R1csHandle* h = static_cast<lsr::R1csHandle*>(r1cs);
+    if (witness_len != h->cols) return LAMBDA_SNARK_ERR_INVALID_PARAMS;
+    return lsr::r1cs_quotient_batch(h, reinterpret_cast<const u64*>(witnesses), count, omega, reinterpret_cast<u64*>(out), status);
+    LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
+}
+
+LambdaSnarkError lsr_r1cs_quotient(void* r1cs, const uint64_t* witness, size_t witness_len, uint64_t omega,
+                                   uint64_t* out, size_t out_cap, size_t* out_len) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!r1cs || !witness || !out || !out_len) return LAMBDA_SNARK_ERR_NULL_PTR;
+    lsr::R1csHandle* h = static_cast<lsr::R1csHandle*>(r1cs);
+    if (witness_len != h->cols || out_cap < h->rows) return LAMBDA_SNARK_ERR_INVALID_PARAMS;
+    int status = 0;
+    const int rc = lsr::r1cs_quotient_batch(h, reinterpret_cast<const u64*>(witness), 1, omega, reinterpret_cast<u64*>(out), &status);
+    if (rc != 0) return static_cast<LambdaSnarkError>(rc);
+    if (status != 0) return LAMBDA_SNARK_ERR_CRYPTO_FAILED;          // r1cs.rs:477-481, :1055-1059: witness invalid
+    size_t len = h->rows;                                            // r1cs.rs:1062-1064: trailing zeros removed
+    while (len > 1 && out[len - 1] == 0) --len;
+    *out_len = len;
+    return LAMBDA_SNARK_OK;
+    LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
 }
 
 int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,

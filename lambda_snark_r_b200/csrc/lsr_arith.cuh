@@ -105,13 +105,40 @@ __device__ __forceinline__ u64 barrett128(u64 z0, u64 z1, const ModParams& mp) {
     return csub(r, mp.q);
 }
 
+// ---------------------------------------------------------------------------
+// POL_GOLD: q = 2^64 - 2^32 + 1.  Residues are canonical u64 in [0, q); sums that overflow 2^64
+// are fixed up with 2^64 = 2^32 - 1 (mod q), i.e. a wrapped subtraction of q.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ u64 gold_add(u64 a, u64 b) {
+    const u64 s = a + b;
+    return (s < a || s >= kGoldilocks) ? s - kGoldilocks : s;
+}
+__device__ __forceinline__ u64 gold_sub(u64 a, u64 b) {
+    const u64 d = a - b;
+    return a < b ? d + kGoldilocks : d;
+}
+// (hi:lo) mod q:  hi = hh * 2^32 + hl  ->  lo + hl * (2^32 - 1) - hh
+__device__ __forceinline__ u64 gold_reduce128(u64 lo, u64 hi) {
+    const u64 eps = 0xFFFFFFFFull;
+    const u64 hh = hi >> 32, hl = hi & eps;
+    u64 t0 = lo - hh;
+    if (lo < hh) t0 -= eps;                   // the borrow took 2^64 = eps (mod q) too much
+    const u64 t1 = hl * eps;                  // < 2^64
+    u64 r = t0 + t1;
+    if (r < t1) r += eps;                     // the carry dropped 2^64 = eps (mod q)
+    return r >= kGoldilocks ? r - kGoldilocks : r;
+}
+__device__ __forceinline__ u64 gold_mul(u64 a, u64 b) { return gold_reduce128(a * b, __umul64hi(a, b)); }
+
 // exact (a * b) mod q for any u64 a, b  (ntt.cpp:116-118 -> multiply_uint_mod)
 __device__ __forceinline__ u64 mulmod_exact(u64 a, u64 b, const ModParams& mp) {
+    if (mp.gold) return gold_mul(a, b);       // gold_reduce128 accepts any 128-bit value
     return barrett128(a * b, __umul64hi(a, b), mp);
 }
 
 // exact x mod q for any u64 x
 __device__ __forceinline__ u64 reduce64(u64 x, const ModParams& mp) {
+    if (mp.gold) return x >= kGoldilocks ? x - kGoldilocks : x;
     return barrett128(x, 0, mp);
 }
 
@@ -183,5 +210,10 @@ __device__ __forceinline__ u32 mod_small(u64 m, u32 p, u64 pinv) {
 // modular add/sub on canonical residues
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+// field operations on canonical residues for any supported modulus (q < 2^61, or Goldilocks)
+__device__ __forceinline__ u64 field_add(u64 a, u64 b, const ModParams& mp) { return mp.gold ? gold_add(a, b) : addmod(a, b, mp.q); }
+__device__ __forceinline__ u64 field_sub(u64 a, u64 b, const ModParams& mp) { return mp.gold ? gold_sub(a, b) : submod(a, b, mp.q); }
+__device__ __forceinline__ u64 field_mul(u64 a, u64 b, const ModParams& mp) { return mulmod_exact(a, b, mp); }
 
 }  // namespace lsr

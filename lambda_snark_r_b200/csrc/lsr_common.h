@@ -40,7 +40,7 @@ struct ModParams {
     u32 lazy_fwd;  // (4 + 4 logn) q < 2^63
     u32 lazy_inv;  // 2^(logn+2) q < 2^63
     u32 f64_ok;    // q < 2^45: the FP64-pipe butterfly is exact
-    u32 pad_;
+    u32 gold;      // q = 2^64 - 2^32 + 1 (the reference's NTT_MODULUS): POL_GOLD arithmetic
     double qd;     // (double)q
     double invq;   // RN(1 / q)
     double q52;    // q + 2^52
@@ -53,7 +53,11 @@ struct ModParams {
 //              fma error-free multiplication; q < 2^45.  The FP64 pipe of B200 issues 64
 //              lanes/clk/SM and a butterfly costs 8 of its instructions, against 5 half-rate
 //              IMAD.WIDE + 4 IMAD + 8 ALU for POL_LAZY: measured 2.0x (tools/fp64_microbench.cu)
-enum : int { POL_GUARD = 0, POL_LAZY = 1, POL_F64 = 2 };
+//   POL_GOLD   q = 2^64 - 2^32 + 1 (Goldilocks, lambda-snark-core/src/lib.rs:58): canonical u64 residues,
+//              128-bit product folded with 2^64 = 2^32 - 1, 2^96 = -1 (mod q); cyclic transforms of the
+//              quotient pipeline (rust-api/lambda-snark/src/ntt.rs)
+enum : int { POL_GUARD = 0, POL_LAZY = 1, POL_F64 = 2, POL_GOLD = 3 };
+constexpr u64 kGoldilocks = 0xFFFFFFFF00000001ULL;
 
 // Device twiddle tables, both indexed [m + group] for the stage with m groups
 // (m = 1, 2, 4, ..., n/2): .x = w, .y = floor(w * 2^64 / q).

@@ -55,6 +55,7 @@ struct NttContext {
     ulonglong2* d_f_fwd_last = nullptr;
     ulonglong2* d_f_inv_last = nullptr;
     int arith = 0;                    // 0 auto (FP64 butterflies when exact), 1 integer only
+    bool cyclic = false;              // tables of the cyclic transform (X^n - 1); psi then holds omega
     cudaStream_t stream = nullptr;    // used by the host-pointer entry points
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -107,6 +108,11 @@ bool fused_commit_supported(const LweContext* ctx);
 bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant);
 
 NttContext* ntt_create(u64 q, uint32_t n);
+// cyclic transform over X^n - 1 with the given primitive n-th root (rust-api/lambda-snark/src/ntt.rs);
+// q < 2^61 prime, or Goldilocks 2^64 - 2^32 + 1
+NttContext* ntt_create_cyclic(u64 q, uint32_t n, u64 omega);
+// in-place bit-reversal permutation of each polynomial (natural-order views of the transforms)
+bool ntt_bitrev_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
 void ntt_destroy(NttContext* ctx);
 
 // asynchronous launches on `stream`; data on the context's device
@@ -116,7 +122,8 @@ bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64
                       cudaStream_t stream);
 
 // host-pointer paths (H2D, kernel, D2H, synchronised), chunked + double buffered
-bool ntt_transform_host(const NttContext* ctx, u64* host, size_t batch, bool inverse);
+// natural = true: forward output / inverse input in natural order (bit-reversal permutation added)
+bool ntt_transform_host(const NttContext* ctx, u64* host, size_t batch, bool inverse, bool natural = false);
 bool pointwise_host(const NttContext* ctx, u64* r, const u64* a, const u64* b, size_t total);
 
 }  // namespace lsr

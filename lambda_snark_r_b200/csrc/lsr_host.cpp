@@ -85,6 +85,8 @@ bool ntt_friendly_prime(u64 q, uint32_t n) {
 }
 
 static inline u64 shoup_quotient(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static void transpose_last_pass_impl(NttHostTables& out);
+static void transpose_last_pass(NttHostTables& out) { transpose_last_pass_impl(out); }
 
 static inline uint32_t bitrev(uint32_t x, uint32_t bits) {
     uint32_t r = 0;
@@ -110,6 +112,7 @@ ModParams make_mod_params(u64 q, uint32_t logn) {
     mp.lazy_fwd = ((u128)(4 + 4 * logn) * q < lim) ? 1u : 0u;
     mp.lazy_inv = (((u128)q << (logn + 2)) < lim) ? 1u : 0u;
     mp.f64_ok = (q < ((u64)1 << 45)) ? 1u : 0u;
+    mp.gold = (q == kGoldilocks) ? 1u : 0u;
     mp.qd = (double)q;
     mp.invq = 1.0 / (double)q;
     mp.q52 = (double)q + 4503599627370496.0;
@@ -156,8 +159,14 @@ bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
     }
     out.n_inv.x = n_inv;
     out.n_inv.y = shoup_quotient(n_inv, q);
-    // transposed copy of the unit-stride radix-16 pass (forward stages logn-4 .. logn-1):
-    // work item w, stage r, group t  <-  heap entry ((2^(logn-4) + w) << r) + t
+    transpose_last_pass(out);
+    return true;
+}
+
+// transposed copy of the unit-stride radix-16 pass (forward stages logn-4 .. logn-1):
+// work item w, stage r, group t  <-  heap entry ((2^(logn-4) + w) << r) + t
+static void transpose_last_pass_impl(NttHostTables& out) {
+    const uint32_t n = out.n, logn = out.logn;
     out.fwd_last.clear(); out.inv_last.clear();
     if (logn > 4) {
         const uint32_t items = n >> 4, first = 1u << (logn - 4);
@@ -172,6 +181,49 @@ bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
                     out.inv_last[dst] = out.inv[src];
                 }
     }
+}
+
+bool cyclic_params_ok(u64 q, uint32_t n, u64 omega) {
+    if (n < 2 || (n & (n - 1)) || n > (1u << kMaxLogN)) return false;
+    if (q != kGoldilocks && (q < 3 || (q >> 61))) return false;
+    if ((q - 1) % n) return false;
+    if (omega == 0 || omega >= q) return false;
+    return powmod(omega, n >> 1, q) == q - 1;      // primitive n-th root of unity (q prime is the caller's claim
+                                                   // for Goldilocks; checked below for everything else)
+}
+
+// Cyclic transform of rust-api/lambda-snark/src/ntt.rs:117-201 on the same butterfly networks: the
+// forward network with twiddle  w[m + g] = omega^(brv_{log m}(g) * n / 2m)  maps natural-order
+// coefficients to f(omega^brv(i)) at index i (the negacyclic table is the same with 2*brv + 1 and
+// psi = sqrt(omega)); the inverse network takes w^-1 and n^-1 in its last stage.
+bool build_cyclic_tables(u64 q, uint32_t n, u64 omega, NttHostTables& out) {
+    if (!cyclic_params_ok(q, n, omega)) return false;
+    if (q != kGoldilocks && !is_prime(q)) return false;
+    uint32_t logn = 0;
+    while ((1u << logn) < n) ++logn;
+    const u64 omega_inv = powmod(omega, q - 2, q);
+    const u64 n_inv = powmod(n % q, q - 2, q);
+    out.q = q; out.n = n; out.logn = logn; out.psi = omega;
+    out.fwd.assign(n, ulonglong2{0, 0});
+    out.inv.assign(n, ulonglong2{0, 0});
+    std::vector<u64> pw(n / 2 + 1), ipw(n / 2 + 1);          // omega^e, omega^-e for e < n/2
+    pw[0] = ipw[0] = 1;
+    for (uint32_t e = 1; e <= n / 2; ++e) { pw[e] = mulmod(pw[e - 1], omega, q); ipw[e] = mulmod(ipw[e - 1], omega_inv, q); }
+    const bool small = !(q >> 61);
+    auto pair = [&](u64 w) { return ulonglong2{w, small ? shoup_quotient(w, q) : 0ull}; };
+    out.fwd[0] = out.inv[0] = pair(1);
+    uint32_t logm = 0;
+    for (uint32_t m = 1; m < n; m <<= 1, ++logm) {
+        for (uint32_t g = 0; g < m; ++g) {
+            const uint32_t e = bitrev(g, logm) * (n / (2 * m));   // < n/2
+            out.fwd[m + g] = pair(pw[e]);
+            u64 wi = ipw[e];
+            if (m == 1) wi = mulmod(wi, n_inv, q);               // scalar folded into the last inverse stage
+            out.inv[m + g] = pair(wi);
+        }
+    }
+    out.n_inv = pair(n_inv);
+    transpose_last_pass(out);
     return true;
 }
 

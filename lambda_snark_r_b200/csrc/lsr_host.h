@@ -32,6 +32,9 @@ struct NttHostTables {
     ulonglong2 n_inv{0, 0};
 };
 bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out);
+// cyclic (X^n - 1) tables for a given primitive n-th root omega; q < 2^61 prime or Goldilocks
+bool cyclic_params_ok(u64 q, uint32_t n, u64 omega);
+bool build_cyclic_tables(u64 q, uint32_t n, u64 omega, NttHostTables& out);
 ModParams make_mod_params(u64 q, uint32_t logn);
 
 // utils.cpp:26-75 (long double CDT).  Empty vector on invalid sigma.

@@ -63,6 +63,7 @@ static bool ensure_smem(K kernel, size_t smem) {
 // Arithmetic policy of a transform: FP64 butterflies whenever they are exact for the modulus
 // (q < 2^45, unless the context was pinned to integer arithmetic), else the u64 paths.
 static int policy_of(const NttContext* c, bool inverse) {
+    if (c->mp.gold) return POL_GOLD;
     if (c->arith != 1 && c->mp.f64_ok) return POL_F64;
     return (inverse ? c->mp.lazy_inv : c->mp.lazy_fwd) ? POL_LAZY : POL_GUARD;
 }
@@ -83,6 +84,10 @@ static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t 
         auto k = ntt_tile_kernel<LOGN, LT, POL_LAZY, INV>;
         if (!ensure_smem(k, smem)) return false;
         k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+    } else if (pol == POL_GOLD) {
+        auto k = ntt_tile_kernel<LOGN, LT, POL_GOLD, INV>;
+        if (!ensure_smem(k, smem)) return false;
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
     } else {
         auto k = ntt_tile_kernel<LOGN, LT, POL_GUARD, INV>;
         if (!ensure_smem(k, smem)) return false;
@@ -100,6 +105,7 @@ static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_
     const int pol = policy_of(c, INV);
     if (pol == POL_F64)       ntt_column_kernel<LOGN, S, POL_F64, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch);
     else if (pol == POL_LAZY) ntt_column_kernel<LOGN, S, POL_LAZY, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    else if (pol == POL_GOLD) ntt_column_kernel<LOGN, S, POL_GOLD, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
     else                      ntt_column_kernel<LOGN, S, POL_GUARD, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
     return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
 }
@@ -158,6 +164,29 @@ bool ntt_inverse_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaSt
     return dispatch<true>(ctx, d_data, batch, stream);
 }
 
+// in-place bit-reversal permutation of every polynomial of the batch (index i <-> brv_logn(i))
+static __global__ void __launch_bounds__(256)
+bitrev_permute_kernel(u64* __restrict__ data, int logn, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const u32 i = (u32)(idx & (((size_t)1 << logn) - 1));
+    const u32 j = __brev(i) >> (32 - logn);
+    if (i < j) {
+        u64* p = data + (idx - i);
+        const u64 a = p[i], b = p[j];
+        p[i] = b; p[j] = a;
+    }
+}
+
+bool ntt_bitrev_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream) {
+    const size_t total = batch << ctx->logn;
+    if (total == 0) return true;
+    const size_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    bitrev_permute_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_data, (int)ctx->logn, total);
+    return cuda_ok(cudaGetLastError(), "bitrev_permute_kernel launch");
+}
+
 bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64* d_b, size_t total,
                       cudaStream_t stream) {
     if (total == 0) return true;
@@ -181,17 +210,34 @@ static std::vector<ulonglong2> to_f64_pairs(const std::vector<ulonglong2>& t, u6
     return r;
 }
 
+static NttContext* ntt_create_from(const host::NttHostTables& ht, bool cyclic);
+
 NttContext* ntt_create(u64 q, uint32_t n) {
     host::NttHostTables ht;
     if (!host::build_ntt_tables(q, n, ht)) {
         set_error("ntt_context_create: invalid (q, n)");
         return nullptr;
     }
+    return ntt_create_from(ht, false);
+}
+
+NttContext* ntt_create_cyclic(u64 q, uint32_t n, u64 omega) {
+    host::NttHostTables ht;
+    if (!host::build_cyclic_tables(q, n, omega, ht)) {
+        set_error("cyclic NTT context: invalid (q, n, omega)");
+        return nullptr;
+    }
+    return ntt_create_from(ht, true);
+}
+
+static NttContext* ntt_create_from(const host::NttHostTables& ht, bool cyclic) {
+    const u64 q = ht.q;
+    const uint32_t n = ht.n;
     const int dev = current_device_choice();
     if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return nullptr;
     NttContext* c = new (std::nothrow) NttContext;
     if (!c) return nullptr;
-    c->modulus = q; c->degree = n; c->logn = ht.logn; c->psi = ht.psi; c->device = dev;
+    c->modulus = q; c->degree = n; c->logn = ht.logn; c->psi = ht.psi; c->device = dev; c->cyclic = cyclic;
     c->mp = host::make_mod_params(q, ht.logn);
     const size_t bytes = sizeof(ulonglong2) * n;
     bool ok = cuda_ok(cudaMalloc(&c->d_fwd, bytes), "cudaMalloc(twiddles)") &&
@@ -270,7 +316,7 @@ void ntt_destroy(NttContext* c) {
 // Chunks of <= 32 MiB alternate between two streams, each running
 // H2D -> kernel -> D2H in order, so copies of one chunk overlap the kernel of
 // the other (fully so when the caller's memory is page-locked).
-bool ntt_transform_host(const NttContext* c, u64* host, size_t batch, bool inverse) {
+bool ntt_transform_host(const NttContext* c, u64* host, size_t batch, bool inverse, bool natural) {
     if (batch == 0) return true;
     std::lock_guard<std::mutex> lock(c->mu);
     if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
@@ -290,7 +336,8 @@ bool ntt_transform_host(const NttContext* c, u64* host, size_t batch, bool inver
         u64* d = static_cast<u64*>(c->scratch[b].ptr);
         u64* h = host + done * n;
         ok = cuda_ok(cudaMemcpyAsync(d, h, cnt * poly_bytes, cudaMemcpyHostToDevice, s), "H2D") &&
-             (inverse ? ntt_inverse_launch(c, d, cnt, s) : ntt_forward_launch(c, d, cnt, s)) &&
+             (inverse ? ((!natural || ntt_bitrev_launch(c, d, cnt, s)) && ntt_inverse_launch(c, d, cnt, s))
+                      : (ntt_forward_launch(c, d, cnt, s) && (!natural || ntt_bitrev_launch(c, d, cnt, s)))) &&
              cuda_ok(cudaMemcpyAsync(h, d, cnt * poly_bytes, cudaMemcpyDeviceToHost, s), "D2H");
         done += cnt;
         b ^= 1;

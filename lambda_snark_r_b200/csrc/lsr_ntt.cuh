@@ -95,6 +95,11 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                     const double X = as_d(v[j]);
                     v[j] = as_u(__dadd_rn(X, T));
                     v[jj] = as_u(__dadd_rn(X, -T));
+                } else if (POL == POL_GOLD) {
+                    const u64 T = gold_mul(v[jj], w.x);
+                    const u64 X = v[j];
+                    v[j] = gold_add(X, T);
+                    v[jj] = gold_sub(X, T);
                 } else if (POL == POL_LAZY) {
                     const u64 T = mulred4(v[jj], w.x, w.y, mp.nq);
                     const u64 X = v[j];
@@ -131,6 +136,9 @@ __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglo
         const double Xd = as_d(X), Yd = as_d(Y);
         x = f_to_canonical(mulmod_f(__dadd_rn(Xd, Yd), as_d(n_inv.x), as_d(n_inv.y), mp.qd), mp);
         y = f_to_canonical(mulmod_f(__dadd_rn(Xd, -Yd), as_d(w_scaled.x), as_d(w_scaled.y), mp.qd), mp);
+    } else if (POL == POL_GOLD) {
+        x = gold_mul(gold_add(X, Y), n_inv.x);
+        y = gold_mul(gold_sub(X, Y), w_scaled.x);
     } else if (POL == POL_LAZY) {
         const u64 C = mp.q4 << sigma;
         x = csub(csub(mulred4(X + Y, n_inv.x, n_inv.y, mp.nq), mp.q2), mp.q);
@@ -168,6 +176,9 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                         const double Xd = as_d(X), Yd = as_d(Y);
                         v[j] = as_u(__dadd_rn(Xd, Yd));
                         v[jj] = as_u(mulmod_f(__dadd_rn(Xd, -Yd), as_d(w.x), as_d(w.y), mp.qd));
+                    } else if (POL == POL_GOLD) {
+                        v[j] = gold_add(X, Y);
+                        v[jj] = gold_mul(gold_sub(X, Y), w.x);
                     } else if (POL == POL_LAZY) {
                         v[j] = X + Y;
                         v[jj] = mulred4(X + C - Y, w.x, w.y, mp.nq);
@@ -204,6 +215,7 @@ __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* 
 template <int POL>
 __device__ __forceinline__ u64 fwd_final(u64 v, const ModParams& mp) {
     if (POL == POL_F64) return f_to_canonical(reduce_f(as_d(v), mp.invq, mp.qd), mp);
+    if (POL == POL_GOLD) return v;
     if (POL == POL_LAZY) return reduce_small(v, mp);
     return csub(csub(v, mp.q2), mp.q);
 }
@@ -459,7 +471,7 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
     u64* __restrict__ g = data + tile0;
     const u32 tb = (LT < LOGN) ? (blockIdx.x & ((1u << (LOGN - LT)) - 1u)) : 0u;
     const bool clean = (!INVERSE && LT < LOGN);   // already-lazy values: no sanitiser
-    const TileIo io{g, valid, clean ? 0u : 1u, INVERSE ? mp.q2 : mp.q4};
+    const TileIo io{g, valid, clean ? 0u : 1u, POL == POL_GOLD ? mp.q : (INVERSE ? mp.q2 : mp.q4)};
 
     if constexpr (!INVERSE) {
         tile_forward_from<LOGN, LT, POL, true, 0>(sm, io, tbl, mp, TILE, tb);
@@ -508,7 +520,7 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
     u64 v[1 << S];
     if (!INVERSE) {
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) v[j] = to_working<POL>(sanitize(g[(size_t)j << LG], mp.q4, mp));
+        for (int j = 0; j < (1 << S); j++) v[j] = to_working<POL>(sanitize(g[(size_t)j << LG], POL == POL_GOLD ? mp.q : mp.q4, mp));
         fwd_network<S, POL>(v, tbl.fwd, 1u, mp);
     } else {
 #pragma unroll

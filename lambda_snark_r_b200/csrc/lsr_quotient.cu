@@ -1,0 +1,254 @@
+// lsr_quotient.cu -- SURVEY row N1: the quotient-polynomial pipeline of the prover on the GPU.
+//
+// Replaces, on the NTT path, rust-api/lambda-snark/src/r1cs.rs:474-503 (compute_quotient_poly):
+//   compute_constraint_evals      (:296-304, SparseMatrix::mul_vec sparse_matrix.rs:259-289)  -> spmv3_kernel
+//   lagrange_interpolate_ntt      (:746-793, ntt_inverse of size m over H = {omega^j})        -> inverse cyclic NTT
+//   poly_mul / poly_sub           (:846-895, O(m^2) schoolbook)                               -> size-2m NTTs + pointwise
+//   poly_div_vanishing(use_ntt)   (:995-1065, long division by X^m - 1)                       -> split of the 2m coefficients
+// The quotient of an exact division is unique, so the result is the reference's coefficient vector bit
+// for bit (canonical residues, trailing zeros trimmed by the caller-facing wrapper).
+//
+// Data flow for a batch of W witnesses of one R1CS instance (m constraints, m a power of two):
+//   E[3][W][m]   evaluations of A_z, B_z, C_z, written by the mat-vec directly in bit-reversed row
+//                order (the order the inverse transform consumes)
+//   -> inverse cyclic NTT (size m, batch 3W) -> coefficients, natural order
+//   P[3][W][2m]  zero-extended -> forward cyclic NTT (size 2m, batch 3W)
+//   N[W][2m]     A*B - C pointwise (in the first third of P) -> inverse cyclic NTT (size 2m, batch W)
+//   Q[W][m]      Q_i = N_{m+i};  N = Q*X^m - Q  <=>  N_i + Q_i = 0 for i < m  (remainder check)
+#include <algorithm>
+#include <new>
+
+#include "lsr_arith.cuh"
+#include "lsr_engine.h"
+#include "lsr_r1cs.h"
+
+namespace lsr {
+
+struct DeviceCsr {
+    uint32_t* row_ptr = nullptr;   // [3][rows + 1], offsets into col / val of the concatenated A|B|C entries
+    uint32_t* col = nullptr;
+    u64* val = nullptr;            // reduced mod q (sparse_matrix.rs:279 `val % modulus`)
+};
+
+struct QuotientState {
+    NttContext* small = nullptr;   // cyclic, size m
+    NttContext* big = nullptr;     // cyclic, size 2m
+    DeviceCsr csr;
+    DeviceScratch z, e, p, qbuf, flags;
+    PinnedScratch h_flags;
+    u64 omega = 0;
+    int device = 0;
+};
+
+void quotient_state_free(QuotientState* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->small) ntt_destroy(s->small);
+    if (s->big) ntt_destroy(s->big);
+    if (s->csr.row_ptr) cudaFree(s->csr.row_ptr);
+    if (s->csr.col) cudaFree(s->csr.col);
+    if (s->csr.val) cudaFree(s->csr.val);
+    s->z.release(); s->e.release(); s->p.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
+    delete s;
+}
+
+// ------------------------------------------------------------------ kernels
+// one thread per (witness, row); the three matrices share the witness loads
+__global__ void __launch_bounds__(256)
+spmv3_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+             const u64* __restrict__ val, const u64* __restrict__ z, uint32_t rows, uint32_t cols, int logm,
+             size_t witnesses, u64* __restrict__ E) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= witnesses * rows) return;
+    const size_t w = idx / rows;
+    const uint32_t r = (uint32_t)(idx % rows);
+    const u64* __restrict__ zw = z + w * cols;
+    const uint32_t dst = logm ? (__brev(r) >> (32 - logm)) : 0u;
+#pragma unroll
+    for (int mat = 0; mat < 3; mat++) {
+        const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
+        u64 acc = 0;
+        for (uint32_t k = rp[r]; k < rp[r + 1]; k++)
+            acc = field_add(acc, field_mul(val[k], reduce64(zw[col[k]], mp), mp), mp);     // v[col] % modulus
+        E[((size_t)mat * witnesses + w) * rows + dst] = acc;
+    }
+}
+
+// P[p][i] = i < m ? C[p][i] : 0   (p < polys, i < 2m)
+__global__ void __launch_bounds__(256)
+zero_extend_kernel(const u64* __restrict__ src, u64* __restrict__ dst, uint32_t m, size_t polys) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= polys * 2 * m) return;
+    const size_t p = idx / (2 * (size_t)m);
+    const uint32_t i = (uint32_t)(idx % (2 * (size_t)m));
+    dst[idx] = i < m ? src[p * m + i] : 0ull;
+}
+
+// N = A*B - C on the 2m-point evaluations (any order: pointwise), written over A
+__global__ void __launch_bounds__(256)
+numerator_kernel(const ModParams mp, u64* __restrict__ P, size_t per_matrix) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_matrix) return;
+    P[idx] = field_sub(field_mul(P[idx], P[per_matrix + idx], mp), P[2 * per_matrix + idx], mp);
+}
+
+// Q_i = N_{m+i}; flags[w] |= (N_i + Q_i != 0)
+__global__ void __launch_bounds__(256)
+split_kernel(const ModParams mp, const u64* __restrict__ N, u64* __restrict__ Q, uint32_t m, size_t witnesses,
+             unsigned* __restrict__ flags) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= witnesses * m) return;
+    const size_t w = idx / m;
+    const uint32_t i = (uint32_t)(idx % m);
+    const u64 lo = N[w * 2 * m + i], hi = N[w * 2 * m + m + i];
+    Q[idx] = hi;
+    if (field_add(lo, hi, mp) != 0) atomicOr(flags + w, 1u);
+}
+
+// ------------------------------------------------------------------ host side
+static bool build_csr(const R1csHandle* h, QuotientState* st) {
+    const uint32_t rows = h->rows;
+    const std::vector<SparseEntry>* mats[3] = {&h->A, &h->B, &h->C};
+    size_t total = 0;
+    for (auto* m : mats) total += m->size();
+    if (total > 0xfffffff0ull) { set_error("R1CS too large"); return false; }
+    std::vector<uint32_t> row_ptr((size_t)3 * (rows + 1), 0), col(std::max<size_t>(total, 1));
+    std::vector<u64> val(std::max<size_t>(total, 1));
+    size_t base = 0;
+    for (int k = 0; k < 3; k++) {
+        uint32_t* rp = row_ptr.data() + (size_t)k * (rows + 1);
+        std::vector<uint32_t> count(rows + 1, 0);
+        for (const SparseEntry& e : *mats[k]) {
+            if (e.row >= rows || e.col >= h->cols) { set_error("R1CS entry out of range"); return false; }
+            count[e.row + 1]++;
+        }
+        for (uint32_t r = 0; r < rows; r++) count[r + 1] += count[r];
+        for (uint32_t r = 0; r <= rows; r++) rp[r] = (uint32_t)(base + count[r]);
+        std::vector<uint32_t> fill(count.begin(), count.end() - 1);
+        for (const SparseEntry& e : *mats[k]) {                 // stable: entries of a row keep their order
+            const size_t at = base + fill[e.row]++;
+            col[at] = e.col;
+            val[at] = e.value % h->q;
+        }
+        base += mats[k]->size();
+    }
+    bool ok = cuda_ok(cudaMalloc(&st->csr.row_ptr, row_ptr.size() * 4), "cudaMalloc(csr)") &&
+              cuda_ok(cudaMalloc(&st->csr.col, col.size() * 4), "cudaMalloc(csr)") &&
+              cuda_ok(cudaMalloc(&st->csr.val, val.size() * 8), "cudaMalloc(csr)") &&
+              cuda_ok(cudaMemcpy(st->csr.row_ptr, row_ptr.data(), row_ptr.size() * 4, cudaMemcpyHostToDevice), "H2D csr") &&
+              cuda_ok(cudaMemcpy(st->csr.col, col.data(), col.size() * 4, cudaMemcpyHostToDevice), "H2D csr") &&
+              cuda_ok(cudaMemcpy(st->csr.val, val.data(), val.size() * 8, cudaMemcpyHostToDevice), "H2D csr");
+    return ok;
+}
+
+// The reference's roots: NTT_PRIMITIVE_ROOT^(2^32 / n) for Goldilocks (lambda-snark-core/src/lib.rs:78,
+// ntt.rs:214-221 compute_root_of_unity); 3^((q-1)/n) for 17592169062401 (r1cs.rs:534-547 ROOTS_OF_UNITY);
+// the minimal primitive n-th root otherwise.
+u64 reference_root_of_unity(u64 q, uint32_t n) {
+    if (n < 2 || (n & (n - 1)) || (q - 1) % n) return 0;
+    if (q == kGoldilocks) return host::powmod(1753635133440165772ULL, (1ull << 32) / n, q);
+    if (q == kDefaultModulusSmall) return host::powmod(3, (q - 1) / n, q);
+    return host::min_primitive_root(q, n);
+}
+
+static QuotientState* get_state(R1csHandle* h, u64 omega) {
+    if (h->quotient && h->quotient->omega == omega) return h->quotient;
+    if (h->quotient) { quotient_state_free(h->quotient); h->quotient = nullptr; }
+    const uint32_t m = h->rows;
+    QuotientState* st = new (std::nothrow) QuotientState;
+    if (!st) return nullptr;
+    st->device = current_device_choice();
+    st->omega = omega;
+    bool ok = cuda_ok(cudaSetDevice(st->device), "cudaSetDevice");
+    if (ok && m >= 2) {
+        st->small = ntt_create_cyclic(h->q, m, omega);
+        // any primitive 2m-th root serves the product: take the reference's family so that its square is omega
+        // whenever omega is the reference's own choice
+        u64 w2 = reference_root_of_unity(h->q, 2 * m);
+        st->big = w2 ? ntt_create_cyclic(h->q, 2 * m, w2) : nullptr;
+        ok = st->small && st->big;
+        if (!ok) set_error("quotient: the modulus has no NTT of size 2m (need 2m | q-1, q prime < 2^61 or Goldilocks)");
+    }
+    ok = ok && build_csr(h, st);
+    if (!ok) { quotient_state_free(st); return nullptr; }
+    h->quotient = st;
+    return st;
+}
+
+// witnesses: [count][cols] host words; out: [count][m] host words (Q zero-padded to m); status[count]: 0 ok,
+// 1 the witness does not satisfy the constraints (non-zero remainder)
+int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    const uint32_t m = h->rows, cols = h->cols;
+    if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^16"); return 2; }
+    if (h->q != kGoldilocks && (h->q >> 61)) { set_error("quotient: unsupported modulus"); return 2; }
+    if (m >= 2 && omega == 0) omega = reference_root_of_unity(h->q, m);
+    if (m >= 2 && !host::cyclic_params_ok(h->q, m, omega)) { set_error("quotient: omega is not a primitive m-th root of unity"); return 2; }
+    if (count == 0) return 0;
+    QuotientState* st = get_state(h, m >= 2 ? omega : 0);
+    if (!st) return 4;
+    if (!cuda_ok(cudaSetDevice(st->device), "cudaSetDevice")) return 4;
+    const ModParams mp = host::make_mod_params(h->q, 1);
+    cudaStream_t s = nullptr;      // legacy default stream: the cyclic contexts are private to this handle
+    const size_t W = count;
+    const size_t em = (size_t)3 * W * m;
+    int logm = 0;
+    while ((1u << logm) < m) ++logm;
+    bool ok = st->z.reserve(W * cols * 8) && st->e.reserve(em * 8) && st->p.reserve(em * 2 * 8) &&
+              st->qbuf.reserve(W * m * 8) && st->flags.reserve(W * 4) && st->h_flags.reserve(W * 4);
+    if (!ok) return 3;
+    u64* dz = static_cast<u64*>(st->z.ptr);
+    u64* dE = static_cast<u64*>(st->e.ptr);
+    u64* dP = static_cast<u64*>(st->p.ptr);
+    u64* dQ = static_cast<u64*>(st->qbuf.ptr);
+    unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
+    auto grid = [](size_t n) { return (unsigned)((n + 255) / 256); };
+    ok = cuda_ok(cudaMemcpyAsync(dz, witnesses, W * cols * 8, cudaMemcpyHostToDevice, s), "H2D witness") &&
+         cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
+    if (ok) {
+        spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE);
+        ok = cuda_ok(cudaGetLastError(), "spmv3_kernel");
+    }
+    if (ok && m >= 2) {
+        ok = ntt_inverse_launch(st->small, dE, 3 * W, s);
+        if (ok) {
+            zero_extend_kernel<<<grid(em * 2), 256, 0, s>>>(dE, dP, m, 3 * W);
+            ok = cuda_ok(cudaGetLastError(), "zero_extend_kernel");
+        }
+        ok = ok && ntt_forward_launch(st->big, dP, 3 * W, s);
+        if (ok) {
+            numerator_kernel<<<grid(W * 2 * m), 256, 0, s>>>(mp, dP, W * 2 * (size_t)m);
+            ok = cuda_ok(cudaGetLastError(), "numerator_kernel");
+        }
+        ok = ok && ntt_inverse_launch(st->big, dP, W, s);
+        if (ok) {
+            split_kernel<<<grid(W * m), 256, 0, s>>>(mp, dP, dQ, m, W, dF);
+            ok = cuda_ok(cudaGetLastError(), "split_kernel");
+        }
+    } else if (ok) {
+        // m = 1: A_z, B_z, C_z are constants; the numerator a*b - c has degree 0 < deg(X - 1), so the quotient is 0
+        // and the division is exact iff the numerator vanishes (r1cs.rs:1010-1020)
+        numerator_kernel<<<grid(W), 256, 0, s>>>(mp, dE, W);
+        ok = cuda_ok(cudaGetLastError(), "numerator_kernel");
+        if (ok) {
+            // reuse split semantics by hand: flags = (numerator != 0), Q = 0
+            ok = cuda_ok(cudaMemsetAsync(dQ, 0, W * 8, s), "memset");
+        }
+    }
+    ok = ok && cuda_ok(cudaMemcpyAsync(out, dQ, W * m * 8, cudaMemcpyDeviceToHost, s), "D2H quotient");
+    if (ok && m == 1) {
+        std::vector<u64> num(W);
+        ok = cuda_ok(cudaMemcpyAsync(num.data(), dE, W * 8, cudaMemcpyDeviceToHost, s), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(s), "sync");
+        for (size_t w = 0; ok && w < W; w++) status[w] = num[w] != 0 ? 1 : 0;
+        return ok ? 0 : 4;
+    }
+    ok = ok && cuda_ok(cudaMemcpyAsync(st->h_flags.ptr, dF, W * 4, cudaMemcpyDeviceToHost, s), "D2H flags") &&
+         cuda_ok(cudaStreamSynchronize(s), "sync");
+    if (!ok) return 4;
+    const unsigned* hf = static_cast<const unsigned*>(st->h_flags.ptr);
+    for (size_t w = 0; w < W; w++) status[w] = hf[w] ? 1 : 0;
+    return 0;
+}
+
+}  // namespace lsr

@@ -13,16 +13,16 @@
 #include <vector>
 
 #include "lambda_snark_b200.h"
+#include "lsr_r1cs.h"
+
+namespace lsr {
+R1csHandle::~R1csHandle() { quotient_state_free(quotient); }
+}  // namespace lsr
 
 namespace {
 
 typedef unsigned __int128 u128;
-
-struct R1csHandle {
-    std::vector<SparseEntry> A, B, C;
-    uint32_t rows = 0, cols = 0;
-    uint64_t q = 0;
-};
+using lsr::R1csHandle;
 
 // NTL::conv(ZZ_p, long): signed value reduced into [0, q)
 inline uint64_t to_field(uint64_t raw, uint64_t q) {
