@@ -325,7 +325,9 @@ int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
 /* Test hook: CDT magnitude #{k : cdf[k] < u[i]} evaluated on the device for caller-chosen
  * u (boundary cases the keystream never reaches).  variant 0 = linear scan of the table in
  * global memory (generic path), 1 = unrolled scan of the by-value table, 2 = warp-shuffle
- * binary search (fused kernel).  HOST memory.                                        */
+ * binary search over the first 31 entries + tail scan, 3 = the fused kernel's search: the
+ * compact borrow-chain search over the distinct table values when there are at most 31 of
+ * them, else variant 2.  HOST memory.                                                  */
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out,
                              int variant) LSR_NOEXCEPT;
 

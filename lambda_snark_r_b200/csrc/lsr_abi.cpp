@@ -390,7 +390,7 @@ int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LS
 
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out, int variant) LSR_NOEXCEPT {
     LSR_TRY
-    if (!u || !out || count == 0 || variant < 0 || variant > 2) return -1;
+    if (!u || !out || count == 0 || variant < 0 || variant > 3) return -1;
     return lsr::cdt_probe_host(sigma, reinterpret_cast<const u64*>(u), count, out, variant) ? 0 : -1;
     LSR_CATCH(-1)
 }

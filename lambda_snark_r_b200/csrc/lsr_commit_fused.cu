@@ -83,7 +83,10 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const size_t b = blockIdx.x;
     const u64 seed = fp.seeds[b];
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
-    const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const bool compact = cdt.compact != 0;                           // a property of the table, uniform over the grid
+    const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
+                                   : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const u32 lane_cum = cdt.dcum[threadIdx.x & 31u];
 
     // the message is consumed by the last pass only: pull it towards L2 now (one 128-byte line per thread)
     // so that the epilogue's loads do not wait on HBM
@@ -110,14 +113,17 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
 #pragma unroll
                 for (u32 w = 0; w < 8; w++) {
                     const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
-                    const u32 mag = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
+                    const u32 mag = compact ? cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u)
+                                            : cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
                     const u32 j = 8 * h + w;
                     const u32 sign = (sbits >> j) & 1u;
+                    const int sv = sign ? -(int)mag : (int)mag;                // -0 == 0: no test of mag needed
                     if (P < K) {
-                        S[swz((P << LOGN) + 16u * tau + j)] =
-                            POL == POL_F64 ? as_u((double)(int)signed_value(mag, sign)) : signed_residue(mag, sign, mp.q);
+                        // swz(i) = i ^ ((i >> 4) & 15) with i = (P << LOGN) + 16 tau + j only touches j
+                        S[(P << LOGN) + 16u * tau + (j ^ (tau & 15u))] =
+                            POL == POL_F64 ? as_u((double)sv) : signed_residue(mag, sign, mp.q);
                     } else {
-                        E[((P - K) << LOGN) + 16u * tau + j] = (signed char)signed_value(mag, sign);
+                        E[((P - K) << LOGN) + 16u * tau + j] = (signed char)sv;
                     }
                 }
             }
@@ -178,6 +184,19 @@ static bool build_cdt_param(const LweContext* c, CdtParam& out) {
     for (int i = 0; i < kCdtInline; i++) out.cdf[i] = (size_t)i < used ? c->cdf[i] : ~0ull;
     out.pad = 1;
     for (int i = 31; i < kCdtInline; i++) if ((out.cdf[i] >> 32) != 0xffffffffull) out.pad = 0;
+    // compact form: distinct values with cumulative multiplicities (the table is non-decreasing)
+    out.pad2 = 0;
+    for (int i = 0; i < 32; i++) { out.dval[i] = ~0ull; out.dcum[i] = 0; }
+    size_t distinct = 0;
+    out.compact = 1;
+    for (size_t i = 0; i < used; i++) {
+        if (i > 0 && c->cdf[i] == c->cdf[i - 1]) continue;
+        if (distinct == 31) { out.compact = 0; break; }
+        out.dval[distinct] = c->cdf[i];
+        out.dcum[distinct] = (u32)i;                          // entries strictly below this value
+        ++distinct;
+    }
+    for (size_t i = distinct; i < 32; i++) out.dcum[i] = (u32)used;
     return true;
 }
 
@@ -188,11 +207,15 @@ template <int NCH8>
 __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64* __restrict__ cdf_full, u32 cdf_n,
                                  const u64* __restrict__ u, size_t count, u32* __restrict__ out, int variant) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // count is padded to a multiple of 32
-    const u64 lane_entry = cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const bool compact = variant == 3 && cdt.compact != 0;
+    const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
+                                   : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const u32 lane_cum = cdt.dcum[threadIdx.x & 31u];
     const u64 x = i < count ? u[i] : 0;
     u32 r;
     if (variant == 0) r = cdt_magnitude_global(cdf_full, cdf_n, x);
     else if (variant == 1) r = cdt_magnitude<NCH8>(cdt, x);
+    else if (compact) r = cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, x);
     else r = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, x);
     if (i < count) out[i] = r;
 }

@@ -53,6 +53,14 @@ struct CdtParam {
     u32 count;                 // entries in use (<= kCdtInline); trailing 2^64-1 entries trimmed
     u32 pad;                   // 1 if every entry with index >= 31 has high word 0xffffffff (32-bit tail scan)
     u64 cdf[kCdtInline];       // unused entries = 2^64-1 (never "below u")
+    // Compact form (build_cdt_param): the DISTINCT table values below 2^64-1 in ascending order with the
+    // number of table entries they stand for.  The reference's long-double table saturates (sigma = 3.19:
+    // cdf[29..38] are all 2^64-2), so 39 entries are 30 distinct values and the whole table fits one value
+    // per lane: no tail scan at all.  #{k : cdf[k] < u} = dcum[#{i : dval[i] < u}].
+    u32 compact;               // 1 if there are at most 31 distinct values
+    u32 pad2;
+    u64 dval[32];              // unused = 2^64-1; dval[31] is always 2^64-1
+    u32 dcum[32];              // dcum[i] = number of table entries < dval[i] (= entries counted by dval[0..i-1])
 };
 
 // magnitude = #{k : cdf[k] < u}; NCH8 = ceil(count / 8)
@@ -110,6 +118,32 @@ __device__ __forceinline__ u32 cdt_magnitude_shfl(const CdtParam& t, u64 lane_en
         for (int k = 31; k < NCH8 * 8; k++) pos += (u32)(t.cdf[k] < u);
     }
     return pos;
+}
+
+// Compact search (CdtParam::compact): 31 distinct values, one per lane (lane_val = dval[lane]), and the
+// cumulative entry counts (lane_cum = dcum[lane]).  Five 64-bit comparisons, each the carry of
+// u + ~v (= [v < u]; an add.cc / addc.cc pair on the complemented table value, so only add-type carries
+// are chained) shifted into the position with addc (pos = 2 pos + carry): a step is two shuffles, two
+// ALU-pipe additions, one FMA-pipe add-with-carry and the probe index -- the sampler phase is bound by
+// the ALU pipe (2 cycles per warp instruction), which the compare / select / add formulation of
+// cdt_magnitude_shfl loads twice as much.  The first probe (dval[15]) is the same for every lane and
+// comes from the constant bank; the last shuffle turns the position into the entry count.  No branch
+// and no address depends on u.  All 32 lanes must call.
+__device__ __forceinline__ u32 cdt_magnitude_compact(u64 mid, u64 lane_val, u32 lane_cum, u64 u) {
+    const u32 e_lo = ~(u32)lane_val, e_hi = ~(u32)(lane_val >> 32);
+    const u32 u_lo = (u32)u, u_hi = (u32)(u >> 32);
+    u32 p;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %3;\n\taddc.cc.u32 t, %2, %4;\n\taddc.u32 %0, 0, 0;\n\t}"
+        : "=r"(p) : "r"(~(u32)mid), "r"(~(u32)(mid >> 32)), "r"(u_lo), "r"(u_hi));
+#pragma unroll
+    for (int i = 1; i < 5; i++) {
+        const u32 probe = p * (1u << (5 - i)) + ((1u << (4 - i)) - 1u);       // pos + half - 1, pos = p << (5 - i)
+        const u32 v_lo = __shfl_sync(0xffffffffu, e_lo, probe);
+        const u32 v_hi = __shfl_sync(0xffffffffu, e_hi, probe);
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %3;\n\taddc.cc.u32 t, %2, %4;\n\taddc.u32 %0, %0, %0;\n\t}"
+            : "+r"(p) : "r"(v_lo), "r"(v_hi), "r"(u_lo), "r"(u_hi));
+    }
+    return __shfl_sync(0xffffffffu, lane_cum, p);                             // p = #{i < 31 : dval[i] < u}
 }
 
 // table in global memory, any size

@@ -345,7 +345,7 @@ def test_cdt_search_variants_on_boundaries(gpu, rng):
         us += [int(x) | 0xFFFFFFFF00000000 for x in rng.integers(0, 2**32, 500, dtype=np.uint64)]   # tail region
         u = np.array(us, dtype=np.uint64)
         want = np.array([abs(O.cdt_sample(cdf, int(x), 0)) for x in u], dtype=np.uint32)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             out = np.zeros(u.size, dtype=np.uint32)
             rc = lib.lsr_cdt_magnitude_device(sigma, u.ctypes.data_as(capi.u64p), u.size,
                                               out.ctypes.data_as(C.POINTER(C.c_uint32)), variant)
