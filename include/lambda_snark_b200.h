@@ -274,7 +274,7 @@ int lsr_cyclic_ntt_inverse(const NttContext* ctx, uint64_t* evals, size_t batch)
 /* Quotient polynomial Q(X) = (A_z(X) B_z(X) - C_z(X)) / (X^m - 1) of the R1CS instance behind `r1cs`
  * (lambda_snark_r1cs_create), A_z, B_z, C_z interpolated over H = {omega^j}: compute_quotient_poly on
  * its NTT path (r1cs.rs:474-503, :746-793, :995-1065).  m = number of constraints, a power of two
- * <= 2^16; matrix values and witness words are reduced as unsigned words (sparse_matrix.rs:279).
+ * <= 2^23; matrix values and witness words are reduced as unsigned words (sparse_matrix.rs:279).
  * One witness: `out` receives the coefficients with trailing zeros removed (*out_len >= 1, out_cap >= m);
  * LAMBDA_SNARK_ERR_CRYPTO_FAILED when the witness does not satisfy the constraints.
  * Batch: witnesses [count][witness_len] -> out [count][m] zero-padded, status[count] (0 ok, 1 unsatisfied). */
@@ -282,6 +282,26 @@ LambdaSnarkError lsr_r1cs_quotient(void* r1cs, const uint64_t* witness, size_t w
                                    uint64_t* out, size_t out_cap, size_t* out_len) LSR_NOEXCEPT;
 int lsr_r1cs_quotient_batch(void* r1cs, const uint64_t* witnesses, size_t witness_len, size_t count,
                             uint64_t omega, uint64_t* out, int* status) LSR_NOEXCEPT;
+
+/* Commitment phase of the prover for a circuit larger than one ring element (BASELINE configs[4]; replaces
+ * compute_quotient_poly + Commitment::new of prove_r1cs, rust-api/lambda-snark/src/lib.rs:747-757, where the
+ * reference silently truncates Q to ring_degree coefficients -- cpp-core/src/commitment.cpp:146-149).
+ * The quotient of every witness is cut into chunks = max(1, m / ring_degree) messages of ring_degree coefficients
+ * (one message of m coefficients when m < ring_degree); message (w, j) is committed with seeds[w * chunks + j]
+ * exactly as lwe_commit_batch would commit it.  Only chunk indices [chunk_lo, chunk_hi) are committed -- a rank's
+ * slice of a job sharded over GPUs; seeds is always indexed globally ([count][chunks]) so the containers do not
+ * depend on the sharding.  Quotient and messages never leave the device.
+ * out: [count][chunk_hi - chunk_lo][1 + k n] words; status[count]: 0 ok, 1 witness does not satisfy the
+ * constraints (its containers are then commitments to a meaningless quotient and must be discarded).
+ * Returns a LambdaSnarkError code.  _device: witnesses, seeds and out are DEVICE pointers on the context's
+ * device (status stays on the host); the call synchronises before returning.                                  */
+size_t lsr_prover_quotient_chunks(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT;
+int lsr_prover_commit_quotient(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len,
+                               size_t count, uint64_t omega, const uint64_t* seeds, size_t chunk_lo,
+                               size_t chunk_hi, uint64_t* out, int* status) LSR_NOEXCEPT;
+int lsr_prover_commit_quotient_device(void* r1cs, LweContext* ctx, const uint64_t* d_witnesses,
+                                      size_t witness_len, size_t count, uint64_t omega, const uint64_t* d_seeds,
+                                      size_t chunk_lo, size_t chunk_hi, uint64_t* d_out, int* status) LSR_NOEXCEPT;
 
 /* Arithmetic of the NTT butterflies (NttContext, and the NttContext inside an
  * LweContext): 0 auto -- FP64-pipe butterflies (exact modular products by

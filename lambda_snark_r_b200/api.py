@@ -202,6 +202,62 @@ class R1CS:
         self._h = h
         self.rows, self.cols, self.modulus = rows, cols, modulus
 
+    @classmethod
+    def from_arrays(cls, rows: int, cols: int, A, B, C, modulus: int) -> "R1CS":
+        """Same handle from numpy triples (row[], col[], value[]) per matrix -- no per-entry Python work, for
+        circuits with millions of constraints.  The buffer has the SparseEntry layout of r1cs.h:38-43."""
+        from .capi import SparseEntry, SparseMatrix
+        import ctypes as C_
+        self = cls.__new__(cls)
+        self._keep = []
+        mats = []
+        dt = np.dtype([("row", np.uint32), ("col", np.uint32), ("value", np.uint64)])
+        assert dt.itemsize == C_.sizeof(SparseEntry)
+        for r, c, v in (A, B, C):
+            arr = np.zeros(max(len(r), 1), dtype=dt)
+            arr["row"][: len(r)], arr["col"][: len(r)], arr["value"][: len(r)] = r, c, v
+            self._keep.append(arr)
+            mats.append(SparseMatrix(arr.ctypes.data_as(C_.POINTER(SparseEntry)), len(r), rows, cols))
+        h = C_.c_void_p()
+        rc = _lib().lambda_snark_r1cs_create(C_.byref(mats[0]), C_.byref(mats[1]), C_.byref(mats[2]), modulus, C_.byref(h))
+        if rc != 0:
+            raise LambdaSnarkError(f"lambda_snark_r1cs_create failed with code {rc}")
+        self._h = h
+        self.rows, self.cols, self.modulus = rows, cols, modulus
+        return self
+
+    def quotient_chunks(self, ctx: "LweContext") -> int:
+        return int(_lib().lsr_prover_quotient_chunks(self._h, ctx.as_ptr()))
+
+    def commit_quotient(self, ctx: "LweContext", witnesses, seeds, chunk_lo: int = 0, chunk_hi: int | None = None,
+                        omega: int = 0):
+        """Commitment phase of prove_r1cs (lib.rs:747-757) for quotients longer than one ring element:
+        witnesses [count][cols], seeds [count][chunks] (global chunk index) -> (containers
+        [count][chunk_hi - chunk_lo][1 + k n], status [count]).  Q stays on the device."""
+        import ctypes as C_
+        w = np.ascontiguousarray(_u64(witnesses)).reshape(-1, self.cols)
+        chunks = self.quotient_chunks(ctx)
+        chunk_hi = chunks if chunk_hi is None else chunk_hi
+        sd = np.ascontiguousarray(_u64(seeds)).reshape(w.shape[0], chunks)
+        out = np.zeros((w.shape[0], chunk_hi - chunk_lo, ctx.words), dtype=np.uint64)
+        status = np.zeros(w.shape[0], dtype=np.int32)
+        rc = _lib().lsr_prover_commit_quotient(self._h, ctx.as_ptr(), _p(w), self.cols, w.shape[0], omega, _p(sd),
+                                               chunk_lo, chunk_hi, _p(out), status.ctypes.data_as(C_.POINTER(C_.c_int)))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_prover_commit_quotient failed with code {rc}: {last_error()}")
+        return out, status
+
+    def commit_quotient_device(self, ctx: "LweContext", witnesses_ptr: int, count: int, seeds_ptr: int, out_ptr: int,
+                               chunk_lo: int, chunk_hi: int, omega: int = 0) -> np.ndarray:
+        import ctypes as C_
+        status = np.zeros(count, dtype=np.int32)
+        rc = _lib().lsr_prover_commit_quotient_device(self._h, ctx.as_ptr(), witnesses_ptr, self.cols, count, omega,
+                                                      seeds_ptr, chunk_lo, chunk_hi, out_ptr,
+                                                      status.ctypes.data_as(C_.POINTER(C_.c_int)))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_prover_commit_quotient_device failed with code {rc}: {last_error()}")
+        return status
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             try:

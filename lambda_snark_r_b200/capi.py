@@ -97,6 +97,12 @@ SIGNATURES = {
     "lsr_cyclic_ntt_inverse": (C.c_int, [C.c_void_p, u64p, C.c_size_t]),
     "lsr_r1cs_quotient": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lsr_r1cs_quotient_batch": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.POINTER(C.c_int)]),
+    "lsr_prover_quotient_chunks": (C.c_size_t, [C.c_void_p, C.c_void_p]),
+    "lsr_prover_commit_quotient": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p,
+                                            C.c_size_t, C.c_size_t, u64p, C.POINTER(C.c_int)]),
+    "lsr_prover_commit_quotient_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
+                                                   C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                   C.POINTER(C.c_int)]),
     "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
     "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),

@@ -17,6 +17,8 @@
 namespace lsr {
 u64 reference_root_of_unity(u64 q, uint32_t n);
 int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status);
+int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
+                           const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, bool io_on_device, int* status);
 }
 
 using lsr::u64;
@@ -172,6 +174,39 @@ LambdaSnarkError lsr_r1cs_quotient(void* r1cs, const uint64_t* witness, size_t w
     while (len > 1 && out[len - 1] == 0) --len;
     *out_len = len;
     return LAMBDA_SNARK_OK;
+    LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
+}
+
+size_t lsr_prover_quotient_chunks(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT {
+    if (!r1cs || !ctx) return 0;
+    const lsr::R1csHandle* h = static_cast<const lsr::R1csHandle*>(r1cs);
+    return h->rows <= ctx->n ? 1 : (size_t)h->rows / ctx->n;
+}
+
+static int prover_commit_impl(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len, size_t count,
+                              uint64_t omega, const uint64_t* seeds, size_t chunk_lo, size_t chunk_hi, uint64_t* out,
+                              int* status, bool on_device) {
+    if (!r1cs || !ctx || !witnesses || !seeds || !out || !status) return LAMBDA_SNARK_ERR_NULL_PTR;
+    lsr::R1csHandle* h = static_cast<lsr::R1csHandle*>(r1cs);
+    if (witness_len != h->cols) return LAMBDA_SNARK_ERR_INVALID_PARAMS;
+    return lsr::prover_commit_quotient(h, ctx, reinterpret_cast<const u64*>(witnesses), count, omega,
+                                       reinterpret_cast<const u64*>(seeds), chunk_lo, chunk_hi,
+                                       reinterpret_cast<u64*>(out), on_device, status);
+}
+
+int lsr_prover_commit_quotient(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len, size_t count,
+                               uint64_t omega, const uint64_t* seeds, size_t chunk_lo, size_t chunk_hi, uint64_t* out,
+                               int* status) LSR_NOEXCEPT {
+    LSR_TRY
+    return prover_commit_impl(r1cs, ctx, witnesses, witness_len, count, omega, seeds, chunk_lo, chunk_hi, out, status, false);
+    LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
+}
+
+int lsr_prover_commit_quotient_device(void* r1cs, LweContext* ctx, const uint64_t* d_witnesses, size_t witness_len,
+                                      size_t count, uint64_t omega, const uint64_t* d_seeds, size_t chunk_lo,
+                                      size_t chunk_hi, uint64_t* d_out, int* status) LSR_NOEXCEPT {
+    LSR_TRY
+    return prover_commit_impl(r1cs, ctx, d_witnesses, witness_len, count, omega, d_seeds, chunk_lo, chunk_hi, d_out, status, true);
     LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
 }
 

@@ -17,6 +17,7 @@ typedef unsigned int u32;
 constexpr u64 kDefaultModulusSmall = 17592169062401ULL;  // reference r1cs.rs:527, 2-adicity 13
 constexpr u64 kDefaultModulusLarge = 17592180539393ULL;  // 44-bit, 2-adicity 18
 constexpr int kMaxLogN = 17;                              // SEAL_POLY_MOD_DEGREE_MAX = 131072
+constexpr int kMaxEngineLogN = 24;                        // cyclic transforms of the quotient pipeline (3 column passes + tile)
 constexpr int kChaChaRounds = 8;
 
 constexpr u32 kDomMatrix = 0x01000000u;

@@ -184,7 +184,7 @@ static void transpose_last_pass_impl(NttHostTables& out) {
 }
 
 bool cyclic_params_ok(u64 q, uint32_t n, u64 omega) {
-    if (n < 2 || (n & (n - 1)) || n > (1u << kMaxLogN)) return false;
+    if (n < 2 || (n & (n - 1)) || n > (1u << kMaxEngineLogN)) return false;
     if (q != kGoldilocks && (q < 3 || (q >> 61))) return false;
     if ((q - 1) % n) return false;
     if (omega == 0 || omega >= q) return false;

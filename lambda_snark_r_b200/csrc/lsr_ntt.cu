@@ -68,8 +68,9 @@ static int policy_of(const NttContext* c, bool inverse) {
     return (inverse ? c->mp.lazy_inv : c->mp.lazy_fwd) ? POL_LAZY : POL_GUARD;
 }
 
-template <int LOGN, int LT, bool INV>
-static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s) {
+// d = log n - LT for block tiles (WHOLE = false), ignored otherwise
+template <int LT, bool WHOLE, bool INV>
+static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s, u32 dlog = 0) {
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
     const size_t smem = sizeof(u64) << TL;
     const size_t tiles = (total + ((size_t)1 << TL) - 1) >> TL;
@@ -77,56 +78,92 @@ static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t 
     if (tiles > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
     if (pol == POL_F64) {
-        auto k = ntt_tile_kernel<LOGN, LT, POL_F64, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_F64, INV>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables_f, d, total);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables_f, d, total, dlog);
     } else if (pol == POL_LAZY) {
-        auto k = ntt_tile_kernel<LOGN, LT, POL_LAZY, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_LAZY, INV>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
     } else if (pol == POL_GOLD) {
-        auto k = ntt_tile_kernel<LOGN, LT, POL_GOLD, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_GOLD, INV>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
     } else {
-        auto k = ntt_tile_kernel<LOGN, LT, POL_GUARD, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_GUARD, INV>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
     }
     return cuda_ok(cudaGetLastError(), "ntt_tile_kernel launch");
 }
 
-template <int LOGN, int S, bool INV>
-static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
-    const size_t cols = batch << (LOGN - S);
+template <int S, bool INV, bool FIRST>
+static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+    const size_t cols = batch << (logn - S);
     const size_t blocks = (cols + kNttThreads - 1) / kNttThreads;
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
-    if (pol == POL_F64)       ntt_column_kernel<LOGN, S, POL_F64, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch);
-    else if (pol == POL_LAZY) ntt_column_kernel<LOGN, S, POL_LAZY, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
-    else if (pol == POL_GOLD) ntt_column_kernel<LOGN, S, POL_GOLD, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
-    else                      ntt_column_kernel<LOGN, S, POL_GUARD, INV><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch);
+    if (pol == POL_F64)       ntt_column_kernel<S, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0);
+    else if (pol == POL_LAZY) ntt_column_kernel<S, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    else if (pol == POL_GOLD) ntt_column_kernel<S, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    else                      ntt_column_kernel<S, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
     return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
 }
 
+template <bool INV, bool FIRST>
+static bool launch_column_s(int S, const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+    switch (S) {
+        case 1: return launch_column<1, INV, FIRST>(c, d, batch, s, logn, s0);
+        case 2: return launch_column<2, INV, FIRST>(c, d, batch, s, logn, s0);
+        case 3: return launch_column<3, INV, FIRST>(c, d, batch, s, logn, s0);
+        case 4: return launch_column<4, INV, FIRST>(c, d, batch, s, logn, s0);
+        case 5: return launch_column<5, INV, FIRST>(c, d, batch, s, logn, s0);
+        default: set_error("bad column pass"); return false;
+    }
+}
+
 // n <= 2^13: one kernel, the polynomial never leaves shared memory.
-// n >= 2^14: column kernel (first LOGN-12 stages) + tile kernel on 4096-blocks.
+// n >= 2^14: column passes (first log n - 12 stages, at most 5 per pass: one pass up to 2^17, two up to
+// 2^22, three up to 2^24) + tile kernel on 4096-blocks.
 // (n = 2^14 fits one CTA's shared memory, but at one 8-warp CTA per SM it ran at
 // 625 G butterflies/s against 800 for the two-kernel path: profiles/r01_ntt_sweep.json)
 // (Issuing the two kernels in L2-sized batch chunks so the second finds the first one's output on chip
 // was measured and rejected: 16/32/64 MB chunks ran at 0.60/0.77/0.85 of the whole-batch rate -- the
 // small dependent launches cost more in tails than the second HBM round trip does.)
 template <int LOGN, bool INV>
-static bool launch_transform(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
-    const size_t total = batch << LOGN;
-    if constexpr (LOGN <= 13) {
-        return launch_tile<LOGN, LOGN, INV>(c, d, total, s);
-    } else {
-        constexpr int S = LOGN - 12;
-        if (!INV) return launch_column<LOGN, S, false>(c, d, batch, s) && launch_tile<LOGN, 12, false>(c, d, total, s);
-        return launch_tile<LOGN, 12, true>(c, d, total, s) && launch_column<LOGN, S, true>(c, d, batch, s);
+static bool launch_whole(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    return launch_tile<LOGN, true, INV>(c, d, batch << LOGN, s);
+}
+
+template <bool INV>
+static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+    const u32 logn = c->logn;
+    const int C = (int)logn - 12;                       // column stages
+    const int passes = (C + 4) / 5;
+    int S[3] = {0, 0, 0}, s0[3] = {0, 0, 0};
+    for (int i = 0, left = C, at = 0; i < passes; i++) {
+        S[i] = (left + (passes - i) - 1) / (passes - i);   // as even as possible, larger passes first
+        s0[i] = at;
+        at += S[i];
+        left -= S[i];
     }
+    const size_t total = batch << logn;
+    if (!INV) {
+        for (int i = 0; i < passes; i++) {
+            const bool ok = i == 0 ? launch_column_s<false, true>(S[i], c, d, batch, s, logn, (u32)s0[i])
+                                   : launch_column_s<false, false>(S[i], c, d, batch, s, logn, (u32)s0[i]);
+            if (!ok) return false;
+        }
+        return launch_tile<12, false, false>(c, d, total, s, (u32)C);
+    }
+    if (!launch_tile<12, false, true>(c, d, total, s, (u32)C)) return false;
+    for (int i = passes - 1; i >= 0; i--) {
+        const bool ok = i == 0 ? launch_column_s<true, true>(S[i], c, d, batch, s, logn, (u32)s0[i])
+                               : launch_column_s<true, false>(S[i], c, d, batch, s, logn, (u32)s0[i]);
+        if (!ok) return false;
+    }
+    return true;
 }
 
 template <bool INV>
@@ -136,24 +173,23 @@ static bool dispatch(const NttContext* c, u64* d, size_t batch, cudaStream_t s) 
         return false;
     }
     switch (c->logn) {
-        case 1: return launch_transform<1, INV>(c, d, batch, s);
-        case 2: return launch_transform<2, INV>(c, d, batch, s);
-        case 3: return launch_transform<3, INV>(c, d, batch, s);
-        case 4: return launch_transform<4, INV>(c, d, batch, s);
-        case 5: return launch_transform<5, INV>(c, d, batch, s);
-        case 6: return launch_transform<6, INV>(c, d, batch, s);
-        case 7: return launch_transform<7, INV>(c, d, batch, s);
-        case 8: return launch_transform<8, INV>(c, d, batch, s);
-        case 9: return launch_transform<9, INV>(c, d, batch, s);
-        case 10: return launch_transform<10, INV>(c, d, batch, s);
-        case 11: return launch_transform<11, INV>(c, d, batch, s);
-        case 12: return launch_transform<12, INV>(c, d, batch, s);
-        case 13: return launch_transform<13, INV>(c, d, batch, s);
-        case 14: return launch_transform<14, INV>(c, d, batch, s);
-        case 15: return launch_transform<15, INV>(c, d, batch, s);
-        case 16: return launch_transform<16, INV>(c, d, batch, s);
-        case 17: return launch_transform<17, INV>(c, d, batch, s);
-        default: set_error("unsupported ring degree"); return false;
+        case 1: return launch_whole<1, INV>(c, d, batch, s);
+        case 2: return launch_whole<2, INV>(c, d, batch, s);
+        case 3: return launch_whole<3, INV>(c, d, batch, s);
+        case 4: return launch_whole<4, INV>(c, d, batch, s);
+        case 5: return launch_whole<5, INV>(c, d, batch, s);
+        case 6: return launch_whole<6, INV>(c, d, batch, s);
+        case 7: return launch_whole<7, INV>(c, d, batch, s);
+        case 8: return launch_whole<8, INV>(c, d, batch, s);
+        case 9: return launch_whole<9, INV>(c, d, batch, s);
+        case 10: return launch_whole<10, INV>(c, d, batch, s);
+        case 11: return launch_whole<11, INV>(c, d, batch, s);
+        case 12: return launch_whole<12, INV>(c, d, batch, s);
+        case 13: return launch_whole<13, INV>(c, d, batch, s);
+        default:
+            if (c->logn >= 14 && c->logn <= (uint32_t)kMaxEngineLogN) return launch_big<INV>(c, d, batch, s);
+            set_error("unsupported ring degree");
+            return false;
     }
 }
 

@@ -283,17 +283,20 @@ struct NoEpilogue {
     __device__ __forceinline__ u64 operator()(u32, u64 v) const { return v; }
 };
 
-template <int LOGN, int LT, int S, int R, int POL, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue>
+// WHOLE: the tile holds whole polynomials (LT == log n).  Otherwise it is one 2^LT block of a larger
+// polynomial and d = log n - LT (a run-time value: one kernel serves every big ring degree) only enters
+// the twiddle indices.  SL = first stage of the pass, counted inside the block.
+template <int LT, bool WHOLE, int SL, int R, int POL, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io, const NttTables& tb_,
-                                          const ModParams& mp, u32 items, u32 tb, const Epi& epi = Epi()) {
-    constexpr int LG = LOGN - S - R;          // log2 of the element stride g
+                                          const ModParams& mp, u32 items, u32 tb, u32 d_, const Epi& epi = Epi()) {
+    constexpr int LG = LT - SL - R;           // log2 of the element stride g
     constexpr u32 g = 1u << LG;
-    constexpr int SL = S - (LOGN - LT);       // stage index local to the block
     static_assert(LG >= 0 && SL >= 0, "bad pass");
+    const u32 d = WHOLE ? 0u : d_;
     // unit-stride radix-16 pass of a multi-pass plan: per-work-item twiddles, transposed table
     constexpr bool LL = (LG == 0) && (R == 4) && (LT > 4);
-    constexpr bool HEAD = (S == 0) && (LT == LOGN) && !LL;     // twiddles 1 .. 2^R - 1, grid-uniform
-    constexpr u32 ll_stride = 1u << (LOGN - R);
+    constexpr bool HEAD = (SL == 0) && WHOLE && !LL;           // twiddles 1 .. 2^R - 1, grid-uniform
+    const u32 ll_stride = 1u << (d + LT - R);
     const ulonglong2* __restrict__ tw = LL ? (INVERSE ? tb_.inv_last : tb_.fwd_last) : (INVERSE ? tb_.inv : tb_.fwd);
     for (u32 W = threadIdx.x; W < items; W += blockDim.x) {
         const u32 poly = W >> (LT - R);                   // polynomial slot within the tile
@@ -301,7 +304,7 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         const u32 blk = w >> LG;
         const u32 c = w & (g - 1u);
         const u32 base = (poly << LT) + (blk << (LG + R)) + c;
-        const u32 T0 = LL ? ((tb << (LT - R)) + w) : ((1u << S) + (tb << SL) + blk);
+        const u32 T0 = LL ? ((tb << (LT - R)) + w) : ((1u << (d + SL)) + (tb << SL) + blk);
         const bool live = (IN == IO_GLOBAL || OUT == IO_GLOBAL) ? ((poly << LT) < io.valid) : true;
         u64 v[1 << R];
         if constexpr (IN == IO_GLOBAL && LG == 0 && R >= 1) {
@@ -349,8 +352,8 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
                 for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<POL>(v[j], mp);
             }
         } else {
-            constexpr int sigma0 = LOGN - S - R;          // inverse stages already done
-            static_assert(!INVERSE || !FINAL || S == 0, "final inverse pass must contain stage 0");
+            constexpr int sigma0 = LT - SL - R;           // inverse stages already done
+            static_assert(!INVERSE || !FINAL || (SL == 0 && WHOLE), "final inverse pass must contain stage 0");
             inv_network<R, POL, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
         }
         if constexpr (OUT == IO_GLOBAL && LG == 0 && R >= 1 && std::is_same<Epi, NoEpilogue>::value) {
@@ -386,34 +389,34 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
 //              inverse expects the tile in shared memory (global when one
 //              pass) and writes its last pass to global memory.
 // ---------------------------------------------------------------------------
-template <int LOGN, int LT, int POL, bool GIO, int I, bool FIN = true>
+template <int LT, bool WHOLE, int POL, bool GIO, int I, bool FIN = true>
 __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, const NttTables& t,
-                                                  const ModParams& mp, u32 tile_elems, u32 tb) {
+                                                  const ModParams& mp, u32 tile_elems, u32 tb, u32 d) {
     using P = plan<LT>;
     if constexpr (I < P::N) {
-        constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
+        constexpr int SL = (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && (P::N == 1 || (ntt_direct_out<POL>() && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LOGN, LT, S, R, POL, false, (FIN && I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb);
+        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT>(sm, io, t, mp, tile_elems >> R, tb, d);
         if constexpr (OUT == IO_SMEM) __syncthreads();
-        tile_forward_from<LOGN, LT, POL, GIO, I + 1, FIN>(sm, io, t, mp, tile_elems, tb);
+        tile_forward_from<LT, WHOLE, POL, GIO, I + 1, FIN>(sm, io, t, mp, tile_elems, tb, d);
     }
 }
 
-template <int LOGN, int LT, int POL, bool GIO, int I, typename Epi = NoEpilogue>
+template <int LT, bool WHOLE, int POL, bool GIO, int I, typename Epi = NoEpilogue>
 __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, const NttTables& t,
-                                                  const ModParams& mp, u32 tile_elems, u32 tb,
+                                                  const ModParams& mp, u32 tile_elems, u32 tb, u32 d,
                                                   const Epi& epi = Epi()) {
     using P = plan<LT>;
     if constexpr (I >= 0) {
-        constexpr int S = (LOGN - LT) + (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
+        constexpr int SL = (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && (P::N == 1 || (LSR_NTT_DIRECT_IN && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LOGN, LT, S, R, POL, true, (I == 0 && LT == LOGN), IN, OUT, Epi>(sm, io, t, mp, tile_elems >> R, tb, epi);
+        tile_pass<LT, WHOLE, SL, R, POL, true, (I == 0 && WHOLE), IN, OUT, Epi>(sm, io, t, mp, tile_elems >> R, tb, d, epi);
         if constexpr (OUT == IO_SMEM) __syncthreads();
-        tile_inverse_from<LOGN, LT, POL, GIO, I - 1, Epi>(sm, io, t, mp, tile_elems, tb, epi);
+        tile_inverse_from<LT, WHOLE, POL, GIO, I - 1, Epi>(sm, io, t, mp, tile_elems, tb, d, epi);
     }
 }
 
@@ -423,14 +426,16 @@ __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, con
 template <int LOGN, int LT, int POL>
 __device__ __forceinline__ void tile_forward(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
+    static_assert(LOGN == LT, "whole polynomials only");
     const TileIo io{nullptr, tile_elems, 0u, 0ull};
-    tile_forward_from<LOGN, LT, POL, false, 0, POL != POL_F64>(sm, io, t, mp, tile_elems, tb);
+    tile_forward_from<LT, true, POL, false, 0, POL != POL_F64>(sm, io, t, mp, tile_elems, tb, 0u);
 }
 template <int LOGN, int LT, int POL>
 __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
+    static_assert(LOGN == LT, "whole polynomials only");
     const TileIo io{nullptr, tile_elems, 0u, 0ull};
-    tile_inverse_from<LOGN, LT, POL, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb);
+    tile_inverse_from<LT, true, POL, false, plan<LT>::N - 1>(sm, io, t, mp, tile_elems, tb, 0u);
 }
 
 // shared memory in, last pass straight to global memory through an epilogue
@@ -439,8 +444,9 @@ template <int LOGN, int LT, int POL, typename Epi>
 __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const NttTables& t, const ModParams& mp,
                                                        u32 tile_elems, const Epi& epi) {
     static_assert(plan<LT>::N > 1, "single-pass plans read from global memory");
+    static_assert(LOGN == LT, "whole polynomials only");
     const TileIo io{g, tile_elems, 0u, 0ull};
-    tile_inverse_from<LOGN, LT, POL, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, epi);
+    tile_inverse_from<LT, true, POL, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, 0u, epi);
 }
 
 // ---------------------------------------------------------------------------
@@ -458,9 +464,9 @@ __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const Nt
 template <int LT>
 constexpr int ntt_min_blocks() { return LT <= 12 ? LSR_NTT_MINB : (LT == 13 ? 2 : 1); }
 
-template <int LOGN, int LT, int POL, bool INVERSE>
+template <int LT, bool WHOLE, int POL, bool INVERSE>
 __global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
-ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems) {
+ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems, u32 d) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
     constexpr u32 TILE = 1u << TL;
@@ -469,12 +475,12 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
     const size_t tile0 = (size_t)blockIdx.x << TL;
     const u32 valid = (u32)((total_elems - tile0) < TILE ? (total_elems - tile0) : TILE);
     u64* __restrict__ g = data + tile0;
-    const u32 tb = (LT < LOGN) ? (blockIdx.x & ((1u << (LOGN - LT)) - 1u)) : 0u;
-    const bool clean = (!INVERSE && LT < LOGN);   // already-lazy values: no sanitiser
+    const u32 tb = WHOLE ? 0u : (blockIdx.x & ((1u << d) - 1u));
+    const bool clean = (!INVERSE && !WHOLE);      // already-lazy values: no sanitiser
     const TileIo io{g, valid, clean ? 0u : 1u, POL == POL_GOLD ? mp.q : (INVERSE ? mp.q2 : mp.q4)};
 
     if constexpr (!INVERSE) {
-        tile_forward_from<LOGN, LT, POL, true, 0>(sm, io, tbl, mp, TILE, tb);
+        tile_forward_from<LT, WHOLE, POL, true, 0>(sm, io, tbl, mp, TILE, tb, d);
         if constexpr (!ONE_PASS && !ntt_direct_out<POL>()) {
 #pragma unroll 4
             for (u32 k = 0; k < PER_THREAD; k++) {
@@ -497,35 +503,44 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
             }
             __syncthreads();
         }
-        tile_inverse_from<LOGN, LT, POL, true, plan<LT>::N - 1>(sm, io, tbl, mp, TILE, tb);
+        tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1>(sm, io, tbl, mp, TILE, tb, d);
     }
 }
 
 // ---------------------------------------------------------------------------
-// Big-n helper (n > 2^14): the first S = LOGN - LT forward stages (or the last
-// S inverse stages) touch coefficients n/2^S apart; each thread owns the 2^S
-// coefficients of one column, straight from / to global memory (coalesced
-// across threads), no shared memory.
+// Big-n helper (n >= 2^14): S forward stages s0 .. s0+S-1 ahead of the 4096-blocks of the tile kernel
+// (or the matching inverse stages behind it).  At stage s0 a polynomial is 2^s0 blocks of
+// n >> s0 coefficients; the S stages couple coefficients g = n >> (s0 + S) apart inside a block.
+// A thread owns the 2^S coefficients of one column, straight from / to global memory (consecutive
+// threads take consecutive columns: coalesced, g >= 4096), no shared memory.  log n, s0 are
+// run-time values: n <= 2^17 needs one such pass (S <= 5), the cyclic transforms of the quotient
+// pipeline (up to 2^24) chain two or three.  FIRST: the pass reads raw caller data (forward s0 == 0)
+// or ends the inverse transform (n^-1 folded in, canonical output).
 // ---------------------------------------------------------------------------
-template <int LOGN, int S, int POL, bool INVERSE>
+template <int S, int POL, bool INVERSE, bool FIRST>
 __global__ void __launch_bounds__(kNttThreads)
-ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch) {
-    constexpr int LG = LOGN - S;
-    const size_t cols = batch << LG;
+ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0) {
+    const u32 LG = logn - s0 - (u32)S;                   // log2 g
+    const size_t cols = batch << (logn - (u32)S);        // (polynomial, block, column) triples
     const size_t idx = (size_t)blockIdx.x * kNttThreads + threadIdx.x;
     if (idx >= cols) return;
-    const size_t poly = idx >> LG;
-    const u32 c = (u32)(idx & ((1u << LG) - 1u));
-    u64* __restrict__ g = data + (poly << LOGN) + c;
+    const size_t pb = idx >> LG;                         // polynomial * 2^s0 + block
+    const u32 c = (u32)(idx & (((size_t)1 << LG) - 1u));
+    const u32 blk = (u32)(pb & (((size_t)1 << s0) - 1u));
+    u64* __restrict__ g = data + (pb << (LG + (u32)S)) + c;
+    const u32 T0 = (1u << s0) + blk;
     u64 v[1 << S];
     if (!INVERSE) {
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) v[j] = to_working<POL>(sanitize(g[(size_t)j << LG], POL == POL_GOLD ? mp.q : mp.q4, mp));
-        fwd_network<S, POL>(v, tbl.fwd, 1u, mp);
+        for (int j = 0; j < (1 << S); j++) {
+            const u64 x = g[(size_t)j << LG];
+            v[j] = FIRST ? to_working<POL>(sanitize(x, POL == POL_GOLD ? mp.q : mp.q4, mp)) : x;
+        }
+        fwd_network<S, POL>(v, tbl.fwd, T0, mp);
     } else {
 #pragma unroll
         for (int j = 0; j < (1 << S); j++) v[j] = g[(size_t)j << LG];
-        inv_network<S, POL, true>(v, tbl.inv, 1u, LG, tbl.n_inv, mp);
+        inv_network<S, POL, FIRST>(v, tbl.inv, T0, (int)LG, tbl.n_inv, mp);
     }
 #pragma unroll
     for (int j = 0; j < (1 << S); j++) g[(size_t)j << LG] = v[j];

@@ -34,7 +34,7 @@ struct QuotientState {
     NttContext* small = nullptr;   // cyclic, size m
     NttContext* big = nullptr;     // cyclic, size 2m
     DeviceCsr csr;
-    DeviceScratch z, e, p, qbuf, flags;
+    DeviceScratch z, e, p, qbuf, flags, seeds, containers;
     PinnedScratch h_flags;
     u64 omega = 0;
     int device = 0;
@@ -49,6 +49,7 @@ void quotient_state_free(QuotientState* s) {
     if (s->csr.col) cudaFree(s->csr.col);
     if (s->csr.val) cudaFree(s->csr.val);
     s->z.release(); s->e.release(); s->p.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
+    s->seeds.release(); s->containers.release();
     delete s;
 }
 
@@ -175,18 +176,20 @@ static QuotientState* get_state(R1csHandle* h, u64 omega) {
     return st;
 }
 
-// witnesses: [count][cols] host words; out: [count][m] host words (Q zero-padded to m); status[count]: 0 ok,
-// 1 the witness does not satisfy the constraints (non-zero remainder)
-int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status) {
-    std::lock_guard<std::mutex> lock(h->mu);
+// Device part of the pipeline: witnesses [count][cols] (HOST words, or DEVICE words when witnesses_on_device)
+// -> Q [count][m] zero-padded, left in st->qbuf on the device, status[count] on the host (0 ok, 1 the witness
+// does not satisfy the constraints).  The caller holds h->mu.  Synchronises the stream before returning.
+static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_on_device, size_t count, u64 omega,
+                           int* status, QuotientState** out_state) {
     const uint32_t m = h->rows, cols = h->cols;
-    if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^16"); return 2; }
+    if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxEngineLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^23"); return 2; }
     if (h->q != kGoldilocks && (h->q >> 61)) { set_error("quotient: unsupported modulus"); return 2; }
     if (m >= 2 && omega == 0) omega = reference_root_of_unity(h->q, m);
     if (m >= 2 && !host::cyclic_params_ok(h->q, m, omega)) { set_error("quotient: omega is not a primitive m-th root of unity"); return 2; }
-    if (count == 0) return 0;
     QuotientState* st = get_state(h, m >= 2 ? omega : 0);
     if (!st) return 4;
+    *out_state = st;
+    if (count == 0) return 0;
     if (!cuda_ok(cudaSetDevice(st->device), "cudaSetDevice")) return 4;
     const ModParams mp = host::make_mod_params(h->q, 1);
     cudaStream_t s = nullptr;      // legacy default stream: the cyclic contexts are private to this handle
@@ -203,7 +206,8 @@ int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 o
     u64* dQ = static_cast<u64*>(st->qbuf.ptr);
     unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
     auto grid = [](size_t n) { return (unsigned)((n + 255) / 256); };
-    ok = cuda_ok(cudaMemcpyAsync(dz, witnesses, W * cols * 8, cudaMemcpyHostToDevice, s), "H2D witness") &&
+    ok = cuda_ok(cudaMemcpyAsync(dz, witnesses, W * cols * 8,
+                                 witnesses_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D witness") &&
          cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
     if (ok) {
         spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE);
@@ -235,7 +239,6 @@ int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 o
             ok = cuda_ok(cudaMemsetAsync(dQ, 0, W * 8, s), "memset");
         }
     }
-    ok = ok && cuda_ok(cudaMemcpyAsync(out, dQ, W * m * 8, cudaMemcpyDeviceToHost, s), "D2H quotient");
     if (ok && m == 1) {
         std::vector<u64> num(W);
         ok = cuda_ok(cudaMemcpyAsync(num.data(), dE, W * 8, cudaMemcpyDeviceToHost, s), "D2H") &&
@@ -249,6 +252,60 @@ int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 o
     const unsigned* hf = static_cast<const unsigned*>(st->h_flags.ptr);
     for (size_t w = 0; w < W; w++) status[w] = hf[w] ? 1 : 0;
     return 0;
+}
+
+// witnesses: [count][cols] host words; out: [count][m] host words (Q zero-padded to m); status[count]: 0 ok,
+// 1 the witness does not satisfy the constraints (non-zero remainder)
+int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    QuotientState* st = nullptr;
+    const int rc = quotient_device(h, witnesses, false, count, omega, status, &st);
+    if (rc != 0 || count == 0) return rc;
+    return cuda_ok(cudaMemcpy(out, st->qbuf.ptr, count * (size_t)h->rows * 8, cudaMemcpyDeviceToHost), "D2H quotient") ? 0 : 4;
+}
+
+// Commitment phase of the prover (BASELINE configs[4]; replaces compute_quotient_poly + Commitment::new of
+// prove_r1cs, rust-api/lambda-snark/src/lib.rs:747-757, for quotients longer than one ring element, which the
+// reference silently truncates -- SURVEY F6).  Q of every witness is cut into chunks = ceil(m / n) messages of
+// n = ring_degree coefficients (the last one shorter when m < n); message (w, j) is committed with seed
+// seeds[w * chunks + j]; only chunk indices [chunk_lo, chunk_hi) are committed (a rank's slice of a sharded
+// job).  Nothing but the witness and the containers crosses PCIe.
+// out: [count][chunk_hi - chunk_lo][1 + k n] host words (or device words when out_on_device).
+int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
+                           const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, bool io_on_device,
+                           int* status) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    const uint32_t m = h->rows, n = lwe->n;
+    const size_t chunks = m <= n ? 1 : (size_t)m / n;
+    if (chunk_lo > chunk_hi || chunk_hi > chunks) { set_error("prover_commit_quotient: bad chunk range"); return 2; }
+    QuotientState* st = nullptr;
+    const int rc = quotient_device(h, witnesses, io_on_device, count, omega, status, &st);
+    if (rc != 0) return rc;
+    const size_t mine = chunk_hi - chunk_lo;
+    if (count == 0 || mine == 0) return 0;
+    if (st->device != lwe->device) { set_error("prover_commit_quotient: R1CS and LWE context live on different devices"); return 2; }
+    const size_t words = lwe_words(lwe);
+    const size_t msg_len = std::min<uint32_t>(m, n);
+    cudaStream_t s = nullptr;
+    if (!st->seeds.reserve(count * mine * 8)) return 3;
+    u64* d_out = out;
+    if (!io_on_device) {
+        if (!st->containers.reserve(count * mine * words * 8)) return 3;
+        d_out = static_cast<u64*>(st->containers.ptr);
+    }
+    u64* d_seeds = static_cast<u64*>(st->seeds.ptr);
+    const u64* dQ = static_cast<const u64*>(st->qbuf.ptr);
+    bool ok = true;
+    for (size_t w = 0; ok && w < count; w++) {
+        ok = cuda_ok(cudaMemcpyAsync(d_seeds + w * mine, seeds + w * chunks + chunk_lo, mine * 8,
+                                     io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds") &&
+             lwe_commit_launch(lwe, dQ + w * (size_t)m + chunk_lo * (size_t)n, msg_len, d_seeds + w * mine, mine,
+                               d_out + w * mine * words, s);
+    }
+    if (ok && !io_on_device)
+        ok = cuda_ok(cudaMemcpyAsync(out, d_out, count * mine * words * 8, cudaMemcpyDeviceToHost, s), "D2H containers");
+    ok = ok && cuda_ok(cudaStreamSynchronize(s), "sync");
+    return ok ? 0 : 4;
 }
 
 }  // namespace lsr

@@ -112,6 +112,16 @@ int  lsro_lwe_linear_combine(const lsro_lwe *c, const uint64_t *const *comms,
 
 int lsro_max_threads(void);
 
+/* ------------------------------------------------- quotient pipeline
+ * lsr_oracle_quotient.c: rust-api/lambda-snark/src/ntt.rs:117-201 (cyclic transform, natural order)
+ * and r1cs.rs:474-503, 995-1065 (quotient by X^m - 1), for sizes oracle/quotient.py cannot reach.  */
+int lsro_cyclic_ntt_forward(uint64_t *data, size_t n, uint64_t q, uint64_t omega);
+int lsro_cyclic_ntt_inverse(uint64_t *data, size_t n, uint64_t q, uint64_t omega);
+/* rows/cols/vals[3]: the entries of A, B, C; out[m]; returns 0, 1 (witness does not satisfy), -1 */
+int lsro_r1cs_quotient(size_t m, size_t cols, const uint32_t *rows_idx[3], const uint32_t *cols_idx[3],
+                       const uint64_t *vals[3], const size_t nnz[3], const uint64_t *witness, uint64_t q,
+                       uint64_t omega, uint64_t omega2, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,13 @@ class _Lib:
         lib.lsro_lwe_linear_combine.argtypes = [C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), u64p,
                                                 C.c_size_t, u64p]
         lib.lsro_max_threads.restype = C.c_int
+        for name in ("lsro_cyclic_ntt_forward", "lsro_cyclic_ntt_inverse"):
+            getattr(lib, name).restype = C.c_int
+            getattr(lib, name).argtypes = [u64p, C.c_size_t, C.c_uint64, C.c_uint64]
+        u32pp, u64pp = C.POINTER(C.c_uint32) * 3, u64p * 3
+        lib.lsro_r1cs_quotient.restype = C.c_int
+        lib.lsro_r1cs_quotient.argtypes = [C.c_size_t, C.c_size_t, u32pp, u32pp, u64pp, C.c_size_t * 3, u64p,
+                                           C.c_uint64, C.c_uint64, C.c_uint64, u64p]
 
 
 _lib_cache: dict[bool, _Lib] = {}
@@ -112,7 +119,7 @@ _lib_cache: dict[bool, _Lib] = {}
 def lib(native: bool = False) -> _Lib:
     if native not in _lib_cache:
         path = _BUILD / ("liblsr_oracle_native.so" if native else "liblsr_oracle.so")
-        src_mtime = max((_HERE / "lsr_oracle.c").stat().st_mtime, (_HERE / "lsr_oracle.h").stat().st_mtime)
+        src_mtime = max((_HERE / f).stat().st_mtime for f in ("lsr_oracle.c", "lsr_oracle_quotient.c", "lsr_oracle.h"))
         if not path.exists() or path.stat().st_mtime < src_mtime:
             build(native=native)
         _lib_cache[native] = _Lib(path)
@@ -369,3 +376,37 @@ def py_negacyclic_mul(a, b, q: int) -> list[int]:
             else:
                 r[k] = (r[k] + v) % q
     return r
+
+
+# ---------------------------------------------------------------- quotient pipeline (C restatement)
+def cyclic_ntt_forward(coeffs, q: int, omega: int) -> np.ndarray:
+    """ntt.rs:117-160 (natural order in and out); coeffs reduced mod q first."""
+    x = _np_u64(coeffs).copy()
+    if lib().lib.lsro_cyclic_ntt_forward(_ptr(x), x.size, q, omega) != 0:
+        raise ValueError("bad size")
+    return x
+
+
+def cyclic_ntt_inverse(evals, q: int, omega: int) -> np.ndarray:
+    x = _np_u64(evals).copy()
+    if lib().lib.lsro_cyclic_ntt_inverse(_ptr(x), x.size, q, omega) != 0:
+        raise ValueError("bad size")
+    return x
+
+
+def r1cs_quotient(rows: int, cols: int, A, B, C_, witness, q: int, omega: int, omega2: int):
+    """r1cs.rs:474-503 on the NTT path for big m.  A, B, C_: (row[], col[], val[]) numpy triples.
+    Returns (Q zero-padded to m, status) with status 1 when the witness does not satisfy the constraints."""
+    u32p = C.POINTER(C.c_uint32)
+    mats = [(np.ascontiguousarray(r, dtype=np.uint32), np.ascontiguousarray(c, dtype=np.uint32), _np_u64(v))
+            for r, c, v in (A, B, C_)]
+    rp = (u32p * 3)(*[m[0].ctypes.data_as(u32p) for m in mats])
+    cp = (u32p * 3)(*[m[1].ctypes.data_as(u32p) for m in mats])
+    vp = (u64p * 3)(*[_ptr(m[2]) for m in mats])
+    nn = (C.c_size_t * 3)(*[m[2].size for m in mats])
+    w = _np_u64(witness)
+    out = np.zeros(rows, dtype=np.uint64)
+    st = lib().lib.lsro_r1cs_quotient(rows, cols, rp, cp, vp, nn, _ptr(w), q, omega, omega2, _ptr(out))
+    if st < 0:
+        raise ValueError("bad arguments")
+    return out, st

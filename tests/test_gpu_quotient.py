@@ -152,3 +152,88 @@ def test_quotient_rejects_bad_shapes(gpu):
     assert not lib.lsr_cyclic_ntt_context_create(P, 6, 0)
     assert not lib.lsr_cyclic_ntt_context_create(Q0, 1 << 14, 0)          # 2-adicity of q0 is 13
     assert not lib.lsr_cyclic_ntt_context_create(P, 8, 3)                 # not a primitive 8th root
+
+
+# ------------------------------------------------------------------ sizes beyond 2^17 (BASELINE configs[4])
+def np_mult_gates(m, q, seed):
+    """mult_gates as numpy triples (tests/integration_matrix.rs:60-75 shape), for millions of constraints."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    a = rng.integers(0, q, size=m, dtype=np.uint64)
+    b = rng.integers(0, q, size=m, dtype=np.uint64)
+    c = np.array([(int(x) * int(y)) % q for x, y in zip(a, b)], dtype=np.uint64)
+    z = np.zeros(3 * m + 1, dtype=np.uint64)
+    z[0] = 1
+    z[1::3], z[2::3], z[3::3] = a, b, c
+    rows = np.arange(m, dtype=np.uint32)
+    one = np.ones(m, dtype=np.uint64)
+    return 3 * m + 1, (rows, 3 * rows + 1, one), (rows, 3 * rows + 2, one), (rows, 3 * rows + 3, one), z
+
+
+@pytest.mark.parametrize("q,logn", [(P, 18), (P, 20), (P, 21), (P, 23), (Q1, 18)])
+def test_big_cyclic_transform_matches_c_oracle(gpu, q, logn):
+    """One, two and three column passes ahead of the 4096-blocks (log n - 12 = 6, 8, 9, 11 stages), against
+    the C restatement of ntt.rs."""
+    from oracle import oracle as O
+    n = 1 << logn
+    rng = np.random.Generator(np.random.PCG64(logn))
+    w = api.reference_root_of_unity(q, n)
+    assert pow(w, n // 2, q) == q - 1
+    c = api.CyclicNtt(q, n)
+    x = rng.integers(0, q, size=(2, n), dtype=np.uint64)
+    x[1, :] = q - 1
+    x[1, 5] = 0
+    ev = c.forward_natural(x)
+    for b in range(2):
+        assert np.array_equal(ev[b], O.cyclic_ntt_forward(x[b], q, w)), (q, logn, b)
+    assert np.array_equal(c.inverse_natural(ev), x)
+    c.close()
+
+
+@pytest.mark.parametrize("q,logm", [(P, 17), (P, 20), (Q1, 17)])
+def test_big_quotient_matches_c_oracle(gpu, q, logm):
+    from oracle import oracle as O
+    m = 1 << logm
+    cols, A, B, C, z = np_mult_gates(m, q, 40 + logm)
+    r = api.R1CS.from_arrays(m, cols, A, B, C, q)
+    w, w2 = api.reference_root_of_unity(q, m), api.reference_root_of_unity(q, 2 * m)
+    want, st = O.r1cs_quotient(m, cols, A, B, C, z, q, w, w2)
+    assert st == 0
+    bad = z.copy(); bad[3] = (int(bad[3]) + 1) % q
+    out, status = r.quotient_batch(np.stack([z, bad]))
+    assert status.tolist() == [0, 1]
+    assert np.array_equal(out[0], want)
+    r.close()
+
+
+@pytest.mark.parametrize("logm", [10, 14, 20])
+def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
+    """BASELINE configs[4]: quotient -> ring-element chunks -> Module-LWE commitments without leaving the
+    device.  Equal to (C oracle quotient) -> (oracle commitment) bit for bit, and to the concatenation of
+    disjoint chunk slices (what ranks of a sharded job produce)."""
+    from oracle import oracle as O
+    q, m, n, k = P, 1 << logm, 4096, 2
+    seed32 = bytes(range(32))
+    cols, A, B, C, z = np_mult_gates(m, q, 70 + logm)
+    r = api.R1CS.from_arrays(m, cols, A, B, C, q)
+    ctx = api.LweContext(api.Params(n=n, k=k, q=Q0, sigma=3.19), seed32=seed32)
+    chunks = r.quotient_chunks(ctx)
+    assert chunks == max(1, m // n)
+    seeds = np.arange(1, 2 * chunks + 1, dtype=np.uint64).reshape(2, chunks) * np.uint64(0x9E3779B97F4A7C15)
+    bad = z.copy(); bad[3] = (int(bad[3]) + 1) % q
+    got, status = r.commit_quotient(ctx, np.stack([z, bad]), seeds)
+    assert status.tolist() == [0, 1] and got.shape == (2, chunks, ctx.words)
+    want_q, st = O.r1cs_quotient(m, cols, A, B, C, z, q, api.reference_root_of_unity(q, m) if m > 1 else 1,
+                                 api.reference_root_of_unity(q, 2 * m))
+    assert st == 0
+    orc = O.OracleLwe(Q0, n, k, 3.19, seed32)
+    msgs = want_q.reshape(chunks, -1)                   # [chunks][min(m, n)]
+    assert np.array_equal(got[0], orc.commit_batch(msgs, seeds[0]))
+    # the context opens what the prover committed (slots hold the quotient coefficients mod the plaintext modulus)
+    assert ctx.verify_batch(got[0], msgs % np.uint64(ctx.p)).tolist() == [1] * chunks
+    if chunks >= 4:
+        lo, _ = r.commit_quotient(ctx, z[None, :], seeds[:1], 0, chunks // 4)
+        hi, _ = r.commit_quotient(ctx, z[None, :], seeds[:1], chunks // 4, chunks)
+        assert np.array_equal(np.concatenate([lo[0], hi[0]]), got[0])
+    with pytest.raises(api.LambdaSnarkError):
+        r.commit_quotient(ctx, z[None, :], seeds[:1], 0, chunks + 1)
+    ctx.close(); r.close()

@@ -73,3 +73,49 @@ def test_quotient_identity_and_rejection():
                 assert False, "invalid witness accepted"
             except ValueError:
                 pass
+
+
+# ---------------------------------------------------------------- C restatement (oracle/lsr_oracle_quotient.c)
+def _triples(M):
+    import numpy as np
+    return (np.array([e[0] for e in M], dtype=np.uint32), np.array([e[1] for e in M], dtype=np.uint32),
+            np.array([e[2] % 2**64 for e in M], dtype=np.uint64))
+
+
+def test_c_cyclic_transform_passes_the_reference_unit_tests_and_matches_the_python_restatement():
+    from oracle import oracle as O
+    # ntt.rs:284-331
+    assert [int(v) for v in O.cyclic_ntt_forward([1, 2], P, Q.compute_root_of_unity(2))] == [3, P - 1]
+    assert int(O.cyclic_ntt_forward([1, 2, 3, 4], P, Q.compute_root_of_unity(4))[0]) == 10
+    assert int(O.cyclic_ntt_forward(list(range(1, 9)), P, Q.compute_root_of_unity(8))[0]) == 36
+    rng = random.Random(3)
+    for q, n in ((P, 1), (P, 2), (P, 64), (P, 2048), (Q.NTT_FRIENDLY_MODULUS, 512)):
+        w = Q.reference_root(q, n) if n > 1 else 1
+        f = [rng.randrange(q) for _ in range(n)]
+        ev = O.cyclic_ntt_forward(f, q, w)
+        assert [int(v) for v in ev] == Q.ntt_forward(f, q, w)
+        assert [int(v) for v in O.cyclic_ntt_inverse(ev, q, w)] == f
+    # ntt.rs:333-347 round trips
+    for log_n in range(1, 11):
+        n = 1 << log_n
+        w = Q.compute_root_of_unity(n)
+        coeffs = [(i * 123456789) % P for i in range(n)]
+        assert [int(v) for v in O.cyclic_ntt_inverse(O.cyclic_ntt_forward(coeffs, P, w), P, w)] == coeffs
+
+
+def test_c_quotient_matches_the_schoolbook_python_restatement():
+    from oracle import oracle as O
+    for q in (P, Q.NTT_FRIENDLY_MODULUS):
+        for m in (1, 2, 4, 32, 128):
+            rng = random.Random(1000 + m)
+            cols, A, B, C, z = mult_gates(m, q, rng)
+            if m >= 4:
+                A.append((1, 0, 5)); C.append((1, 0, (5 * z[3 * 1 + 2]) % q))
+                B.append((2, 0, 2**64 - 1)); C.append((2, 0, ((2**64 - 1) % q) * z[3 * 2 + 1] % q))   # wrapped -1
+            want = Q.compute_quotient_poly(m, A, B, C, z, q)
+            om = Q.reference_root(q, m) if m > 1 else 1
+            got, st = O.r1cs_quotient(m, cols, _triples(A), _triples(B), _triples(C), z, q, om, Q.reference_root(q, 2 * m))
+            assert st == 0
+            assert [int(v) for v in got] == want + [0] * (m - len(want)), (q, m)
+            bad = list(z); bad[3] = (bad[3] + 1) % q
+            assert O.r1cs_quotient(m, cols, _triples(A), _triples(B), _triples(C), bad, q, om, Q.reference_root(q, 2 * m))[1] == 1
