@@ -111,6 +111,9 @@ NttContext* ntt_create(u64 q, uint32_t n);
 // cyclic transform over X^n - 1 with the given primitive n-th root (rust-api/lambda-snark/src/ntt.rs);
 // q < 2^61 prime, or Goldilocks 2^64 - 2^32 + 1
 NttContext* ntt_create_cyclic(u64 q, uint32_t n, u64 omega);
+// negacyclic transform (bit-reversed evaluations at psi^(2 brv(i) + 1)) for a caller-chosen primitive 2n-th
+// root psi: the coset evaluations of the quotient pipeline; q < 2^61 prime or Goldilocks, n <= 2^24
+NttContext* ntt_create_negacyclic(u64 q, uint32_t n, u64 psi);
 // in-place bit-reversal permutation of each polynomial (natural-order views of the transforms)
 bool ntt_bitrev_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
 void ntt_destroy(NttContext* ctx);

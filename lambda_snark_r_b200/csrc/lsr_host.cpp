@@ -119,14 +119,20 @@ ModParams make_mod_params(u64 q, uint32_t logn) {
     return mp;
 }
 
-bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
-    if (!ntt_params_ok(q, n)) return false;
+// Negacyclic tables for a given primitive 2n-th root psi: out[i] = f(psi^(2 brv(i) + 1)).
+// SEAL's NTTTables (q < 2^61, n <= 2^17, minimal psi) is the special case build_ntt_tables below; the
+// quotient pipeline evaluates on the coset psi * <psi^2> of the m-th roots of unity with any psi, over
+// Goldilocks too, and up to 2^kMaxEngineLogN points.
+bool build_negacyclic_tables(u64 q, uint32_t n, u64 psi, NttHostTables& out) {
+    if (n < 2 || (n & (n - 1)) || n > (1u << kMaxEngineLogN)) return false;
+    if (q != kGoldilocks && (q < 3 || (q >> 61))) return false;
+    if (psi == 0 || psi >= q || powmod(psi, n, q) != q - 1) return false;
     uint32_t logn = 0;
     while ((1u << logn) < n) ++logn;
-    const u64 psi = min_primitive_root(q, 2ull * n);
-    if (!psi) return false;
     const u64 psi_inv = powmod(psi, q - 2, q);
     const u64 n_inv = powmod(n % q, q - 2, q);
+    const bool small = !(q >> 61);
+    auto pair = [&](u64 w) { return ulonglong2{w, small ? shoup_quotient(w, q) : 0ull}; };
 
     out.q = q; out.n = n; out.logn = logn; out.psi = psi;
     out.fwd.assign(n, ulonglong2{0, 0});
@@ -141,26 +147,29 @@ bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
             ipw = mulmod(ipw, psi_inv, q);
             seal_inv[bitrev(i - 1, logn) + 1] = ipw;
         }
-        const uint32_t slot = bitrev(i, logn);
-        out.fwd[slot].x = pw;
-        out.fwd[slot].y = shoup_quotient(pw, q);
+        out.fwd[bitrev(i, logn)] = pair(pw);
     }
     seal_inv[0] = 1;
     // re-index the inverse table: stage with m groups reads SEAL slots
     // n-2m+1 .. n-m (transform_from_rev consumes them sequentially from 1)
-    out.inv[0] = ulonglong2{1, shoup_quotient(1, q)};
+    out.inv[0] = pair(1);
     for (uint32_t m = 1; m < n; m <<= 1) {
         for (uint32_t g = 0; g < m; ++g) {
             u64 w = seal_inv[n - 2 * m + 1 + g];
             if (m == 1) w = mulmod(w, n_inv, q);      // scalar folded into the last stage
-            out.inv[m + g].x = w;
-            out.inv[m + g].y = shoup_quotient(w, q);
+            out.inv[m + g] = pair(w);
         }
     }
-    out.n_inv.x = n_inv;
-    out.n_inv.y = shoup_quotient(n_inv, q);
+    out.n_inv = pair(n_inv);
     transpose_last_pass(out);
     return true;
+}
+
+bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out) {
+    if (!ntt_params_ok(q, n)) return false;
+    const u64 psi = min_primitive_root(q, 2ull * n);
+    if (!psi) return false;
+    return build_negacyclic_tables(q, n, psi, out);
 }
 
 // transposed copy of the unit-stride radix-16 pass (forward stages logn-4 .. logn-1):

@@ -32,6 +32,8 @@ struct NttHostTables {
     ulonglong2 n_inv{0, 0};
 };
 bool build_ntt_tables(u64 q, uint32_t n, NttHostTables& out);
+// same layout for a caller-chosen primitive 2n-th root psi; q < 2^61 or Goldilocks, n <= 2^kMaxEngineLogN
+bool build_negacyclic_tables(u64 q, uint32_t n, u64 psi, NttHostTables& out);
 // cyclic (X^n - 1) tables for a given primitive n-th root omega; q < 2^61 prime or Goldilocks
 bool cyclic_params_ok(u64 q, uint32_t n, u64 omega);
 bool build_cyclic_tables(u64 q, uint32_t n, u64 omega, NttHostTables& out);

@@ -257,6 +257,15 @@ NttContext* ntt_create(u64 q, uint32_t n) {
     return ntt_create_from(ht, false);
 }
 
+NttContext* ntt_create_negacyclic(u64 q, uint32_t n, u64 psi) {
+    host::NttHostTables ht;
+    if ((q != kGoldilocks && !host::is_prime(q)) || !host::build_negacyclic_tables(q, n, psi, ht)) {
+        set_error("negacyclic NTT context: invalid (q, n, psi)");
+        return nullptr;
+    }
+    return ntt_create_from(ht, false);
+}
+
 NttContext* ntt_create_cyclic(u64 q, uint32_t n, u64 omega) {
     host::NttHostTables ht;
     if (!host::build_cyclic_tables(q, n, omega, ht)) {

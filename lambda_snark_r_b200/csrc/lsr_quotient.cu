@@ -8,13 +8,19 @@
 // The quotient of an exact division is unique, so the result is the reference's coefficient vector bit
 // for bit (canonical residues, trailing zeros trimmed by the caller-facing wrapper).
 //
-// Data flow for a batch of W witnesses of one R1CS instance (m constraints, m a power of two):
-//   E[3][W][m]   evaluations of A_z, B_z, C_z, written by the mat-vec directly in bit-reversed row
-//                order (the order the inverse transform consumes)
-//   -> inverse cyclic NTT (size m, batch 3W) -> coefficients, natural order
-//   P[3][W][2m]  zero-extended -> forward cyclic NTT (size 2m, batch 3W)
-//   N[W][2m]     A*B - C pointwise (in the first third of P) -> inverse cyclic NTT (size 2m, batch W)
-//   Q[W][m]      Q_i = N_{m+i};  N = Q*X^m - Q  <=>  N_i + Q_i = 0 for i < m  (remainder check)
+// Data flow for a batch of W witnesses of one R1CS instance (m constraints, m a power of two).  The
+// reference multiplies A_z and B_z as coefficient vectors (degree 2m - 2) and long-divides by X^m - 1.
+// Here the division is done where it is free: on the coset psi * H of the m-th roots of unity H (psi any
+// primitive 2m-th root), X^m - 1 is the constant psi^m - 1 = -2, and deg Q <= m - 2, so m coset values
+// determine Q.  Evaluating at psi^(2j+1) is exactly the NEGACYCLIC transform of size m with root psi:
+//   E[3][W][m]   evaluations of A_z, B_z, C_z on H, written by the mat-vec directly in bit-reversed row
+//                order (the order the inverse transform consumes); the same kernel checks
+//                a_i * b_i = c_i (is_satisfied, r1cs.rs:477-481  <=>  zero remainder, :1054-1060)
+//   -> inverse cyclic transform (size m, batch 3W)      coefficients of A_z, B_z, C_z
+//   -> forward negacyclic transform (size m, batch 3W)  values on psi * H (bit-reversed order)
+//   Q^[W][m]     (a * b - c) * (-2)^-1 pointwise
+//   -> inverse negacyclic transform (size m, batch W)   Q, natural order
+// 7 W transforms of size m and no zero padding, against 3 W of size m + 4 W of size 2m.
 #include <algorithm>
 #include <new>
 
@@ -31,10 +37,10 @@ struct DeviceCsr {
 };
 
 struct QuotientState {
-    NttContext* small = nullptr;   // cyclic, size m
-    NttContext* big = nullptr;     // cyclic, size 2m
+    NttContext* small = nullptr;   // cyclic, size m (interpolation on H)
+    NttContext* coset = nullptr;   // negacyclic, size m (evaluation / interpolation on psi * H)
     DeviceCsr csr;
-    DeviceScratch z, e, p, qbuf, flags, seeds, containers;
+    DeviceScratch z, e, qbuf, flags, seeds, containers;
     PinnedScratch h_flags;
     u64 omega = 0;
     int device = 0;
@@ -44,27 +50,28 @@ void quotient_state_free(QuotientState* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->small) ntt_destroy(s->small);
-    if (s->big) ntt_destroy(s->big);
+    if (s->coset) ntt_destroy(s->coset);
     if (s->csr.row_ptr) cudaFree(s->csr.row_ptr);
     if (s->csr.col) cudaFree(s->csr.col);
     if (s->csr.val) cudaFree(s->csr.val);
-    s->z.release(); s->e.release(); s->p.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
+    s->z.release(); s->e.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
     s->seeds.release(); s->containers.release();
     delete s;
 }
 
 // ------------------------------------------------------------------ kernels
-// one thread per (witness, row); the three matrices share the witness loads
+// one thread per (witness, row); the three matrices share the witness loads.  flags[w] |= (a * b != c).
 __global__ void __launch_bounds__(256)
 spmv3_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
              const u64* __restrict__ val, const u64* __restrict__ z, uint32_t rows, uint32_t cols, int logm,
-             size_t witnesses, u64* __restrict__ E) {
+             size_t witnesses, u64* __restrict__ E, unsigned* __restrict__ flags) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= witnesses * rows) return;
     const size_t w = idx / rows;
     const uint32_t r = (uint32_t)(idx % rows);
     const u64* __restrict__ zw = z + w * cols;
     const uint32_t dst = logm ? (__brev(r) >> (32 - logm)) : 0u;
+    u64 abc[3];
 #pragma unroll
     for (int mat = 0; mat < 3; mat++) {
         const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
@@ -72,38 +79,18 @@ spmv3_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uin
         for (uint32_t k = rp[r]; k < rp[r + 1]; k++)
             acc = field_add(acc, field_mul(val[k], reduce64(zw[col[k]], mp), mp), mp);     // v[col] % modulus
         E[((size_t)mat * witnesses + w) * rows + dst] = acc;
+        abc[mat] = acc;
     }
+    if (field_mul(abc[0], abc[1], mp) != abc[2]) atomicOr(flags + w, 1u);
 }
 
-// P[p][i] = i < m ? C[p][i] : 0   (p < polys, i < 2m)
+// Q^ = (A * B - C) * h on the coset values (any order: pointwise), h = (-2)^-1 = (q - 1) / 2
 __global__ void __launch_bounds__(256)
-zero_extend_kernel(const u64* __restrict__ src, u64* __restrict__ dst, uint32_t m, size_t polys) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= polys * 2 * m) return;
-    const size_t p = idx / (2 * (size_t)m);
-    const uint32_t i = (uint32_t)(idx % (2 * (size_t)m));
-    dst[idx] = i < m ? src[p * m + i] : 0ull;
-}
-
-// N = A*B - C on the 2m-point evaluations (any order: pointwise), written over A
-__global__ void __launch_bounds__(256)
-numerator_kernel(const ModParams mp, u64* __restrict__ P, size_t per_matrix) {
+coset_quotient_kernel(const ModParams mp, const u64* __restrict__ E, u64* __restrict__ Qh, size_t per_matrix, u64 h) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per_matrix) return;
-    P[idx] = field_sub(field_mul(P[idx], P[per_matrix + idx], mp), P[2 * per_matrix + idx], mp);
-}
-
-// Q_i = N_{m+i}; flags[w] |= (N_i + Q_i != 0)
-__global__ void __launch_bounds__(256)
-split_kernel(const ModParams mp, const u64* __restrict__ N, u64* __restrict__ Q, uint32_t m, size_t witnesses,
-             unsigned* __restrict__ flags) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= witnesses * m) return;
-    const size_t w = idx / m;
-    const uint32_t i = (uint32_t)(idx % m);
-    const u64 lo = N[w * 2 * m + i], hi = N[w * 2 * m + m + i];
-    Q[idx] = hi;
-    if (field_add(lo, hi, mp) != 0) atomicOr(flags + w, 1u);
+    const u64 num = field_sub(field_mul(E[idx], E[per_matrix + idx], mp), E[2 * per_matrix + idx], mp);
+    Qh[idx] = field_mul(num, h, mp);
 }
 
 // ------------------------------------------------------------------ host side
@@ -163,11 +150,10 @@ static QuotientState* get_state(R1csHandle* h, u64 omega) {
     bool ok = cuda_ok(cudaSetDevice(st->device), "cudaSetDevice");
     if (ok && m >= 2) {
         st->small = ntt_create_cyclic(h->q, m, omega);
-        // any primitive 2m-th root serves the product: take the reference's family so that its square is omega
-        // whenever omega is the reference's own choice
-        u64 w2 = reference_root_of_unity(h->q, 2 * m);
-        st->big = w2 ? ntt_create_cyclic(h->q, 2 * m, w2) : nullptr;
-        ok = st->small && st->big;
+        // any primitive 2m-th root serves as the coset shift: psi * H does not depend on the generator of H
+        u64 psi = reference_root_of_unity(h->q, 2 * m);
+        st->coset = psi ? ntt_create_negacyclic(h->q, m, psi) : nullptr;
+        ok = st->small && st->coset;
         if (!ok) set_error("quotient: the modulus has no NTT of size 2m (need 2m | q-1, q prime < 2^61 or Goldilocks)");
     }
     ok = ok && build_csr(h, st);
@@ -197,12 +183,11 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
     const size_t em = (size_t)3 * W * m;
     int logm = 0;
     while ((1u << logm) < m) ++logm;
-    bool ok = st->z.reserve(W * cols * 8) && st->e.reserve(em * 8) && st->p.reserve(em * 2 * 8) &&
+    bool ok = st->z.reserve(W * cols * 8) && st->e.reserve(em * 8) &&
               st->qbuf.reserve(W * m * 8) && st->flags.reserve(W * 4) && st->h_flags.reserve(W * 4);
     if (!ok) return 3;
     u64* dz = static_cast<u64*>(st->z.ptr);
     u64* dE = static_cast<u64*>(st->e.ptr);
-    u64* dP = static_cast<u64*>(st->p.ptr);
     u64* dQ = static_cast<u64*>(st->qbuf.ptr);
     unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
     auto grid = [](size_t n) { return (unsigned)((n + 255) / 256); };
@@ -210,41 +195,21 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
                                  witnesses_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D witness") &&
          cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
     if (ok) {
-        spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE);
+        spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE, dF);
         ok = cuda_ok(cudaGetLastError(), "spmv3_kernel");
     }
     if (ok && m >= 2) {
-        ok = ntt_inverse_launch(st->small, dE, 3 * W, s);
+        const u64 half = (h->q - 1) / 2;                       // (-2) * half = -(q - 1) = 1 (mod q)
+        ok = ntt_inverse_launch(st->small, dE, 3 * W, s) && ntt_forward_launch(st->coset, dE, 3 * W, s);
         if (ok) {
-            zero_extend_kernel<<<grid(em * 2), 256, 0, s>>>(dE, dP, m, 3 * W);
-            ok = cuda_ok(cudaGetLastError(), "zero_extend_kernel");
+            coset_quotient_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m, half);
+            ok = cuda_ok(cudaGetLastError(), "coset_quotient_kernel");
         }
-        ok = ok && ntt_forward_launch(st->big, dP, 3 * W, s);
-        if (ok) {
-            numerator_kernel<<<grid(W * 2 * m), 256, 0, s>>>(mp, dP, W * 2 * (size_t)m);
-            ok = cuda_ok(cudaGetLastError(), "numerator_kernel");
-        }
-        ok = ok && ntt_inverse_launch(st->big, dP, W, s);
-        if (ok) {
-            split_kernel<<<grid(W * m), 256, 0, s>>>(mp, dP, dQ, m, W, dF);
-            ok = cuda_ok(cudaGetLastError(), "split_kernel");
-        }
+        ok = ok && ntt_inverse_launch(st->coset, dQ, W, s);
     } else if (ok) {
         // m = 1: A_z, B_z, C_z are constants; the numerator a*b - c has degree 0 < deg(X - 1), so the quotient is 0
-        // and the division is exact iff the numerator vanishes (r1cs.rs:1010-1020)
-        numerator_kernel<<<grid(W), 256, 0, s>>>(mp, dE, W);
-        ok = cuda_ok(cudaGetLastError(), "numerator_kernel");
-        if (ok) {
-            // reuse split semantics by hand: flags = (numerator != 0), Q = 0
-            ok = cuda_ok(cudaMemsetAsync(dQ, 0, W * 8, s), "memset");
-        }
-    }
-    if (ok && m == 1) {
-        std::vector<u64> num(W);
-        ok = cuda_ok(cudaMemcpyAsync(num.data(), dE, W * 8, cudaMemcpyDeviceToHost, s), "D2H") &&
-             cuda_ok(cudaStreamSynchronize(s), "sync");
-        for (size_t w = 0; ok && w < W; w++) status[w] = num[w] != 0 ? 1 : 0;
-        return ok ? 0 : 4;
+        // and the division is exact iff the numerator vanishes (r1cs.rs:1010-1020): the flag of the mat-vec
+        ok = cuda_ok(cudaMemsetAsync(dQ, 0, W * 8, s), "memset");
     }
     ok = ok && cuda_ok(cudaMemcpyAsync(st->h_flags.ptr, dF, W * 4, cudaMemcpyDeviceToHost, s), "D2H flags") &&
          cuda_ok(cudaStreamSynchronize(s), "sync");
@@ -296,7 +261,12 @@ int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witn
     u64* d_seeds = static_cast<u64*>(st->seeds.ptr);
     const u64* dQ = static_cast<const u64*>(st->qbuf.ptr);
     bool ok = true;
-    for (size_t w = 0; ok && w < count; w++) {
+    if (mine == chunks) {
+        // the whole quotient of every witness: Q [count][m] is [count * chunks][msg_len] -- one launch
+        ok = cuda_ok(cudaMemcpyAsync(d_seeds, seeds, count * chunks * 8,
+                                     io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds") &&
+             lwe_commit_launch(lwe, dQ, msg_len, d_seeds, count * chunks, d_out, s);
+    } else for (size_t w = 0; ok && w < count; w++) {
         ok = cuda_ok(cudaMemcpyAsync(d_seeds + w * mine, seeds + w * chunks + chunk_lo, mine * 8,
                                      io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds") &&
              lwe_commit_launch(lwe, dQ + w * (size_t)m + chunk_lo * (size_t)n, msg_len, d_seeds + w * mine, mine,
