@@ -42,6 +42,10 @@ CTX_SEED = bytes(range(32))
 SEED_BASE = 0xC0FFEE
 ALG_BYTES_COMMIT = 8 * N_RING + 8 * K_RANK * N_RING + 8          # message in + container out
 ALG_BYTES_NTT = 16 * N_RING                                       # read + write, in place
+# quotient pipeline, every stage touching its operands once (multiplication-gate R1CS: 3 non-zeros per constraint):
+# mat-vec 24 (witness) + 48 (CSR: 3 x (col 4 + val 8) + 3 row pointers) + 24 (evaluations out) = 96; 3 inverse + 3 forward
+# size-m transforms 16 each = 96; pointwise 24 in + 8 out = 32; inverse transform of Q 16
+QUOTIENT_BYTES_PER_CONSTRAINT = 96 + 96 + 32 + 16
 BUTTERFLIES_NTT = (N_RING // 2) * 12
 IMAD_PER_MODMUL = 10                                              # SURVEY 8d normalisation
 MODMUL_COMMIT = 2 * K_RANK * BUTTERFLIES_NTT + K_RANK * (N_RING // 2) + K_RANK * K_RANK * N_RING   # 118784
@@ -296,6 +300,67 @@ def run_gpu(args):
     ms_mul = timed(lambda: ntt.mul_pointwise_device(data2.data_ptr(), data.data_ptr(), data2.data_ptr(), NB * N_RING, stream),
                    args.warmup, args.steps) / args.steps
 
+    # ---- prover commitment phase (BASELINE configs[4]): 2^20-constraint R1CS over Goldilocks, quotient polynomial on
+    # the device, cut into m / n ring elements, each committed; weak scaling over witnesses (every rank proves its own)
+    prover = None
+    if args.prover_logm > 0:
+        import numpy as np
+        PM = 1 << args.prover_logm
+        PW = args.prover_witnesses
+        GOLD = 2**64 - 2**32 + 1
+        rng = np.random.Generator(np.random.PCG64(0xC5 + rank))
+        ga = rng.integers(0, GOLD, size=PM, dtype=np.uint64)
+        gb = rng.integers(0, GOLD, size=PM, dtype=np.uint64)
+        gc = np.fromiter(((int(x) * int(y)) % GOLD for x, y in zip(ga.tolist(), gb.tolist())), dtype=np.uint64, count=PM)
+        z = np.zeros(3 * PM + 1, dtype=np.uint64); z[0] = 1
+        z[1::3], z[2::3], z[3::3] = ga, gb, gc              # gates z[3i+1] * z[3i+2] = z[3i+3] (tests/integration_matrix.rs:60-75)
+        rows = np.arange(PM, dtype=np.uint32); one = np.ones(PM, dtype=np.uint64)
+        r1cs = api.R1CS.from_arrays(PM, 3 * PM + 1, (rows, 3 * rows + 1, one), (rows, 3 * rows + 2, one),
+                                    (rows, 3 * rows + 3, one), GOLD)
+        chunks = r1cs.quotient_chunks(ctx)
+        zs = torch.from_numpy(np.tile(z.view(np.int64), (PW, 1))).to(dev)
+        pseeds = torch.arange(1, PW * chunks + 1, dtype=torch.int64, device=dev) + rank * PW * chunks
+        pout = torch.empty((PW, chunks, words), dtype=torch.int64, device=dev)
+
+        def prover_step(hi=chunks):
+            st = r1cs.commit_quotient_device(ctx, zs.data_ptr(), PW, pseeds.data_ptr(), pout.data_ptr(), 0, hi)
+            assert not st.any()
+
+        psteps = max(3, min(args.steps, 10))
+        ms_p = timed(prover_step, args.warmup, psteps) / psteps
+        ms_q = timed(lambda: prover_step(0), args.warmup, psteps) / psteps
+        h_z = torch.from_numpy(np.tile(z.view(np.int64), (PW, 1))).pin_memory()
+        h_ps = pseeds.cpu().pin_memory()
+        h_pout = torch.empty((PW, chunks, words), dtype=torch.int64).pin_memory()
+        lib = capi.load()
+        st_buf = (C.c_int * PW)()
+
+        def prover_e2e():
+            rc = lib.lsr_prover_commit_quotient(r1cs._h, ctx.as_ptr(), C.cast(h_z.data_ptr(), capi.u64p), 3 * PM + 1, PW, 0,
+                                                C.cast(h_ps.data_ptr(), capi.u64p), 0, chunks,
+                                                C.cast(h_pout.data_ptr(), capi.u64p), st_buf)
+            assert rc == 0
+        prover_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            prover_e2e()
+        pe2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+        prover = {"workload": f"prover commitment phase (BASELINE configs[4]): R1CS with 2^{args.prover_logm} multiplication gates over "
+                              f"Goldilocks, quotient polynomial -> {chunks} ring elements of n={N_RING} -> {chunks} commitments per witness",
+                  "witnesses_per_gpu": PW, "constraints": PM, "commitments_per_witness": chunks,
+                  "value": world * PW / (ms_p * 1e-3), "unit": "witnesses/s",
+                  "constraints_per_s": world * PW * PM / (ms_p * 1e-3),
+                  "commitments_per_s": world * PW * chunks / (ms_p * 1e-3),
+                  "ms_per_step": ms_p, "ms_quotient": ms_q, "ms_commit": ms_p - ms_q,
+                  "quotient_bytes_per_constraint": QUOTIENT_BYTES_PER_CONSTRAINT,
+                  "quotient_GBps": PW * PM * QUOTIENT_BYTES_PER_CONSTRAINT / (ms_q * 1e-3) / 1e9,
+                  "e2e": {"value": world * PW / (pe2e_ms * 1e-3), "unit": "witnesses/s", "ms_per_step": pe2e_ms,
+                          "h2d_bytes_per_step": PW * ((3 * PM + 1) + chunks) * 8, "d2h_bytes_per_step": PW * chunks * words * 8,
+                          "api": "lsr_prover_commit_quotient (C ABI, pinned host buffers)"}}
+        del zs, pout
+        r1cs.close()
+
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     EB = args.e2e_batch
     h_msgs = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
@@ -427,6 +492,9 @@ def run_gpu(args):
                               "roofline": {"bound": "hbm", "achieved": mul_gbs, "peak": hbm_peak, "unit": "GB/s",
                                            "frac": mul_gbs / hbm_peak}}},
     }
+    if prover:
+        prover["quotient_hbm_frac"] = prover["quotient_GBps"] / hbm_peak
+        line["prover"] = prover
     if gather:
         line["gather"] = gather
     print(json.dumps(line), flush=True)
@@ -445,6 +513,8 @@ def main():
     ap.add_argument("--ntt-batch", type=int, default=16384, help="polynomials per GPU per NTT step")
     ap.add_argument("--e2e-batch", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--prover-logm", type=int, default=20, help="log2 constraints of the prover-phase block (0 = skip)")
+    ap.add_argument("--prover-witnesses", type=int, default=4, help="witnesses per GPU per prover step")
     ap.add_argument("--arith", default="auto", choices=["auto", "u64"],
                     help="auto: FP64-pipe butterflies (exact for q < 2^45); u64: integer Shoup butterflies (comparison)")
     args = ap.parse_args()
