@@ -204,6 +204,19 @@ void     lambda_snark_r1cs_free(void* r1cs);
 uint32_t lambda_snark_r1cs_num_constraints(void* r1cs);
 uint32_t lambda_snark_r1cs_num_variables(void* r1cs);
 
+/* ---- Lean 4 export (cpp-core/src/lean_ffi.cpp:152-314; declared by hand in the reference, no header).
+ * export_vk_to_lean:     "<nCons, nVars, nPublic, q, SparseMatrix.mk r c [(row, col, value), ...], B, C>" in
+ *                        U+27E8/U+27E9 brackets; q is params->modulus.  Bytes written (without the NUL) or -1.
+ * export_params_to_lean: "{ n := 4096, k := 2, q := 12289, sigma := 3.2, lambda := 128 }" with the Greek letters
+ *                        as UTF-8 and sigma printed with one decimal (std::fixed, setprecision(1)).
+ * export_seal_*:         SEAL-specific; this library holds no SEAL object, so both fail with -1 exactly as the
+ *                        reference does when its SEAL context is absent (lean_ffi.cpp:251-254, 293-296).       */
+int export_vk_to_lean(const R1CSConstraintSystem* r1cs, const PublicParams* params, char* out_buffer,
+                      size_t buffer_size) LSR_NOEXCEPT;
+int export_params_to_lean(const PublicParams* params, char* out_buffer, size_t buffer_size) LSR_NOEXCEPT;
+int export_seal_context_to_lean(const LweContext* ctx, char* out_buffer, size_t buffer_size) LSR_NOEXCEPT;
+int export_seal_pubkey_to_lean(const LweContext* ctx, char* out_buffer, size_t buffer_size) LSR_NOEXCEPT;
+
 /* ===================================================================== */
 /* Part 2 -- batched and device-pointer extensions (new; no reference      */
 /* counterpart: the reference is one polynomial / one commitment per call) */

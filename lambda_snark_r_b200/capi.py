@@ -39,6 +39,11 @@ class SparseMatrix(C.Structure):           # r1cs.h:49-54
                 ("n_rows", C.c_uint32), ("n_cols", C.c_uint32)]
 
 
+class R1CSConstraintSystem(C.Structure):   # r1cs.h:62-69
+    _fields_ = [("A", SparseMatrix), ("B", SparseMatrix), ("C", SparseMatrix), ("n_vars", C.c_uint32),
+                ("n_public_inputs", C.c_uint32), ("n_constraints", C.c_uint32)]
+
+
 class R1CSWitness(C.Structure):            # r1cs.h:76-79
     _fields_ = [("values", u64p), ("len", C.c_size_t)]
 
@@ -67,6 +72,10 @@ SIGNATURES = {
     "lambda_snark_r1cs_free": (None, [C.c_void_p]),
     "lambda_snark_r1cs_num_constraints": (C.c_uint32, [C.c_void_p]),
     "lambda_snark_r1cs_num_variables": (C.c_uint32, [C.c_void_p]),
+    "export_vk_to_lean": (C.c_int, [C.POINTER(R1CSConstraintSystem), C.POINTER(PublicParams), C.c_char_p, C.c_size_t]),
+    "export_params_to_lean": (C.c_int, [C.POINTER(PublicParams), C.c_char_p, C.c_size_t]),
+    "export_seal_context_to_lean": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
+    "export_seal_pubkey_to_lean": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
     # part 2: batched / device extensions
     "lsr_device_count": (C.c_int, []),
     "lsr_set_device": (C.c_int, [C.c_int]),

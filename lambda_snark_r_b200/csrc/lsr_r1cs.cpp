@@ -7,7 +7,11 @@
 // cpp-core/src/r1cs.cpp:18-180 and cpp-core/src/ffi.cpp:27-105 without NTL:
 // values pass through static_cast<long> before reduction (r1cs.cpp:165-167), so
 // a stored u64 of 2^64-1 means -1 mod q.
+#include <cstdio>
 #include <cstring>
+#include <iomanip>
+#include <sstream>
+#include <string>
 #include <new>
 #include <stdexcept>
 #include <vector>
@@ -108,6 +112,80 @@ uint32_t lambda_snark_r1cs_num_constraints(void* r1cs) {
 
 uint32_t lambda_snark_r1cs_num_variables(void* r1cs) {
     return r1cs ? static_cast<R1csHandle*>(r1cs)->cols : 0;
+}
+
+
+/* ---- Lean 4 export: cpp-core/src/lean_ffi.cpp:152-314.  Pure host formatting; the two
+ * SEAL-specific exports have nothing to serialise in this library (no SEAL context, no SEAL public key)
+ * and fail the way the reference does when its SEAL context is missing (:251-254, :293-296).        */
+namespace {
+std::string sparse_matrix_to_lean(const SparseMatrix& m) {               // lean_ffi.cpp:46-61
+    std::ostringstream oss;
+    oss << "SparseMatrix.mk " << m.n_rows << " " << m.n_cols << " [";
+    for (size_t i = 0; i < m.n_entries; ++i) {
+        if (i > 0) oss << ", ";
+        oss << "(" << m.entries[i].row << ", " << m.entries[i].col << ", " << m.entries[i].value << ")";
+    }
+    oss << "]";
+    return oss.str();
+}
+int copy_out(const std::string& text, char* out, size_t cap, const char* who) {
+    if (text.size() + 1 > cap) {
+        std::fprintf(stderr, "%s: buffer too small (need %zu, have %zu)\n", who, text.size() + 1, cap);
+        return -1;
+    }
+    std::memcpy(out, text.c_str(), text.size() + 1);
+    return static_cast<int>(text.size());
+}
+}  // namespace
+
+int export_vk_to_lean(const R1CSConstraintSystem* r1cs, const PublicParams* params, char* out_buffer,
+                      size_t buffer_size) LSR_NOEXCEPT {
+    if (!r1cs || !params || !out_buffer) return -1;
+    try {
+        if (r1cs->n_public_inputs > r1cs->n_vars) {                      // lean_ffi.cpp:161-167
+            std::fprintf(stderr, "export_vk_to_lean: n_public_inputs (%u) exceeds n_vars (%u)\n",
+                         r1cs->n_public_inputs, r1cs->n_vars);
+            return -1;
+        }
+        for (const SparseMatrix* m : {&r1cs->A, &r1cs->B, &r1cs->C})
+            if (m->n_entries && !m->entries) return -1;
+        std::ostringstream oss;
+        oss << "\xE2\x9F\xA8" << r1cs->n_constraints << ", " << r1cs->n_vars << ", " << r1cs->n_public_inputs << ", "
+            << params->modulus << ", " << sparse_matrix_to_lean(r1cs->A) << ", " << sparse_matrix_to_lean(r1cs->B)
+            << ", " << sparse_matrix_to_lean(r1cs->C) << "\xE2\x9F\xA9";   // U+27E8 ... U+27E9
+        return copy_out(oss.str(), out_buffer, buffer_size, "export_vk_to_lean");
+    } catch (...) {
+        return -1;
+    }
+}
+
+int export_params_to_lean(const PublicParams* params, char* out_buffer, size_t buffer_size) LSR_NOEXCEPT {
+    if (!params || !out_buffer) return -1;
+    try {
+        std::ostringstream oss;                                          // lean_ffi.cpp:68-78
+        oss << std::fixed << std::setprecision(1);
+        oss << "{ n := " << params->ring_degree << ", k := " << params->module_rank << ", q := " << params->modulus
+            << ", \xCF\x83 := " << params->sigma << ", \xCE\xBB := " << params->security_level << " }";
+        const std::string text = oss.str();
+        if (text.size() + 1 > buffer_size) return -1;
+        std::memcpy(out_buffer, text.c_str(), text.size() + 1);
+        return static_cast<int>(text.size());
+    } catch (...) {
+        return -1;
+    }
+}
+
+int export_seal_context_to_lean(const LweContext* ctx, char* out_buffer, size_t) LSR_NOEXCEPT {
+    if (!ctx || !out_buffer) return -1;
+    std::fprintf(stderr, "export_seal_context_to_lean: SEAL context not initialized\n");
+    return -1;
+}
+
+int export_seal_pubkey_to_lean(const LweContext* ctx, char* out_buffer, size_t) LSR_NOEXCEPT {
+    if (!ctx || !out_buffer) return -1;
+    std::fprintf(stderr, "export_seal_pubkey_to_lean: SEAL context or key not initialized\n");
+    return -1;
 }
 
 }  // extern "C"

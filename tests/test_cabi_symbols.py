@@ -13,9 +13,9 @@ from lambda_snark_r_b200 import capi
 ROOT = Path(__file__).resolve().parents[1]
 HEADER = ROOT / "include" / "lambda_snark_b200.h"
 
-# the 19 symbols the reference exports for this path minus the four
-# Lean exporters (no callers, SEAL-specific, out of scope)
+# the symbols the reference exports for this path, Lean exporters included
 REFERENCE_SYMBOLS = [
+    "export_vk_to_lean", "export_params_to_lean", "export_seal_context_to_lean", "export_seal_pubkey_to_lean",
     "lwe_context_create", "lwe_context_free", "lwe_commit", "lwe_commitment_free", "lwe_commitment_clone",
     "lwe_verify_opening", "lwe_linear_combine", "ntt_context_create", "ntt_context_free", "ntt_forward",
     "ntt_inverse", "ntt_mul_pointwise", "sample_gaussian", "lambda_snark_r1cs_create",

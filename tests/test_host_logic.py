@@ -172,3 +172,37 @@ def test_world_size_2_gloo_gather_equals_single_process(tmp_path):
     msgs = rng.integers(0, Q0, size=(count, 256), dtype=np.uint64)
     want = ctx.commit_batch(msgs, sharding.global_seeds(0xC0FFEE, 0, count))
     assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------- Lean export
+def test_lean_export_formats_match_the_reference():
+    """cpp-core/src/lean_ffi.cpp:46-78,152-232 and rust-api/lambda-snark/src/lean_export.rs:119-199 (same terms)."""
+    lib = capi.load()
+    buf = C.create_string_buffer(4096)
+    pp = capi.PublicParams(1, 128, 12289, 4096, 2, 3.2)
+    n = lib.export_params_to_lean(C.byref(pp), buf, len(buf))
+    text = "{ n := 4096, k := 2, q := 12289, σ := 3.2, λ := 128 }"            # lean_ffi.cpp:66 doc comment
+    assert n == len(text.encode()) and buf.value.decode() == text
+    pp2 = capi.PublicParams(1, 128, 17592169062401, 4096, 2, 3.19)
+    lib.export_params_to_lean(C.byref(pp2), buf, len(buf))
+    assert buf.value.decode() == "{ n := 4096, k := 2, q := 17592169062401, σ := 3.2, λ := 128 }"   # setprecision(1)
+    assert lib.export_params_to_lean(C.byref(pp), buf, 10) == -1                 # buffer too small
+    assert lib.export_params_to_lean(None, buf, len(buf)) == -1
+
+    # TV-1 (7 * 13 = 91): one constraint, four variables, two public inputs (lean_export.rs:263-280 header check)
+    def mat(entries, rows, cols):
+        arr = (capi.SparseEntry * len(entries))(*[capi.SparseEntry(r, c, v) for r, c, v in entries])
+        return capi.SparseMatrix(arr, len(entries), rows, cols), arr
+    (A, ka), (B, kb), (Cm, kc) = mat([(0, 1, 1)], 1, 4), mat([(0, 2, 1)], 1, 4), mat([(0, 3, 1), (0, 0, 5)], 1, 4)
+    sys_ = capi.R1CSConstraintSystem(A, B, Cm, 4, 2, 1)
+    pp3 = capi.PublicParams(1, 128, TEST_MODULUS, 4096, 2, 3.19)
+    n = lib.export_vk_to_lean(C.byref(sys_), C.byref(pp3), buf, len(buf))
+    want = ("⟨1, 4, 2, 17592186044417, SparseMatrix.mk 1 4 [(0, 1, 1)], SparseMatrix.mk 1 4 [(0, 2, 1)], "
+            "SparseMatrix.mk 1 4 [(0, 3, 1), (0, 0, 5)]⟩")
+    assert buf.value.decode() == want and n == len(want.encode())
+    assert lib.export_vk_to_lean(C.byref(sys_), C.byref(pp3), buf, 16) == -1
+    sys_.n_public_inputs = 5                                                     # lean_ffi.cpp:161-167
+    assert lib.export_vk_to_lean(C.byref(sys_), C.byref(pp3), buf, len(buf)) == -1
+    # SEAL-specific exporters: no SEAL object in this library, -1 like the reference without a SEAL context
+    assert lib.export_seal_context_to_lean(None, buf, len(buf)) == -1
+    assert lib.export_seal_pubkey_to_lean(None, buf, len(buf)) == -1
