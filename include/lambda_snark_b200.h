@@ -316,6 +316,35 @@ int lsr_prover_commit_quotient_device(void* r1cs, LweContext* ctx, const uint64_
                                       size_t witness_len, size_t count, uint64_t omega, const uint64_t* d_seeds,
                                       size_t chunk_lo, size_t chunk_hi, uint64_t* d_out, int* status) LSR_NOEXCEPT;
 
+/* ---- Fiat-Shamir transcript and polynomial evaluations of the prover on the device.  No counterpart
+ * in the reference's C ABI: they replace Rust code (challenge.rs:102-134 Challenge::derive, r1cs.rs:362-373
+ * eval_poly, lib.rs:747-809 prove_r1cs) that a maintainer would bind through lambda-snark-sys.
+ *
+ * lsr_fs_challenge_batch: for i < count,
+ *     hash  = SHA3-256("LAMBDA-SNARK-R-FS-v1" || le64(n_public) || public_inputs[i][..] || le64(words) || containers[i][..])
+ *     alpha = le64(hash[0..8]) mod modulus                                        -> challenges[i][0], hashes[i][0][0..32)
+ *   and, when chain != 0, beta = the same with the single public input alpha (lib.rs:764-767)
+ *                                                                                 -> challenges[i][1], hashes[i][1][0..32)
+ *   (chain == 0 leaves those zero).  hashes is [count][2][4] 64-bit little-endian lanes = [count][2][32] bytes.
+ * lsr_poly_eval_batch: out[p][j] = sum_i coeffs[p][i] * points[p][j]^i mod modulus (modulus < 2^61 or Goldilocks).
+ * lsr_prove_r1cs_batch: prove_r1cs for `count` witnesses of one circuit with m <= ring_degree constraints,
+ *   interpolation over the roots of unity (the NTT path of the reference): per witness the commitment container
+ *   ([1 + k n] words, seed seeds[w]), challenges (alpha, beta), the two transcript hashes, and evals[w][8] =
+ *   {Q(alpha), Q(beta), A_z(alpha), B_z(alpha), C_z(alpha), A_z(beta), B_z(beta), C_z(beta)} -- the field order of
+ *   ProofR1CS::new (lib.rs:795-809; the two openings are Q(alpha), Q(beta) again).  status[w] = 1 marks a witness
+ *   that does not satisfy the constraints (prove_r1cs returns Err: discard that row).  HOST pointers.             */
+int lsr_fs_challenge_batch(const uint64_t* public_inputs, size_t n_public, const uint64_t* containers, size_t words,
+                           size_t count, uint64_t modulus, int chain, uint64_t* challenges,
+                           uint64_t* hashes) LSR_NOEXCEPT;
+int lsr_fs_challenge_batch_device(const uint64_t* d_public_inputs, size_t n_public, const uint64_t* d_containers,
+                                  size_t words, size_t count, uint64_t modulus, int chain, uint64_t* d_challenges,
+                                  uint64_t* d_hashes, void* stream) LSR_NOEXCEPT;
+int lsr_poly_eval_batch(uint64_t modulus, const uint64_t* coeffs, size_t len, size_t polys, const uint64_t* points,
+                        size_t npts, uint64_t* out) LSR_NOEXCEPT;
+int lsr_prove_r1cs_batch(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len, size_t count,
+                         size_t n_public, uint64_t omega, const uint64_t* seeds, uint64_t* containers,
+                         uint64_t* challenges, uint64_t* hashes, uint64_t* evals, int* status) LSR_NOEXCEPT;
+
 /* Arithmetic of the NTT butterflies (NttContext, and the NttContext inside an
  * LweContext): 0 auto -- FP64-pipe butterflies (exact modular products by
  * error-free fma multiplication) when q < 2^45, else u64 Shoup butterflies;

@@ -23,7 +23,7 @@ SO = LIB / "liblambda_snark_core.so"
 AR = LIB / "liblambda_snark_core.a"
 
 SOURCES = ["lsr_host.cpp", "lsr_r1cs.cpp", "lsr_abi.cpp", "lsr_ntt.cu", "lsr_commit.cu", "lsr_commit_fused.cu",
-           "lsr_microbench.cu", "lsr_quotient.cu"]
+           "lsr_microbench.cu", "lsr_quotient.cu", "lsr_fiat_shamir.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

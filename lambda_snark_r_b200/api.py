@@ -258,6 +258,25 @@ class R1CS:
             raise LambdaSnarkError(f"lsr_prover_commit_quotient_device failed with code {rc}: {last_error()}")
         return status
 
+    def prove_batch(self, ctx: "LweContext", witnesses, n_public: int, seeds, omega: int = 0):
+        """prove_r1cs (lib.rs:747-809) for a batch of witnesses, m <= ring_degree, NTT path.  Returns a dict of
+        arrays: containers [count][words], challenges [count][2] (alpha, beta), hashes [count][2][32] bytes,
+        evals [count][8] (ProofR1CS field order), status [count]."""
+        import ctypes as C_
+        w = np.ascontiguousarray(_u64(witnesses)).reshape(-1, self.cols)
+        count = w.shape[0]
+        sd = np.ascontiguousarray(_u64(seeds)).reshape(count)
+        out = {"containers": np.zeros((count, ctx.words), dtype=np.uint64), "challenges": np.zeros((count, 2), dtype=np.uint64),
+               "hashes": np.zeros((count, 2, 4), dtype=np.uint64), "evals": np.zeros((count, 8), dtype=np.uint64),
+               "status": np.zeros(count, dtype=np.int32)}
+        rc = _lib().lsr_prove_r1cs_batch(self._h, ctx.as_ptr(), _p(w), self.cols, count, n_public, omega, _p(sd),
+                                         _p(out["containers"]), _p(out["challenges"]), _p(out["hashes"]), _p(out["evals"]),
+                                         out["status"].ctypes.data_as(C_.POINTER(C_.c_int)))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_prove_r1cs_batch failed with code {rc}: {last_error()}")
+        out["hashes"] = out["hashes"].view(np.uint8).reshape(count, 2, 32)
+        return out
+
     def close(self) -> None:
         if getattr(self, "_h", None):
             try:
@@ -523,3 +542,30 @@ def sample_gaussian(length: int, sigma: float, seed32: bytes | None = None) -> n
     if rc != 0:
         raise LambdaSnarkError("sample_gaussian returned -1")
     return out[:length].view(np.int64)
+
+
+def fs_challenge_batch(public_inputs, containers, modulus: int, chain: bool = True):
+    """Challenge::derive (challenge.rs:102-134) for a batch on the device: public_inputs [count][n_public],
+    containers [count][words] -> (challenges [count][2], hashes [count][2][32] bytes)."""
+    c = np.ascontiguousarray(_u64(containers))
+    c = c.reshape(1, -1) if c.ndim == 1 else c
+    count = c.shape[0]
+    pub = np.ascontiguousarray(_u64(public_inputs)).reshape(count, -1)
+    ch = np.zeros((count, 2), dtype=np.uint64)
+    hs = np.zeros((count, 2, 4), dtype=np.uint64)
+    rc = _lib().lsr_fs_challenge_batch(_p(pub), pub.shape[1], _p(c), c.shape[1], count, modulus, 1 if chain else 0, _p(ch), _p(hs))
+    if rc != 0:
+        raise LambdaSnarkError(f"lsr_fs_challenge_batch failed: {last_error()}")
+    return ch, hs.view(np.uint8).reshape(count, 2, 32)
+
+
+def poly_eval_batch(coeffs, points, modulus: int) -> np.ndarray:
+    """eval_poly (r1cs.rs:362-373): coeffs [polys][len], points [polys][npts] -> [polys][npts]."""
+    c = np.ascontiguousarray(_u64(coeffs))
+    c = c.reshape(1, -1) if c.ndim == 1 else c
+    pts = np.ascontiguousarray(_u64(points)).reshape(c.shape[0], -1)
+    out = np.zeros(pts.shape, dtype=np.uint64)
+    rc = _lib().lsr_poly_eval_batch(modulus, _p(c), c.shape[1], c.shape[0], _p(pts), pts.shape[1], _p(out))
+    if rc != 0:
+        raise LambdaSnarkError(f"lsr_poly_eval_batch failed: {last_error()}")
+    return out

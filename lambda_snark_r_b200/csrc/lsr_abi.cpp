@@ -17,6 +17,13 @@
 namespace lsr {
 u64 reference_root_of_unity(u64 q, uint32_t n);
 int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 omega, u64* out, int* status);
+bool fs_challenge_launch(const u64* d_pub, size_t n_pub, const u64* d_containers, size_t words, size_t count,
+                         u64 modulus, bool chain, u64* d_ab, u64* d_hashes, cudaStream_t s);
+bool fs_challenge_host(const u64* pub, size_t n_pub, const u64* containers, size_t words, size_t count, u64 modulus,
+                       bool chain, u64* ab, u64* hashes);
+bool poly_eval_host(u64 modulus, const u64* coeffs, size_t len, size_t polys, const u64* points, size_t npts, u64* out);
+int prove_r1cs_batch(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, size_t n_public,
+                     u64 omega, const u64* seeds, u64* containers, u64* challenges, u64* hashes, u64* evals, int* status);
 int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
                            const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, bool io_on_device, int* status);
 }
@@ -207,6 +214,53 @@ int lsr_prover_commit_quotient_device(void* r1cs, LweContext* ctx, const uint64_
                                       size_t chunk_hi, uint64_t* d_out, int* status) LSR_NOEXCEPT {
     LSR_TRY
     return prover_commit_impl(r1cs, ctx, d_witnesses, witness_len, count, omega, d_seeds, chunk_lo, chunk_hi, d_out, status, true);
+    LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
+}
+
+/* ------------------------------------------- Fiat-Shamir + evaluations (N2) */
+int lsr_fs_challenge_batch(const uint64_t* public_inputs, size_t n_public, const uint64_t* containers, size_t words,
+                           size_t count, uint64_t modulus, int chain, uint64_t* challenges, uint64_t* hashes) LSR_NOEXCEPT {
+    LSR_TRY
+    if ((!public_inputs && n_public && count) || (!containers && words && count) || !challenges || !hashes || modulus == 0) return -1;
+    return lsr::fs_challenge_host(reinterpret_cast<const u64*>(public_inputs), n_public, reinterpret_cast<const u64*>(containers),
+                                  words, count, modulus, chain != 0, reinterpret_cast<u64*>(challenges),
+                                  reinterpret_cast<u64*>(hashes)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_fs_challenge_batch_device(const uint64_t* d_public_inputs, size_t n_public, const uint64_t* d_containers,
+                                  size_t words, size_t count, uint64_t modulus, int chain, uint64_t* d_challenges,
+                                  uint64_t* d_hashes, void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!d_challenges || !d_hashes || modulus == 0) return -1;
+    return lsr::fs_challenge_launch(reinterpret_cast<const u64*>(d_public_inputs), n_public,
+                                    reinterpret_cast<const u64*>(d_containers), words, count, modulus, chain != 0,
+                                    reinterpret_cast<u64*>(d_challenges), reinterpret_cast<u64*>(d_hashes),
+                                    static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_poly_eval_batch(uint64_t modulus, const uint64_t* coeffs, size_t len, size_t polys, const uint64_t* points,
+                        size_t npts, uint64_t* out) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!coeffs || !points || !out) return -1;
+    return lsr::poly_eval_host(modulus, reinterpret_cast<const u64*>(coeffs), len, polys, reinterpret_cast<const u64*>(points),
+                               npts, reinterpret_cast<u64*>(out)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_prove_r1cs_batch(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len, size_t count,
+                         size_t n_public, uint64_t omega, const uint64_t* seeds, uint64_t* containers,
+                         uint64_t* challenges, uint64_t* hashes, uint64_t* evals, int* status) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!r1cs || !ctx || !witnesses || !seeds || !containers || !challenges || !hashes || !evals || !status)
+        return LAMBDA_SNARK_ERR_NULL_PTR;
+    lsr::R1csHandle* h = static_cast<lsr::R1csHandle*>(r1cs);
+    if (witness_len != h->cols) return LAMBDA_SNARK_ERR_INVALID_PARAMS;
+    return lsr::prove_r1cs_batch(h, ctx, reinterpret_cast<const u64*>(witnesses), count, n_public, omega,
+                                 reinterpret_cast<const u64*>(seeds), reinterpret_cast<u64*>(containers),
+                                 reinterpret_cast<u64*>(challenges), reinterpret_cast<u64*>(hashes),
+                                 reinterpret_cast<u64*>(evals), status);
     LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
 }
 

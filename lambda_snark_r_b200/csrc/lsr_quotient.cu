@@ -30,6 +30,11 @@
 
 namespace lsr {
 
+bool fs_challenge_launch(const u64* d_pub, size_t n_pub, const u64* d_containers, size_t words, size_t count,
+                         u64 modulus, bool chain, u64* d_ab, u64* d_hashes, cudaStream_t s);
+bool poly_eval_launch(u64 modulus, const u64* d_coeffs, size_t len, size_t polys, const u64* d_points, size_t npts,
+                      size_t point_rows, u64* d_out, cudaStream_t s);
+
 struct DeviceCsr {
     uint32_t* row_ptr = nullptr;   // [3][rows + 1], offsets into col / val of the concatenated A|B|C entries
     uint32_t* col = nullptr;
@@ -40,7 +45,7 @@ struct QuotientState {
     NttContext* small = nullptr;   // cyclic, size m (interpolation on H)
     NttContext* coset = nullptr;   // negacyclic, size m (evaluation / interpolation on psi * H)
     DeviceCsr csr;
-    DeviceScratch z, e, qbuf, flags, seeds, containers;
+    DeviceScratch z, e, qbuf, flags, seeds, containers, coef, fs;
     PinnedScratch h_flags;
     u64 omega = 0;
     int device = 0;
@@ -55,7 +60,7 @@ void quotient_state_free(QuotientState* s) {
     if (s->csr.col) cudaFree(s->csr.col);
     if (s->csr.val) cudaFree(s->csr.val);
     s->z.release(); s->e.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
-    s->seeds.release(); s->containers.release();
+    s->seeds.release(); s->containers.release(); s->coef.release(); s->fs.release();
     delete s;
 }
 
@@ -166,7 +171,7 @@ static QuotientState* get_state(R1csHandle* h, u64 omega) {
 // -> Q [count][m] zero-padded, left in st->qbuf on the device, status[count] on the host (0 ok, 1 the witness
 // does not satisfy the constraints).  The caller holds h->mu.  Synchronises the stream before returning.
 static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_on_device, size_t count, u64 omega,
-                           int* status, QuotientState** out_state) {
+                           int* status, QuotientState** out_state, bool keep_coeffs = false) {
     const uint32_t m = h->rows, cols = h->cols;
     if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxEngineLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^23"); return 2; }
     if (h->q != kGoldilocks && (h->q >> 61)) { set_error("quotient: unsupported modulus"); return 2; }
@@ -200,7 +205,11 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
     }
     if (ok && m >= 2) {
         const u64 half = (h->q - 1) / 2;                       // (-2) * half = -(q - 1) = 1 (mod q)
-        ok = ntt_inverse_launch(st->small, dE, 3 * W, s) && ntt_forward_launch(st->coset, dE, 3 * W, s);
+        ok = ntt_inverse_launch(st->small, dE, 3 * W, s);
+        if (ok && keep_coeffs)      // A_z, B_z, C_z as coefficient vectors [3][W][m] for the evaluations of prove_r1cs
+            ok = st->coef.reserve(em * 8) &&
+                 cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
+        ok = ok && ntt_forward_launch(st->coset, dE, 3 * W, s);
         if (ok) {
             coset_quotient_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m, half);
             ok = cuda_ok(cudaGetLastError(), "coset_quotient_kernel");
@@ -210,6 +219,9 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
         // m = 1: A_z, B_z, C_z are constants; the numerator a*b - c has degree 0 < deg(X - 1), so the quotient is 0
         // and the division is exact iff the numerator vanishes (r1cs.rs:1010-1020): the flag of the mat-vec
         ok = cuda_ok(cudaMemsetAsync(dQ, 0, W * 8, s), "memset");
+        if (ok && keep_coeffs)      // degree-0 interpolants: the evaluations themselves
+            ok = st->coef.reserve(em * 8) &&
+                 cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
     }
     ok = ok && cuda_ok(cudaMemcpyAsync(st->h_flags.ptr, dF, W * 4, cudaMemcpyDeviceToHost, s), "D2H flags") &&
          cuda_ok(cudaStreamSynchronize(s), "sync");
@@ -276,6 +288,65 @@ int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witn
         ok = cuda_ok(cudaMemcpyAsync(out, d_out, count * mine * words * 8, cudaMemcpyDeviceToHost, s), "D2H containers");
     ok = ok && cuda_ok(cudaStreamSynchronize(s), "sync");
     return ok ? 0 : 4;
+}
+
+// prove_r1cs for a batch of witnesses of one circuit (rust-api/lambda-snark/src/lib.rs:747-809), on the path
+// where the reference is self-consistent: interpolation over the roots of unity (NTT modulus), quotient no
+// longer than one ring element (m <= ring_degree; longer quotients are truncated by the reference, F6).
+// Per witness w:  Q -> commitment (seed seeds[w]) -> alpha = FS(z[0..n_public), C), beta = FS([alpha], C)
+// -> evals[w] = {Q(alpha), Q(beta), A_z(alpha), B_z(alpha), C_z(alpha), A_z(beta), B_z(beta), C_z(beta)}
+// (the field order of ProofR1CS::new, lib.rs:795-809).  The commitment never visits the host before its
+// challenges exist; containers, challenges [count][2], hashes [count][2][4], evals [count][8] are copied out at
+// the end (HOST pointers).
+int prove_r1cs_batch(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, size_t n_public,
+                     u64 omega, const u64* seeds, u64* containers, u64* challenges, u64* hashes, u64* evals, int* status) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    const uint32_t m = h->rows, cols = h->cols;
+    if (m > lwe->n) { set_error("prove_r1cs_batch: quotient longer than one ring element (use lsr_prover_commit_quotient)"); return 2; }
+    if (n_public > cols) { set_error("prove_r1cs_batch: more public inputs than variables"); return 2; }
+    QuotientState* st = nullptr;
+    const int rc = quotient_device(h, witnesses, false, count, omega, status, &st, true);
+    if (rc != 0 || count == 0) return rc;
+    if (st->device != lwe->device) { set_error("prove_r1cs_batch: R1CS and LWE context live on different devices"); return 2; }
+    const size_t words = lwe_words(lwe), W = count;
+    cudaStream_t s = nullptr;
+    // fs scratch: pub [W][n_public] | ab [W][2] | hashes [W][8] | evals: Q [W][2], ABC [3][W][2]
+    const size_t pub_w = W * std::max<size_t>(n_public, 1);
+    if (!st->seeds.reserve(W * 8) || !st->containers.reserve(W * words * 8) ||
+        !st->fs.reserve((pub_w + W * 2 + W * 8 + W * 2 + 3 * W * 2) * 8)) return 3;
+    u64* d_seeds = static_cast<u64*>(st->seeds.ptr);
+    u64* d_cont = static_cast<u64*>(st->containers.ptr);
+    u64* d_pub = static_cast<u64*>(st->fs.ptr);
+    u64* d_ab = d_pub + pub_w;
+    u64* d_hash = d_ab + W * 2;
+    u64* d_evq = d_hash + W * 8;
+    u64* d_evabc = d_evq + W * 2;
+    const u64* dz = static_cast<const u64*>(st->z.ptr);
+    const u64* dQ = static_cast<const u64*>(st->qbuf.ptr);
+    bool ok = cuda_ok(cudaMemcpyAsync(d_seeds, seeds, W * 8, cudaMemcpyHostToDevice, s), "H2D seeds") &&
+              lwe_commit_launch(lwe, dQ, m, d_seeds, W, d_cont, s);
+    if (ok && n_public)     // public inputs = z[0 .. l) of every witness (r1cs.rs:178-181)
+        ok = cuda_ok(cudaMemcpy2DAsync(d_pub, n_public * 8, dz, (size_t)cols * 8, n_public * 8, W, cudaMemcpyDeviceToDevice, s), "D2D public inputs");
+    ok = ok && fs_challenge_launch(d_pub, n_public, d_cont, words, W, h->q, true, d_ab, d_hash, s) &&
+         poly_eval_launch(h->q, dQ, m, W, d_ab, 2, W, d_evq, s) &&
+         poly_eval_launch(h->q, static_cast<const u64*>(st->coef.ptr), m, 3 * W, d_ab, 2, W, d_evabc, s);
+    std::vector<u64> evq(W * 2), evabc(3 * W * 2);
+    ok = ok && cuda_ok(cudaMemcpyAsync(containers, d_cont, W * words * 8, cudaMemcpyDeviceToHost, s), "D2H containers") &&
+         cuda_ok(cudaMemcpyAsync(challenges, d_ab, W * 16, cudaMemcpyDeviceToHost, s), "D2H challenges") &&
+         cuda_ok(cudaMemcpyAsync(hashes, d_hash, W * 64, cudaMemcpyDeviceToHost, s), "D2H hashes") &&
+         cuda_ok(cudaMemcpyAsync(evq.data(), d_evq, W * 16, cudaMemcpyDeviceToHost, s), "D2H evaluations") &&
+         cuda_ok(cudaMemcpyAsync(evabc.data(), d_evabc, 3 * W * 16, cudaMemcpyDeviceToHost, s), "D2H evaluations") &&
+         cuda_ok(cudaStreamSynchronize(s), "sync");
+    if (!ok) return 4;
+    for (size_t w = 0; w < W; w++) {
+        u64* e = evals + 8 * w;
+        e[0] = evq[2 * w]; e[1] = evq[2 * w + 1];
+        for (size_t mat = 0; mat < 3; mat++) {
+            e[2 + mat] = evabc[2 * (mat * W + w)];          // at alpha
+            e[5 + mat] = evabc[2 * (mat * W + w) + 1];      // at beta
+        }
+    }
+    return 0;
 }
 
 }  // namespace lsr

@@ -206,3 +206,27 @@ def test_lean_export_formats_match_the_reference():
     # SEAL-specific exporters: no SEAL object in this library, -1 like the reference without a SEAL context
     assert lib.export_seal_context_to_lean(None, buf, len(buf)) == -1
     assert lib.export_seal_pubkey_to_lean(None, buf, len(buf)) == -1
+
+
+# ------------------------------------------------------------- Fiat-Shamir transcript hash
+def test_transcript_hash_source_matches_sha3_256(tmp_path):
+    """csrc/lsr_keccak.h (the code fs_challenge_kernel runs, compiled here for the host) against hashlib on
+    every alignment case of the 136-byte rate: challenge.rs:102-134's transcript."""
+    import hashlib
+    import struct
+    import subprocess
+    so = tmp_path / "libkeccak_host.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", str(ROOT / "lambda_snark_r_b200" / "csrc"), "-o", str(so),
+                    str(ROOT / "tests" / "cabi" / "keccak_host.cpp")], check=True)
+    lib = C.CDLL(str(so))
+    rng = np.random.default_rng(1)
+    for n_pub in (0, 1, 2, 5, 16, 17, 40):
+        for n_words in (0, 1, 11, 12, 13, 14, 15, 16, 17, 18, 29, 30, 31, 33, 34, 35, 100, 8193):
+            pub = rng.integers(0, 2**64, n_pub, dtype=np.uint64)
+            words = rng.integers(0, 2**64, n_words, dtype=np.uint64)
+            out = np.zeros(4, dtype=np.uint64)
+            lib.lsr_test_fs_hash(pub.ctypes.data_as(capi.u64p), C.c_uint64(n_pub), words.ctypes.data_as(capi.u64p),
+                                 C.c_uint64(n_words), out.ctypes.data_as(capi.u64p))
+            h = hashlib.sha3_256(b"LAMBDA-SNARK-R-FS-v1" + struct.pack("<Q", n_pub) + pub.tobytes() +
+                                 struct.pack("<Q", n_words) + words.tobytes())
+            assert out.tobytes() == h.digest(), (n_pub, n_words)
