@@ -41,12 +41,20 @@ for row in raw[2:]:
     print("  stalls/issue:", ", ".join(f"{k.split('stalled_')[1].split('_per_')[0]}={v:.2f}" for v, k in stalls[:7]))
 
 src = run("source")
-if len(src) > 2:
-    h = src[1]
+sections, cur = [], None
+for r in src:
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1] if len(r) > 1 else "?", "hdr": None, "rows": []}
+        sections.append(cur)
+    elif cur is not None and cur["hdr"] is None:
+        cur["hdr"] = r
+    elif cur is not None and len(r) == len(cur["hdr"]):
+        cur["rows"].append(r)
+for sec in sections:
+    h, rows = sec["hdr"], sec["rows"]
     ix = {n: i for i, n in enumerate(h)}
-    rows = [r for r in src[2:] if len(r) == len(h)]
     tot = sum(int(r[ix["# Samples"]]) for r in rows)
-    print(f"== source: {len(rows)} SASS instructions, {tot} samples")
+    print(f"== source of {sec['name'][:90]}: {len(rows)} SASS instructions, {tot} samples")
     for r in sorted(rows, key=lambda r: -int(r[ix["# Samples"]]))[:top_n]:
         print(f"  {int(r[ix['# Samples']]):7d} {100.0 * int(r[ix['# Samples']]) / max(tot, 1):5.1f}%  {r[ix['Source']].strip()[:100]}")
     ops = Counter()
@@ -56,6 +64,7 @@ if len(src) > 2:
         op = toks[0].split(".")[0] if toks else "?"
         ops[op] += int(r[ix["# Samples"]])
         execd[op] += int(r[ix["Instructions Executed"]])
-    print("  samples by opcode:", ops.most_common(10))
     te = sum(execd.values())
-    print("  executed by opcode:", [(k, f"{100.0 * v / te:.1f}%") for k, v in execd.most_common(14)])
+    print("  samples by opcode:", ops.most_common(10))
+    print("  executed by opcode:", [(k, f"{100.0 * v / max(te, 1):.1f}%") for k, v in execd.most_common(16)])
+    print(f"  total executed warp-instructions {te}")

@@ -1,7 +1,9 @@
-"""BASELINE configs[2]: batched forward / inverse NTT sweep, n = 2^10 .. 2^16, batch 1 .. 65536 (capped at 4 GiB),
-device-resident data, CUDA events, median of 10 after 3 warm-ups.  q = 17592169062401 for n <= 4096 (2-adicity 13),
-17592180539393 above.  Prints one JSON object; commit it under profiles/."""
+"""BASELINE configs[2]: batched forward / inverse NTT sweep, ring degree 2^10 .. 2^16 (plus the cyclic 2^20 of the
+quotient pipeline), batch 1 .. 65536 (capped at 4 GiB of coefficients), data resident in HBM, CUDA events on the
+launching stream, median of 9 after 3 warm-ups.  q = 17592169062401 for n <= 4096 (2-adicity 13),
+17592180539393 (2-adicity 18) above.  Writes one JSON document to stdout."""
 import json
+import statistics
 import sys
 from pathlib import Path
 
@@ -11,37 +13,55 @@ ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from lambda_snark_r_b200 import api  # noqa: E402
 
-Q0, Q1 = 17592169062401, 17592180539393
-api.set_device(0)
-s = torch.cuda.current_stream().cuda_stream
-hbm = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
-rows = []
-import os
-LOGNS = [int(x) for x in os.environ.get("LSR_SWEEP_LOGN", "10,11,12,13,14,15,16").split(",")]
-BATCHES = [int(x) for x in os.environ.get("LSR_SWEEP_BATCH", "1,16,256,4096,65536").split(",")]
-for logn in LOGNS:
-    n = 1 << logn
-    q = Q0 if n <= 4096 else Q1
-    ctx = api.NttContext(q, n)
-    for batch in BATCHES:
-        if batch * n * 8 > (4 << 30):
-            batch = (4 << 30) // (n * 8)
-        d = torch.randint(0, q, (batch, n), device="cuda", dtype=torch.int64)
-        rec = {"n": n, "batch": batch}
-        for name, fn in (("forward", ctx.forward_device), ("inverse", ctx.inverse_device)):
-            for _ in range(3):
-                fn(d.data_ptr(), batch, s)
-            ts = []
-            for _ in range(10):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); fn(d.data_ptr(), batch, s); e1.record(); torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            ms = sorted(ts)[len(ts) // 2]
-            passes = 1 if logn <= 14 else 2          # n > 2^14: column kernel + tile kernel, two HBM round trips
-            rec[name] = {"ms": ms, "ntt_per_s": batch / (ms * 1e-3), "algorithmic_GBps": batch * n * 16 / (ms * 1e-3) / 1e9,
-                         "hbm_frac": batch * n * 16 / (ms * 1e-3) / 1e9 / hbm, "hbm_round_trips": passes,
-                         "gbutterfly_per_s": batch * (n // 2) * logn / (ms * 1e-3) / 1e9}
-        rows.append(rec)
-        del d
-    ctx.close()
-print(json.dumps({"q_small": Q0, "q_large": Q1, "hbm_peak_gbs": hbm, "rows": rows}))
+Q_SMALL, Q_LARGE, GOLD = 17592169062401, 17592180539393, 2**64 - 2**32 + 1
+
+
+def hbm_peak():
+    try:
+        return json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+    except Exception:
+        return 6549.4
+
+
+def timed(fn, reps=9, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return statistics.median(out)
+
+
+def main():
+    api.set_device(0)
+    s = torch.cuda.current_stream().cuda_stream
+    peak = hbm_peak()
+    rows = []
+    shapes = [(logn, Q_SMALL if logn <= 12 else Q_LARGE, False) for logn in range(10, 17)] + [(20, GOLD, True)]
+    for logn, q, cyclic in shapes:
+        n = 1 << logn
+        ctx = api.CyclicNtt(q, n) if cyclic else api.NttContext(q, n)
+        for batch in (1, 16, 256, 4096, 65536):
+            if batch * n * 8 > (4 << 30):
+                continue
+            data = torch.randint(0, min(q, 2**62), (batch, n), device="cuda", dtype=torch.int64)
+            trips = 1 if logn <= 13 else 1 + (logn - 12 + 4) // 5
+            row = {"n": n, "batch": batch, "q": q, "cyclic": cyclic}
+            for name, fn in (("forward", lambda: ctx.forward_device(data.data_ptr(), batch, s)),
+                             ("inverse", lambda: ctx.inverse_device(data.data_ptr(), batch, s))):
+                ms = timed(fn)
+                gbs = batch * n * 16 / (ms * 1e-3) / 1e9
+                row[name] = {"ms": ms, "ntt_per_s": batch / (ms * 1e-3), "algorithmic_GBps": gbs, "hbm_frac": gbs / peak,
+                             "hbm_round_trips": trips, "gbutterfly_per_s": batch * (n // 2) * logn / (ms * 1e-3) / 1e9}
+            rows.append(row)
+            del data
+        ctx.close()
+    print(json.dumps({"q_small": Q_SMALL, "q_large": Q_LARGE, "goldilocks": GOLD, "hbm_peak_gbs": peak, "rows": rows}))
+
+
+if __name__ == "__main__":
+    main()
