@@ -358,6 +358,22 @@ def run_gpu(args):
                   "e2e": {"value": world * PW / (pe2e_ms * 1e-3), "unit": "witnesses/s", "ms_per_step": pe2e_ms,
                           "h2d_bytes_per_step": PW * ((3 * PM + 1) + chunks) * 8, "d2h_bytes_per_step": PW * chunks * words * 8,
                           "api": "lsr_prover_commit_quotient (C ABI, pinned host buffers)"}}
+        # CPU baseline for this block: the C restatement of ntt.rs / r1cs.rs (oracle/lsr_oracle_quotient.c), one witness,
+        # one host thread -- the reference's own quotient is an O(m^2) schoolbook product (r1cs.rs:846-863) and does not
+        # finish at this size, so the oracle's O(m log m) form is the generous baseline
+        if rank == 0 and args.cpu_seconds > 0:
+            from oracle import oracle as O
+            w1 = api.reference_root_of_unity(GOLD, PM)
+            w2 = api.reference_root_of_unity(GOLD, 2 * PM)
+            tri = [(rows, 3 * rows + 1 + j, one) for j in range(3)]
+            t0 = time.perf_counter()
+            _, st_cpu = O.r1cs_quotient(PM, 3 * PM + 1, tri[0], tri[1], tri[2], z, GOLD, w1, w2)
+            dt_q = time.perf_counter() - t0
+            assert st_cpu == 0
+            prover["cpu_baseline"] = {"value": 1.0 / dt_q, "unit": "quotients/s", "cores": 1, "kind": "port",
+                                      "sample": f"1 quotient of 2^{args.prover_logm} constraints in {dt_q:.2f}s, oracle C port (O(m log m)); "
+                                                f"commitments of the phase are covered by the top-level cpu_baseline",
+                                      "gpu_quotients_per_s": PW / (ms_q * 1e-3)}
         del zs, pout
         r1cs.close()
 

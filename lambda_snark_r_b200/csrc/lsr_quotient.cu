@@ -89,6 +89,62 @@ spmv3_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uin
     if (field_mul(abc[0], abc[1], mp) != abc[2]) atomicOr(flags + w, 1u);
 }
 
+// Same mat-vec for m >= 1024 with both sides coalesced: a CTA owns the 1024 rows r = (a, mid, b) with a fixed
+// middle field (a = top 5 bits, b = low 5 bits); warp a reads 32 consecutive rows, the values cross a padded
+// shared-memory tile, and warp b writes the 32 consecutive destinations brv(r) = (brv5(b), brv(mid), brv5(a)),
+// a = 0..31 -- 256-byte segments instead of 32 scattered 8-byte words.  grid = (m / 1024, witnesses)
+__global__ void __launch_bounds__(256)
+spmv3_tiled_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                   const u64* __restrict__ val, const u64* __restrict__ z, uint32_t rows, uint32_t cols, int logm,
+                   size_t witnesses, u64* __restrict__ E, unsigned* __restrict__ flags) {
+    __shared__ u64 tile[3][32][33];
+    const uint32_t b = threadIdx.x, mid = blockIdx.x;
+    const size_t w = blockIdx.y;
+    const int midbits = logm - 10;
+    const u64* __restrict__ zw = z + w * cols;
+    bool bad = false;
+    // 256 threads, four rows each: a = threadIdx.y + 8 i.  The row pointers of all twelve (row, matrix) pairs are
+    // requested before the first entry is touched.
+    uint32_t lo[4][3], hi[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t r = ((threadIdx.y + 8u * i) << (logm - 5)) | (mid << 5) | b;
+#pragma unroll
+        for (int mat = 0; mat < 3; mat++) {
+            const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
+            lo[i][mat] = __ldg(rp + r);
+            hi[i][mat] = __ldg(rp + r + 1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t a = threadIdx.y + 8u * i;
+        u64 abc[3];
+#pragma unroll
+        for (int mat = 0; mat < 3; mat++) {
+            u64 acc = 0;
+            for (uint32_t k = lo[i][mat]; k < hi[i][mat]; k++)
+                acc = field_add(acc, field_mul(__ldg(val + k), reduce64(__ldg(zw + __ldg(col + k)), mp), mp), mp);
+            tile[mat][a][b] = acc;
+            abc[mat] = acc;
+        }
+        bad |= field_mul(abc[0], abc[1], mp) != abc[2];
+    }
+    if (bad) atomicOr(flags + w, 1u);
+    __syncthreads();
+    // now threadIdx.y (+ 8 i) plays b, threadIdx.x plays a
+    const uint32_t ra = __brev(threadIdx.x) >> 27;
+    const uint32_t rmid = midbits ? (__brev(mid) >> (32 - midbits)) : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t bb = threadIdx.y + 8u * i;
+        const uint32_t dst = ((__brev(bb) >> 27) << (logm - 5)) | (rmid << 5) | ra;
+#pragma unroll
+        for (int mat = 0; mat < 3; mat++)
+            E[((size_t)mat * witnesses + w) * rows + dst] = tile[mat][threadIdx.x][bb];
+    }
+}
+
 // Q^ = (A * B - C) * h on the coset values (any order: pointwise), h = (-2)^-1 = (q - 1) / 2
 __global__ void __launch_bounds__(256)
 coset_quotient_kernel(const ModParams mp, const u64* __restrict__ E, u64* __restrict__ Qh, size_t per_matrix, u64 h) {
@@ -200,7 +256,11 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
                                  witnesses_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D witness") &&
          cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
     if (ok) {
-        spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE, dF);
+        if (logm >= 10 && W <= 65535)
+            spmv3_tiled_kernel<<<dim3(m >> 10, (unsigned)W), dim3(32, 8), 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val,
+                                                                                  dz, m, cols, logm, W, dE, dF);
+        else
+            spmv3_kernel<<<grid(W * m), 256, 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val, dz, m, cols, logm, W, dE, dF);
         ok = cuda_ok(cudaGetLastError(), "spmv3_kernel");
     }
     if (ok && m >= 2) {

@@ -51,8 +51,8 @@ def main():
         return e0.elapsed_time(e1) / reps
     tq = timed(0, 0)
     tf = timed(0, chunks)
-    alg = 324 * m * W
-    print(f"m=2^{logm} W={W} chunks={chunks}: quotient {tq:.3f} ms ({alg / tq / 1e6:.0f} GB/s on 324 B/constraint), "
+    alg = 240 * m * W
+    print(f"m=2^{logm} W={W} chunks={chunks}: quotient {tq:.3f} ms ({alg / tq / 1e6:.0f} GB/s on 240 B/constraint), "
           f"quotient+commit {tf:.3f} ms -> {W / tf * 1e3:.1f} witnesses/s, {W * chunks / tf * 1e3:.0f} commitments/s")
 
 
