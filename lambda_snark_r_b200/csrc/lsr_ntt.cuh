@@ -531,10 +531,22 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
     const u32 T0 = (1u << s0) + blk;
     u64 v[1 << S];
     if (!INVERSE) {
+        // all loads are in flight before the first value is looked at
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) {
-            const u64 x = g[(size_t)j << LG];
-            v[j] = FIRST ? to_working<POL>(sanitize(x, POL == POL_GOLD ? mp.q : mp.q4, mp)) : x;
+        for (int j = 0; j < (1 << S); j++) v[j] = g[(size_t)j << LG];
+        if (FIRST) {
+            // raw caller data: every element <= the OR of all, so one test per thread decides whether the
+            // exact reduction of out-of-range inputs (rare, divergent) can matter at all
+            const u64 limit = POL == POL_GOLD ? mp.q : mp.q4;
+            u64 any = 0;
+#pragma unroll
+            for (int j = 0; j < (1 << S); j++) any |= v[j];
+            if (__builtin_expect(any >= limit, 0)) {
+#pragma unroll
+                for (int j = 0; j < (1 << S); j++) v[j] = sanitize(v[j], limit, mp);
+            }
+#pragma unroll
+            for (int j = 0; j < (1 << S); j++) v[j] = to_working<POL>(v[j]);
         }
         fwd_network<S, POL>(v, tbl.fwd, T0, mp);
     } else {
