@@ -109,26 +109,62 @@ __device__ __forceinline__ u64 barrett128(u64 z0, u64 z1, const ModParams& mp) {
 // POL_GOLD: q = 2^64 - 2^32 + 1.  Residues are canonical u64 in [0, q); sums that overflow 2^64
 // are fixed up with 2^64 = 2^32 - 1 (mod q), i.e. a wrapped subtraction of q.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ u64 gold_add(u64 a, u64 b) {
-    const u64 s = a + b;
-    return (s < a || s >= kGoldilocks) ? s - kGoldilocks : s;
-}
+// Canonical residues in, canonical residue out.  Every correction is a carry / borrow folded back with
+// 2^64 = 2^32 - 1 (mod q): the borrow of a subtraction chain turned into the mask 0xffffffff (= eps) by
+// `subc m, 0, 0`, the carry of an addition chain by `addc` -- no 64-bit compare / select pairs, which is what
+// the ALU-pipe-bound Goldilocks butterflies were mostly made of (12 ISETP + 10 SEL of 48 instructions).
+// Chains are homogeneous (sub.cc ... subc, add.cc ... addc): the two flag conventions are never mixed.
 __device__ __forceinline__ u64 gold_sub(u64 a, u64 b) {
-    const u64 d = a - b;
-    return a < b ? d + kGoldilocks : d;
+    // d = a - b; on borrow the wrapped value is 2^64 = eps too large
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), m;
+    asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "+r"(a0), "+r"(a1), "=r"(m) : "r"(b0), "r"(b1));
+    return ((u64)a1 << 32) | a0;
 }
-// (hi:lo) mod q:  hi = hh * 2^32 + hl  ->  lo + hl * (2^32 - 1) - hh
+__device__ __forceinline__ u64 gold_neg_raw(u64 b) { return kGoldilocks - b; }      // in [1, q] for canonical b
+// a + b = a - (q - b); q - b = q for b = 0 is handled by the same borrow correction
+__device__ __forceinline__ u64 gold_add(u64 a, u64 b) { return gold_sub(a, gold_neg_raw(b)); }
+
+// full 64 x 64 -> 128 product: four 32 x 32 multiply-adds with 64-bit accumulators, two carry adds
+__device__ __forceinline__ void mul64_wide(u64 a, u64 b, u64& lo, u64& hi) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 p0 = (u64)a0 * b0;
+    const u64 t = (u64)a0 * b1 + (p0 >> 32);               // <= (2^32-1)^2 + 2^32 - 1 < 2^64
+    const u64 u = (u64)a1 * b0 + (u32)t;
+    hi = (u64)a1 * b1 + (t >> 32) + (u >> 32);             // the product is < 2^128: no overflow
+    lo = (u << 32) | (u32)p0;
+}
+
+// (hi:lo) mod q for ANY 128-bit value:  hi = hh * 2^32 + hl  ->  lo + hl * (2^32 - 1) - hh   (2^96 = -1, 2^64 = eps)
 __device__ __forceinline__ u64 gold_reduce128(u64 lo, u64 hi) {
-    const u64 eps = 0xFFFFFFFFull;
-    const u64 hh = hi >> 32, hl = hi & eps;
-    u64 t0 = lo - hh;
-    if (lo < hh) t0 -= eps;                   // the borrow took 2^64 = eps (mod q) too much
-    const u64 t1 = hl * eps;                  // < 2^64
-    u64 r = t0 + t1;
-    if (r < t1) r += eps;                     // the carry dropped 2^64 = eps (mod q)
-    return r >= kGoldilocks ? r - kGoldilocks : r;
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32);
+    const u32 hl = (u32)hi, hh = (u32)(hi >> 32);
+    const u64 t1 = (u64)hl * 0xFFFFFFFFu;                   // < 2^64 - 2^33 + 2
+    u32 m;
+    // t0 = lo - hh, borrow -> - eps (cannot borrow again: lo - hh + 2^64 >= 2^64 - eps)
+    asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 %2, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "+r"(r0), "+r"(r1), "=r"(m) : "r"(hh));
+    // r = t0 + t1, carry -> + eps (cannot carry again: the sum is then <= 2^64 - 2^32 - 1 < q)
+    u32 c;
+    asm("{\n\tadd.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;\n\t}"
+        : "+r"(r0), "+r"(r1), "=r"(c) : "r"((u32)t1), "r"((u32)(t1 >> 32)));
+    u32 cm = 0u - c;
+    asm("{\n\tadd.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+r"(r0), "+r"(r1) : "r"(cm));
+    // canonical: r >= q  <=>  r + eps carries; then r - q = r + eps (mod 2^64)
+    u32 c3, s0, s1;
+    asm("{\n\tadd.cc.u32 %0, %3, 0xffffffff;\n\taddc.cc.u32 %1, %4, 0;\n\taddc.u32 %2, 0, 0;\n\t}"
+        : "=r"(s0), "=r"(s1), "=r"(c3) : "r"(r0), "r"(r1));
+    cm = 0u - c3;
+    asm("{\n\tadd.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+r"(r0), "+r"(r1) : "r"(cm));
+    return ((u64)r1 << 32) | r0;
 }
-__device__ __forceinline__ u64 gold_mul(u64 a, u64 b) { return gold_reduce128(a * b, __umul64hi(a, b)); }
+__device__ __forceinline__ u64 gold_mul(u64 a, u64 b) {
+    u64 lo, hi;
+    mul64_wide(a, b, lo, hi);
+    return gold_reduce128(lo, hi);
+}
 
 // exact (a * b) mod q for any u64 a, b  (ntt.cpp:116-118 -> multiply_uint_mod)
 __device__ __forceinline__ u64 mulmod_exact(u64 a, u64 b, const ModParams& mp) {
