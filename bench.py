@@ -300,6 +300,25 @@ def run_gpu(args):
     ms_mul = timed(lambda: ntt.mul_pointwise_device(data2.data_ptr(), data.data_ptr(), data2.data_ptr(), NB * N_RING, stream),
                    args.warmup, args.steps) / args.steps
 
+    # ---- end to end through the host-pointer C ABI, pinned host buffers
+    EB = args.e2e_batch
+    h_msgs = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
+    h_seeds = (torch.arange(EB, dtype=torch.int64) + (SEED_BASE + rank * EB)).pin_memory()
+    h_out = torch.empty((EB, words), dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        ctx.commit_batch_ptr(h_msgs.data_ptr(), N_RING, h_seeds.data_ptr(), EB, h_out.data_ptr())
+
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_value = world * EB / (e2e_ms * 1e-3)
     # ---- prover commitment phase (BASELINE configs[4]): 2^20-constraint R1CS over Goldilocks, quotient polynomial on
     # the device, cut into m / n ring elements, each committed; weak scaling over witnesses (every rank proves its own)
     prover = None
@@ -377,25 +396,6 @@ def run_gpu(args):
         del zs, pout
         r1cs.close()
 
-    # ---- end to end through the host-pointer C ABI, pinned host buffers
-    EB = args.e2e_batch
-    h_msgs = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
-    h_seeds = (torch.arange(EB, dtype=torch.int64) + (SEED_BASE + rank * EB)).pin_memory()
-    h_out = torch.empty((EB, words), dtype=torch.int64).pin_memory()
-
-    def e2e_step():
-        ctx.commit_batch_ptr(h_msgs.data_ptr(), N_RING, h_seeds.data_ptr(), EB, h_out.data_ptr())
-
-    e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
-    e2e_value = world * EB / (e2e_ms * 1e-3)
     # the timed regions are a few tens of ms each: nvidia-smi samples every 100 ms, so the sampler stays on across all of
     # them (commit, NTT, e2e) and the loop below keeps the commit kernel running until it has seen >= 10 samples
     if rank == 0:
