@@ -345,6 +345,15 @@ int lsr_prove_r1cs_batch(void* r1cs, LweContext* ctx, const uint64_t* witnesses,
                          size_t n_public, uint64_t omega, const uint64_t* seeds, uint64_t* containers,
                          uint64_t* challenges, uint64_t* hashes, uint64_t* evals, int* status) LSR_NOEXCEPT;
 
+/* verify_r1cs (lib.rs:1016-1082) for `count` proofs of one circuit with n_constraints = m (a power of two) on the
+ * NTT path, Z_H(X) = X^m - 1 (r1cs.rs:424-430): recomputes alpha from (public_inputs[i], containers[i]) and beta from
+ * (alpha, containers[i]) on the device, compares them with challenges[i][0..2), and checks
+ * Q(x) Z_H(x) = A_z(x) B_z(x) - C_z(x) at x = alpha, beta with evals[i][8] in the order lsr_prove_r1cs_batch writes.
+ * results[i] = 1 accept / 0 reject; returns 0, or -1 on bad arguments / device failure.  HOST pointers.           */
+int lsr_verify_r1cs_batch(uint64_t n_constraints, uint64_t modulus, const uint64_t* public_inputs, size_t n_public,
+                          const uint64_t* containers, size_t words, const uint64_t* challenges, const uint64_t* evals,
+                          size_t count, int* results) LSR_NOEXCEPT;
+
 /* Arithmetic of the NTT butterflies (NttContext, and the NttContext inside an
  * LweContext): 0 auto -- FP64-pipe butterflies (exact modular products by
  * error-free fma multiplication) when q < 2^45, else u64 Shoup butterflies;

@@ -569,3 +569,20 @@ def poly_eval_batch(coeffs, points, modulus: int) -> np.ndarray:
     if rc != 0:
         raise LambdaSnarkError(f"lsr_poly_eval_batch failed: {last_error()}")
     return out
+
+
+def verify_r1cs_batch(n_constraints: int, modulus: int, public_inputs, containers, challenges, evals) -> np.ndarray:
+    """verify_r1cs (lib.rs:1016-1082) for a batch of proofs of one circuit on the NTT path; 1 accept / 0 reject."""
+    import ctypes as C_
+    c = np.ascontiguousarray(_u64(containers))
+    c = c.reshape(1, -1) if c.ndim == 1 else c
+    count = c.shape[0]
+    pub = np.ascontiguousarray(_u64(public_inputs)).reshape(count, -1)
+    ch = np.ascontiguousarray(_u64(challenges)).reshape(count, 2)
+    ev = np.ascontiguousarray(_u64(evals)).reshape(count, 8)
+    res = np.zeros(count, dtype=np.int32)
+    rc = _lib().lsr_verify_r1cs_batch(n_constraints, modulus, _p(pub), pub.shape[1], _p(c), c.shape[1], _p(ch), _p(ev), count,
+                                      res.ctypes.data_as(C_.POINTER(C_.c_int)))
+    if rc != 0:
+        raise LambdaSnarkError(f"lsr_verify_r1cs_batch failed: {last_error()}")
+    return res

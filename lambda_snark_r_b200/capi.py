@@ -118,6 +118,8 @@ SIGNATURES = {
     "lsr_poly_eval_batch": (C.c_int, [C.c_uint64, u64p, C.c_size_t, C.c_size_t, u64p, C.c_size_t, u64p]),
     "lsr_prove_r1cs_batch": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, u64p,
                                       u64p, u64p, u64p, u64p, C.POINTER(C.c_int)]),
+    "lsr_verify_r1cs_batch": (C.c_int, [C.c_uint64, C.c_uint64, u64p, C.c_size_t, u64p, C.c_size_t, u64p, u64p, C.c_size_t,
+                                       C.POINTER(C.c_int)]),
     "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
     "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),

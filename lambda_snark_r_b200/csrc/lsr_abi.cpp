@@ -21,6 +21,8 @@ bool fs_challenge_launch(const u64* d_pub, size_t n_pub, const u64* d_containers
                          u64 modulus, bool chain, u64* d_ab, u64* d_hashes, cudaStream_t s);
 bool fs_challenge_host(const u64* pub, size_t n_pub, const u64* containers, size_t words, size_t count, u64 modulus,
                        bool chain, u64* ab, u64* hashes);
+bool verify_r1cs_host(u64 m, u64 modulus, const u64* pub, size_t n_pub, const u64* containers, size_t words,
+                      const u64* challenges, const u64* evals, size_t count, int* results);
 bool poly_eval_host(u64 modulus, const u64* coeffs, size_t len, size_t polys, const u64* points, size_t npts, u64* out);
 int prove_r1cs_batch(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, size_t n_public,
                      u64 omega, const u64* seeds, u64* containers, u64* challenges, u64* hashes, u64* evals, int* status);
@@ -262,6 +264,17 @@ int lsr_prove_r1cs_batch(void* r1cs, LweContext* ctx, const uint64_t* witnesses,
                                  reinterpret_cast<u64*>(challenges), reinterpret_cast<u64*>(hashes),
                                  reinterpret_cast<u64*>(evals), status);
     LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
+}
+
+int lsr_verify_r1cs_batch(uint64_t n_constraints, uint64_t modulus, const uint64_t* public_inputs, size_t n_public,
+                          const uint64_t* containers, size_t words, const uint64_t* challenges, const uint64_t* evals,
+                          size_t count, int* results) LSR_NOEXCEPT {
+    LSR_TRY
+    if ((!public_inputs && n_public && count) || !containers || !challenges || !evals || !results) return -1;
+    return lsr::verify_r1cs_host(n_constraints, modulus, reinterpret_cast<const u64*>(public_inputs), n_public,
+                                 reinterpret_cast<const u64*>(containers), words, reinterpret_cast<const u64*>(challenges),
+                                 reinterpret_cast<const u64*>(evals), count, results) ? 0 : -1;
+    LSR_CATCH(-1)
 }
 
 int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,

@@ -14,6 +14,7 @@
 // source is checked on the host against hashlib by the CPU tests).  Evaluations: one CTA per
 // (polynomial, point), each thread a contiguous run of coefficients by Horner, scaled by x^start, tree sum.
 #include <algorithm>
+#include <vector>
 
 #include "lsr_arith.cuh"
 #include "lsr_engine.h"
@@ -134,6 +135,34 @@ bool poly_eval_host(u64 modulus, const u64* coeffs, size_t len, size_t polys, co
          cuda_ok(cudaMemcpy(out, d_o, polys * npts * 8, cudaMemcpyDeviceToHost), "D2H");
     cudaFree(d_c); cudaFree(d_p); cudaFree(d_o);
     return ok;
+}
+
+// verify_r1cs (rust-api/lambda-snark/src/lib.rs:1016-1082) for a batch of proofs of one circuit on its NTT path
+// (Z_H(X) = X^m - 1, r1cs.rs:424-430): the two transcript hashes run on the device (fs_challenge_kernel), the two
+// field equations per proof are a dozen modular products on the host.  results[i] = 1 accept, 0 reject.
+bool verify_r1cs_host(u64 m, u64 modulus, const u64* pub, size_t n_pub, const u64* containers, size_t words,
+                      const u64* challenges, const u64* evals, size_t count, int* results) {
+    if (count == 0) return true;
+    if (modulus < 2 || m == 0) { set_error("verify_r1cs: bad modulus / constraint count"); return false; }
+    std::vector<u64> ab(count * 2), hs(count * 8);
+    if (!fs_challenge_host(pub, n_pub, containers, words, count, modulus, true, ab.data(), hs.data())) return false;
+    typedef unsigned __int128 u128;
+    auto mul = [&](u64 a, u64 b) { return (u64)(((u128)(a % modulus) * (b % modulus)) % modulus); };
+    auto sub = [&](u64 a, u64 b) { a %= modulus; b %= modulus; return a >= b ? a - b : (u64)((u128)a + modulus - b); };
+    auto zh = [&](u64 x) {                                     // x^m - 1
+        u64 r = 1 % modulus, base = x % modulus;
+        for (u64 e = m; e; e >>= 1) { if (e & 1) r = mul(r, base); base = mul(base, base); }
+        return sub(r, 1);
+    };
+    for (size_t i = 0; i < count; i++) {
+        const u64* e = evals + 8 * i;                          // {Q(a), Q(b), A(a), B(a), C(a), A(b), B(b), C(b)}
+        const u64 alpha = ab[2 * i], beta = ab[2 * i + 1];
+        bool ok = challenges[2 * i] == alpha && challenges[2 * i + 1] == beta;       // lib.rs:1020-1037
+        ok = ok && mul(e[0], zh(alpha)) == sub(mul(e[2], e[3]), e[4]);                // :1047-1056
+        ok = ok && mul(e[1], zh(beta)) == sub(mul(e[5], e[6]), e[7]);                 // :1058-1067
+        results[i] = ok ? 1 : 0;                               // openings carry Q(alpha), Q(beta) themselves (:1073-1079)
+    }
+    return true;
 }
 
 }  // namespace lsr

@@ -81,4 +81,14 @@ def test_prove_r1cs_batch_matches_the_restated_prover(gpu, m):
         assert got == want
         for x, qx, ax, bx, cx in ((alpha, got[0], got[2], got[3], got[4]), (beta, got[1], got[5], got[6], got[7])):
             assert (qx * (pow(x, m, q) - 1)) % q == (ax * bx - cx) % q   # Q(x) Z_H(x) = A_z(x) B_z(x) - C_z(x)
+    # the batched verifier accepts the two honest proofs and rejects tampered ones
+    pubs = W[:, :l]
+    ok = api.verify_r1cs_batch(m, q, pubs, out["containers"], out["challenges"], out["evals"])
+    assert ok.tolist() == [1, 0, 1]                                    # row 1 is the unsatisfying witness
+    bad_ev = out["evals"].copy(); bad_ev[0, 0] = (int(bad_ev[0, 0]) + 1) % q
+    bad_ct = out["containers"].copy(); bad_ct[2, 5] ^= np.uint64(1)
+    bad_pub = pubs.copy(); bad_pub[0, -1] = (int(bad_pub[0, -1]) + 1) % q
+    assert api.verify_r1cs_batch(m, q, pubs, out["containers"], out["challenges"], bad_ev).tolist()[0] == 0
+    assert api.verify_r1cs_batch(m, q, pubs, bad_ct, out["challenges"], out["evals"]).tolist()[2] == 0
+    assert api.verify_r1cs_batch(m, q, bad_pub, out["containers"], out["challenges"], out["evals"]).tolist()[0] == 0
     ctx.close(); r.close()
