@@ -220,6 +220,27 @@ def workload_config(batch, where):
             "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)"}
 
 
+def bind_to_gpu_numa_node(props):
+    """Multi-rank runs: keep a rank's threads (and therefore its pinned host buffers, first-touch) on the NUMA node its
+    GPU hangs off, so the end-to-end leg does not cross the socket interconnect.  Best effort; returns the node or None."""
+    try:
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -234,6 +255,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     api.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local)) if world > 1 else None
     if world > 1:
         # stdout carries the one JSON line: NCCL's own log (it prints its version banner at NCCL_DEBUG >= VERSION) goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -463,7 +486,8 @@ def run_gpu(args):
                              "bounds_ntt_per_s": bounds, "slower_bound": slow, "frac_of_slower_bound": per_gpu / live[slow],
                              "imad_survey_frac": gimad / imad_peak if imad_peak else None}}
 
-    # CPU baseline: bounded sample of the same workload on this box's host cores
+    # CPU baseline: bounded sample of the same workload on this box's host cores (all of them again)
+    os.sched_setaffinity(0, all_cpus)
     cpu_rate, cpu_threads, cpu_count, cpu_dt, native = cpu_commit_rate(args.cpu_seconds)
     ntt_cpu_rate, _, ntt_cpu_count, ntt_cpu_dt = cpu_ntt_rate(min(args.cpu_seconds, 5.0))
 
@@ -500,7 +524,7 @@ def run_gpu(args):
                          "ntt_forward_per_s": ntt_cpu_rate},
         "e2e": {"value": e2e_value, "unit": "commitments/s", "h2d_bytes_per_step": EB * (N_RING + 1) * 8,
                 "d2h_bytes_per_step": EB * words * 8, "batch_per_gpu": EB, "ms_per_step": e2e_ms,
-                "api": "lwe_commit_batch (C ABI, pinned host buffers)"},
+                "api": "lwe_commit_batch (C ABI, pinned host buffers)", "numa_node": numa},
         "gpu_launches": args.steps,
         "clocks": clocks,
         "ntt": {"batch_per_gpu": NB, "forward": ntt_block(ms_fwd, FP64_NTT_FWD), "inverse": ntt_block(ms_inv, FP64_NTT_INV, N_RING // 2),
