@@ -120,6 +120,7 @@ __device__ __forceinline__ u64 gold_sub(u64 a, u64 b) {
     asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;\n\t"
         "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
         : "+r"(a0), "+r"(a1), "=r"(m) : "r"(b0), "r"(b1));
+    (void)m;
     return ((u64)a1 << 32) | a0;
 }
 __device__ __forceinline__ u64 gold_neg_raw(u64 b) { return kGoldilocks - b; }      // in [1, q] for canonical b
@@ -146,6 +147,7 @@ __device__ __forceinline__ u64 gold_reduce128(u64 lo, u64 hi) {
     asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 %2, 0, 0;\n\t"
         "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
         : "+r"(r0), "+r"(r1), "=r"(m) : "r"(hh));
+    (void)m;
     // r = t0 + t1, carry -> + eps (cannot carry again: the sum is then <= 2^64 - 2^32 - 1 < q)
     u32 c;
     asm("{\n\tadd.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;\n\t}"

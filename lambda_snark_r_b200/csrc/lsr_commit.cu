@@ -48,8 +48,9 @@ sample_se_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, u6
     u32 sg[16];
     chacha_block(key, s_lo, s_hi, tau, kDomCommit | (4u * k), sg);
     for (u32 P = 0; P < 2 * k; P++) {
-        u64* dst = (P < k) ? S + ((b * k + P) * (size_t)n) + 16u * tau
-                           : out + b * out_stride + 1 + (size_t)(P - k) * n + 16u * tau;
+        // chunk tau = the 16 coefficients tau + (n/16) j
+        u64* dst = (P < k) ? S + ((b * k + P) * (size_t)n) + tau
+                           : out + b * out_stride + 1 + (size_t)(P - k) * n + tau;
         const u32 sbits = sg[P >> 1] >> ((P & 1) * 16);
 #pragma unroll
         for (u32 h = 0; h < 2; h++) {
@@ -60,7 +61,7 @@ sample_se_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, u6
                 const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
                 const u32 mag = cdt_magnitude_global(cdf, cdf_n, u);
                 const u32 j = 8 * h + w;
-                dst[j] = signed_residue(mag, (sbits >> j) & 1u, q);
+                dst[(size_t)j * chunks] = signed_residue(mag, (sbits >> j) & 1u, q);
             }
         }
     }

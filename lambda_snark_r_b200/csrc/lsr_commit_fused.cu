@@ -11,8 +11,9 @@
 //   phase 4  inverse NTT of the k rows, same tile
 //   phase 5  + e_i (+ Delta*m on the last row) fused into the coalesced store of
 //            the LweCommitment container
-// Shared memory: k*n*8 (residues) + k*n (errors) = 72 KiB at n=4096, k=2, so
-// three CTAs share an SM.  HBM traffic per commitment: message in (8n) +
+// Shared memory: k*n*8 (residues) + k*n (errors) = 72 KiB at n=4096, k=2 in the general form; the n = 4096
+// form (fused_fast) samples s and e in the registers that consume them and needs 68 KiB (padded layout).
+// Three CTAs share an SM either way.  HBM traffic per commitment: message in (8n) +
 // container out (8kn + 8).
 //
 // Replaces Encryptor::encrypt_symmetric + BatchEncoder::encode +
@@ -24,6 +25,10 @@
 #include "lsr_engine.h"
 #include "lsr_ntt.cuh"
 #include "lsr_sampler.cuh"
+
+#ifndef LSR_FUSED_FAST
+#define LSR_FUSED_FAST 1
+#endif
 
 namespace lsr {
 
@@ -43,31 +48,120 @@ struct FusedParams {
     u32 skip;                 // PROFILING ONLY (env LSR_FUSED_SKIP): bit i set = phase i+1 not executed; results are garbage
 };
 
+// FAST shape: n = 4096.  n/16 chunks = kNttThreads and plan<12> = 4+4+4, so the radix-16 first forward pass and
+// last inverse pass give thread tau exactly the coefficients tau + 256 j of every polynomial -- the chunk tau of the
+// randomness layout.  s is then sampled straight into the registers of the first forward pass and e
+// straight into the registers of the epilogue: neither crosses shared memory, the e buffer disappears, and the 4 KiB
+// per polynomial that frees pay for the padded layout (lsr_ntt.cuh padx) and leave the L1 some room for twiddles.
 template <int LOGN, int K>
-constexpr size_t fused_smem() { return ((size_t)K << LOGN) * sizeof(u64) + ((size_t)K << LOGN); }
+__host__ __device__ constexpr bool fused_fast() { return LOGN == 12 && kNttThreads == 256 && LSR_FUSED_FAST; }
 
 template <int LOGN, int K>
-constexpr int fused_min_blocks() {
+__host__ __device__ constexpr size_t fused_smem() {
+    return fused_fast<LOGN, K>() ? (((size_t)K << LOGN) + ((size_t)K << (LOGN - 4))) * sizeof(u64)
+                                 : ((size_t)K << LOGN) * sizeof(u64) + ((size_t)K << LOGN);
+}
+
+template <int LOGN, int K>
+__host__ __device__ constexpr int fused_min_blocks() {
     return fused_smem<LOGN, K>() <= 75 * 1024 ? 3 : (fused_smem<LOGN, K>() <= 113 * 1024 ? 2 : 1);
 }
 
-// value (canonical row coefficient) -> + e_i[x] (+ Delta * (m[x] mod p) on row K-1), reduced
+// canonical row coefficient v at tile index idx -> + e (+ Delta * (m[x] mod p) on row K-1), reduced
+template <int LOGN, int K>
+__device__ __forceinline__ u64 commit_finish(u32 idx, u64 v, int ev, const u64* __restrict__ msg, u64 q, u64 delta,
+                                             u64 p, u64 pinv, u32 msg_used) {
+    v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                    // < 2q
+    const u32 x = idx - ((u32)(K - 1) << LOGN);                                // wraps for earlier rows
+    if (idx >= ((u32)(K - 1) << LOGN) && x < msg_used) {
+        // messages are field elements in practice (>= p more often than not): Barrett, not a 64-bit division
+        const u64 m = p < (1ull << 21) ? (u64)mod_small(__ldcs(msg + x), (u32)p, pinv) : __ldcs(msg + x) % p;
+        v = csub(v + delta * m, q);                                            // delta*m <= q-1
+    }
+    return csub(v, q);
+}
+
+// legacy epilogue: e comes from the int8 buffer in shared memory
 template <int LOGN, int K>
 struct CommitEpilogue {
+    static constexpr bool kWholeItem = false;
+    struct Pre {};
     const signed char* E;
     const u64* msg;
     u64 q, delta, p, pinv;
     u32 msg_used;
     __device__ __forceinline__ u64 operator()(u32 idx, u64 v) const {
-        const int ev = E[idx];
-        v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                // < 2q
-        const u32 x = idx - ((u32)(K - 1) << LOGN);                            // wraps for earlier rows
-        if (idx >= ((u32)(K - 1) << LOGN) && x < msg_used) {
-            // messages are field elements in practice (>= p more often than not): Barrett, not a 64-bit division
-            const u64 m = p < (1ull << 21) ? (u64)mod_small(__ldcs(msg + x), (u32)p, pinv) : __ldcs(msg + x) % p;
-            v = csub(v + delta * m, q);                                        // delta*m <= q-1
+        return commit_finish<LOGN, K>(idx, v, (int)E[idx], msg, q, delta, p, pinv, msg_used);
+    }
+};
+
+// one CDT sample from a 64-bit uniform word; all 32 lanes of the warp call together
+template <int NCH8>
+struct CdtLanes {
+    const CdtParam& cdt;
+    bool compact;
+    u64 lane_entry;
+    u32 lane_cum;
+    __device__ __forceinline__ u32 operator()(u64 u) const {
+        return compact ? cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u)
+                       : cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
+    }
+};
+
+// The 16 samples of chunk tau of polynomial P as signed bytes packed into four words (lane j in byte j & 3 of word
+// j >> 2).  Sampling into 4 registers instead of 16 doubles keeps the register pressure low enough for the compiler
+// to interleave the eight shuffle searches of a ChaCha block.
+template <int NCH8>
+__device__ __forceinline__ void sample_chunk_packed(const ChaChaKey& key, u32 s_lo, u32 s_hi, u32 tau, u32 P, u32 sbits,
+                                                    const CdtLanes<NCH8>& cdtl, u32 (&pk)[4]) {
+    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+#pragma unroll
+    for (u32 h = 0; h < 2; h++) {
+        u32 x[16];
+        chacha_block(key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
+#pragma unroll
+        for (u32 w = 0; w < 8; w++) {
+            const u32 j = 8 * h + w;
+            const u32 mag = cdtl((u64)x[2 * w] | ((u64)x[2 * w + 1] << 32));
+            const int sv = ((sbits >> j) & 1u) ? -(int)mag : (int)mag;        // -0 == 0: no test of mag needed
+            pk[j >> 2] |= ((u32)sv & 0xffu) << (8u * (j & 3u));
         }
-        return csub(v, q);
+    }
+}
+__device__ __forceinline__ int unpack_s8(const u32 (&pk)[4], u32 j) {
+    return (int)(signed char)(pk[j >> 2] >> (8u * (j & 3u)));
+}
+
+// FAST epilogue: the work item (row, tau) samples its own 16 error terms -- before its coefficients are loaded --
+// and finishes + stores its coefficients
+template <int LOGN, int K, int NCH8>
+struct CommitEpilogueFast {
+    static constexpr bool kWholeItem = true;
+    struct Pre { u32 pk[4]; };
+    const FusedParams& fp;
+    const CdtLanes<NCH8>& cdtl;
+    const u64* msg;
+    u32 s_lo, s_hi;
+    u32 esg[2];                   // sign words of the e polynomials: block 4K words (K >> 1), (K >> 1) + 1
+    bool no_e;                    // profiling only
+    __device__ __forceinline__ Pre pre(u32 W) const {
+        constexpr u32 LG = LOGN - 4;
+        const u32 row = W >> LG, tau = W & ((1u << LG) - 1u);
+        const u32 P = (u32)K + row;
+        const u32 sbits = esg[(P >> 1) - ((u32)K >> 1)] >> ((P & 1u) * 16u);
+        Pre r;
+        if (no_e) { r.pk[0] = r.pk[1] = r.pk[2] = r.pk[3] = 0u; }
+        else sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, sbits, cdtl, r.pk);
+        return r;
+    }
+    __device__ __forceinline__ void item(u64* __restrict__ g, u32, u32 base, const u64 (&v)[16], const Pre& pre) const {
+        constexpr u32 LG = LOGN - 4;
+        const ModParams& mp = fp.mp;
+#pragma unroll
+        for (u32 j = 0; j < 16; j++) {
+            const u32 idx = base + (j << LG);
+            __stcs(g + idx, commit_finish<LOGN, K>(idx, v[j], unpack_s8(pre.pk, j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used));
+        }
     }
 };
 
@@ -75,10 +169,11 @@ template <int LOGN, int K, int NCH8, int POL>
 __global__ void __launch_bounds__(kNttThreads, fused_min_blocks<LOGN, K>())
 fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constant__ CdtParam cdt) {
     constexpr u32 n = 1u << LOGN;
+    constexpr bool FAST = fused_fast<LOGN, K>();
     static_assert((n >> 4) % 32 == 0, "whole warps must take part in the shuffle search");
+    static_assert(K <= 4, "sign words 0..3 only");
     extern __shared__ __align__(16) u64 sm[];
-    u64* S = sm;                                                     // [K][n], swizzled
-    signed char* E = reinterpret_cast<signed char*>(sm + (size_t)K * n);   // [K][n]
+    u64* S = sm;                                                     // [K][n], swizzled (FAST: padded)
     const ModParams& mp = fp.mp;
     const size_t b = blockIdx.x;
     const u64 seed = fp.seeds[b];
@@ -86,7 +181,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const bool compact = cdt.compact != 0;                           // a property of the table, uniform over the grid
     const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
                                    : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
-    const u32 lane_cum = cdt.dcum[threadIdx.x & 31u];
+    const CdtLanes<NCH8> cdtl{cdt, compact, lane_entry, cdt.dcum[threadIdx.x & 31u]};
 
     // the message is consumed by the last pass only: pull it towards L2 now (one 128-byte line per thread)
     // so that the epilogue's loads do not wait on HBM
@@ -95,12 +190,89 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         for (u32 x = threadIdx.x * 16u; x < fp.msg_used; x += kNttThreads * 16u)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(m + x));
     }
+    u64* o = fp.out + b * (1 + (size_t)K * n);
+    if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
 
+    if constexpr (FAST) {
+        // ---- phase 1+2a: chunk tau = threadIdx.x.  s_P[tau + 256 j] is sampled into v[j], the radix-16 first
+        // pass (stages 0-3, grid-uniform twiddles from the kernel parameters) runs on it, and only its output
+        // goes to shared memory.
+        const u32 tau = threadIdx.x;
+        u32 esg[2] = {0u, 0u};
+        {
+            u32 sg[16];
+            if (!(fp.skip & 1u)) chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
+            else { for (int i = 0; i < 16; i++) sg[i] = 0; }
+            esg[0] = sg[K >> 1];
+            esg[1] = sg[(K >> 1) + 1 < 4 ? (K >> 1) + 1 : 3];
+#pragma unroll 1
+            for (u32 P = 0; P < (u32)K; P++) {
+                const u32 wsel = P >> 1;
+                const u32 sw = wsel == 0 ? sg[0] : sg[1];
+                const u32 sbits = sw >> ((P & 1) * 16);
+                u32 pk[4] = {0u, 0u, 0u, 0u};
+                if (!(fp.skip & 1u)) sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, sbits, cdtl, pk);
+                u64 v[16];
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) {
+                    const int sv = unpack_s8(pk, j);
+                    v[j] = POL == POL_F64 ? as_u((double)sv) : (sv < 0 ? mp.q - (u64)(-sv) : (u64)sv);
+                }
+                if (!(fp.skip & 2u)) fwd_network<4, POL, false, true>(v, fp.tbl.fwd, 1u, mp, 0u, fp.tbl.head_fwd);
+                const u32 pb = padx((P << LOGN) + tau);
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) S[pb + j * 272u] = v[j];          // padded stride of 256 coefficients
+            }
+        }
+        __syncthreads();
+        // ---- phase 2b: remaining forward passes (POL_F64: evaluations stay unreduced, the mat-vec product reduces)
+        if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, POL, true, 1>(S, fp.tbl, mp, (u32)K * n, 0u);
+
+        // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
+        for (u32 x = threadIdx.x; x < ((fp.skip & 4u) ? 0u : n); x += kNttThreads) {
+            u64 sv[K];
+#pragma unroll
+            for (u32 j = 0; j < (u32)K; j++) sv[j] = S[padx((j << LOGN) + x)];
+#pragma unroll
+            for (u32 i = 0; i < (u32)K; i++) {
+                if (POL == POL_F64) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (u32 j = 0; j < (u32)K; j++) {
+                        const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
+                        acc = __dadd_rn(acc, mulmod_f(as_d(sv[j]), as_d(a.x), as_d(a.y), mp.qd));   // each term <= 0.75 q
+                    }
+                    S[padx((i << LOGN) + x)] = as_u(acc);                          // |acc| <= 0.75 K q <= 3 q
+                } else {
+                    u64 acc = 0;
+#pragma unroll
+                    for (u32 j = 0; j < (u32)K; j++) {
+                        const ulonglong2 a = __ldg(fp.A2 + ((size_t)(i * K + j) << LOGN) + x);
+                        acc += mulred4(sv[j], a.x, a.y, mp.nq);                   // each term < 4q
+                    }
+                    S[padx((i << LOGN) + x)] = reduce_small(acc, mp);              // 4Kq <= 16q < 2^7 q
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 4+5: inverse transform of the K rows; its last pass (thread tau again owns tau + 256 j) samples
+        // e in registers, adds it (and Delta*m on the last row) and stores the container straight to HBM
+        if (!(fp.skip & 8u)) {
+            const CommitEpilogueFast<LOGN, K, NCH8> epi{fp, cdtl, fp.msgs + b * (size_t)fp.msg_len, s_lo, s_hi,
+                                                        {esg[0], esg[1]}, (fp.skip & 33u) != 0};
+            tile_inverse_to_global<LOGN, LOGN, POL, CommitEpilogueFast<LOGN, K, NCH8>, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
+        }
+        return;
+    }
+
+    // =============================== other shapes: sampler -> shared memory -> transforms ===============================
+    signed char* E = reinterpret_cast<signed char*>(sm + (size_t)K * n);   // [K][n]
+    constexpr u32 CH = n >> 4;                                              // chunks; chunk tau = coefficients tau + CH j
     // ---- phase 1: randomness (DESIGN.md 3.3 layout, same as sample_se_kernel)
-    for (u32 tau = threadIdx.x; tau < ((fp.skip & 1u) ? 0u : (n >> 4)); tau += kNttThreads) {
+    for (u32 tau = threadIdx.x; tau < ((fp.skip & 1u) ? 0u : CH); tau += kNttThreads) {
         u32 sg[16];
         chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
-        static_assert(K <= 4, "sign words 0..3 only");
 #pragma unroll 1
         for (u32 P = 0; P < 2 * K; P++) {
             const u32 wsel = P >> 1;
@@ -113,17 +285,15 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
 #pragma unroll
                 for (u32 w = 0; w < 8; w++) {
                     const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
-                    const u32 mag = compact ? cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u)
-                                            : cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
+                    const u32 mag = cdtl(u);
                     const u32 j = 8 * h + w;
                     const u32 sign = (sbits >> j) & 1u;
                     const int sv = sign ? -(int)mag : (int)mag;                // -0 == 0: no test of mag needed
                     if (P < K) {
-                        // swz(i) = i ^ ((i >> 4) & 15) with i = (P << LOGN) + 16 tau + j only touches j
-                        S[(P << LOGN) + 16u * tau + (j ^ (tau & 15u))] =
+                        S[swz((P << LOGN) + tau + CH * j)] =
                             POL == POL_F64 ? as_u((double)sv) : signed_residue(mag, sign, mp.q);
                     } else {
-                        E[((P - K) << LOGN) + 16u * tau + j] = (signed char)sv;
+                        E[((P - K) << LOGN) + tau + CH * j] = (signed char)sv;
                     }
                 }
             }
@@ -166,8 +336,6 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     // ---- phase 4+5: rows of A*s back to coefficients; the last inverse pass (coalesced
     // thread -> coefficient map) adds e (and Delta*m on the last row) in registers and
     // stores the LweCommitment container straight to HBM
-    u64* o = fp.out + b * (1 + (size_t)K * n);
-    if (threadIdx.x == 0) o[0] = (u64)K * n * 8;
     if (!(fp.skip & 8u)) {
         const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used};
         tile_inverse_to_global<LOGN, LOGN, POL>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);

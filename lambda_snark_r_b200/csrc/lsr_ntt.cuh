@@ -292,7 +292,12 @@ struct TileIo {
 };
 
 // Epilogue hook for the pass that stores to global memory: value = epi(tile index, value).
+// kWholeItem = true: the hook takes the whole work item instead -- item(g, W, base, v) stores the 2^R coefficients
+// base + (j << LG) itself (the fused commitment samples its error terms right there, in registers).
+// pre(W) runs before the coefficients of the work item are loaded (few live registers) and hands its result to item().
 struct NoEpilogue {
+    static constexpr bool kWholeItem = false;
+    struct Pre {};
     __device__ __forceinline__ u64 operator()(u32, u64 v) const { return v; }
 };
 
@@ -322,6 +327,8 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         const u32 base = (poly << LT) + (blk << (LG + R)) + c;
         const u32 T0 = LL ? ((tb << (LT - R)) + w) : ((1u << (d + SL)) + (tb << SL) + blk);
         const bool live = (IN == IO_GLOBAL || OUT == IO_GLOBAL) ? ((poly << LT) < io.valid) : true;
+        typename Epi::Pre pre;
+        if constexpr (OUT == IO_GLOBAL && Epi::kWholeItem) pre = epi.pre(W);
         u64 v[1 << R];
         if constexpr (IN == IO_GLOBAL && LG == 0 && R >= 1) {
             // unit-stride pass: each thread owns 2^R consecutive coefficients -> 16-byte accesses
@@ -379,7 +386,9 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
                 for (int j = 0; j < (1 << R); j += 2) __stcs(gp + (j >> 1), make_ulonglong2(v[j], v[j + 1]));
             }
         } else if constexpr (OUT == IO_GLOBAL) {
-            if (live) {
+            if constexpr (Epi::kWholeItem) {
+                if (live) epi.item(io.g, W, base, v, pre);
+            } else if (live) {
 #pragma unroll
                 for (int j = 0; j < (1 << R); j++) {
                     const u32 idx = base + ((u32)j << LG);
@@ -442,12 +451,13 @@ __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, con
 // shared-memory-only forms (fused commitment kernel).  Values in shared memory are in the
 // policy's working representation.  POL_F64 forward leaves the evaluations unreduced (bounded by
 // (b + 0.75 logn) q for inputs bounded by b q): the consumer multiplies them, which reduces.
-template <int LOGN, int LT, int POL>
+// I0 = first pass to run (the fused commitment kernel does pass 0 itself, on freshly sampled registers)
+template <int LOGN, int LT, int POL, bool PAD = false, int I0 = 0>
 __device__ __forceinline__ void tile_forward(u64* sm, const NttTables& t, const ModParams& mp,
                                              u32 tile_elems, u32 tb) {
     static_assert(LOGN == LT, "whole polynomials only");
     const TileIo io{nullptr, tile_elems, 0u, 0ull};
-    tile_forward_from<LT, true, POL, false, 0, POL != POL_F64>(sm, io, t, mp, tile_elems, tb, 0u);
+    tile_forward_from<LT, true, POL, false, I0, POL != POL_F64, PAD>(sm, io, t, mp, tile_elems, tb, 0u);
 }
 template <int LOGN, int LT, int POL>
 __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const ModParams& mp,
@@ -459,13 +469,13 @@ __device__ __forceinline__ void tile_inverse(u64* sm, const NttTables& t, const 
 
 // shared memory in, last pass straight to global memory through an epilogue
 // (fused commitment kernel: + e, + Delta*m, container store); needs a multi-pass plan
-template <int LOGN, int LT, int POL, typename Epi>
+template <int LOGN, int LT, int POL, typename Epi, bool PAD = false>
 __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const NttTables& t, const ModParams& mp,
                                                        u32 tile_elems, const Epi& epi) {
     static_assert(plan<LT>::N > 1, "single-pass plans read from global memory");
     static_assert(LOGN == LT, "whole polynomials only");
     const TileIo io{g, tile_elems, 0u, 0ull};
-    tile_inverse_from<LT, true, POL, true, plan<LT>::N - 1, Epi>(sm, io, t, mp, tile_elems, 0u, 0u, epi);
+    tile_inverse_from<LT, true, POL, true, plan<LT>::N - 1, Epi, PAD>(sm, io, t, mp, tile_elems, 0u, 0u, epi);
 }
 
 // ---------------------------------------------------------------------------

@@ -586,7 +586,8 @@ const uint64_t *lsro_lwe_trapdoor(const lsro_lwe *c) { return c->zh; }
 
 /*
  * Commitment randomness layout.  Coefficient c of
- * polynomial P (P<k: s_P, P>=k: e_{P-k}) lives in chunk tau = c>>4, lane j=c&15:
+ * polynomial P (P<k: s_P, P>=k: e_{P-k}) lives in chunk tau = c mod (n/16), lane j = c div (n/16)
+ * (a chunk is the 16 coefficients tau + (n/16) j that one thread of the radix-16 first / last NTT pass owns):
  *   u1   = 64-bit word (j&7) of block b = 2P + (j>>3)
  *   sign = bit (16P + j) of block b = 4k
  * block(b) = ChaCha(key, w12=seed_lo, w13=seed_hi, w14=tau, w15=DOM_COMMIT|b).
@@ -618,8 +619,8 @@ void lsro_lwe_sample_se(const lsro_lwe *c, uint64_t seed, int64_t *s, int64_t *e
         sample_chunk(c, seed, tau, buf);
         for (uint32_t P = 0; P < k; P++) {
             for (uint32_t j = 0; j < 16; j++) {
-                s[(size_t)P * n + 16 * tau + j] = buf[P * 16 + j];
-                e[(size_t)P * n + 16 * tau + j] = buf[(k + P) * 16 + j];
+                s[(size_t)P * n + tau + (size_t)(n / 16) * j] = buf[P * 16 + j];
+                e[(size_t)P * n + tau + (size_t)(n / 16) * j] = buf[(k + P) * 16 + j];
             }
         }
     }
