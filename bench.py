@@ -498,7 +498,7 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(B, "hbm-resident"),
         "roofline": {
-            "kernel": "fused_commit_kernel<12,2,5,%s>" % ("POL_F64" if arith == "fp64" else "POL_LAZY"), "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
+            "kernel": "fused_commit_kernel<12,2,0,%s>" % ("POL_F64" if arith == "fp64" else "POL_LAZY"), "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
             "unit": "GB/s", "frac": commit_gbs / hbm_peak, "peak_source": hbm_src,
             "traffic": (tr.get("fused_commit_bytes_per_commitment") or 0) * B or None,
             "algorithmic_bytes_per_commitment": ALG_BYTES_COMMIT,

@@ -96,15 +96,17 @@ struct CommitEpilogue {
 };
 
 // one CDT sample from a 64-bit uniform word; all 32 lanes of the warp call together
+// NCH8 = 0: the compact search (tables with at most 31 distinct values; the host picks the instantiation, so only one
+// search is compiled into a kernel -- the fused kernel is 150 KB of code and its three resident CTAs are rarely in the
+// same phase); NCH8 = 5, 8: binary search over 31 entries + tail scan.
 template <int NCH8>
 struct CdtLanes {
     const CdtParam& cdt;
-    bool compact;
     u64 lane_entry;
     u32 lane_cum;
     __device__ __forceinline__ u32 operator()(u64 u) const {
-        return compact ? cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u)
-                       : cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
+        if constexpr (NCH8 == 0) return cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u);
+        else return cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
     }
 };
 
@@ -115,17 +117,20 @@ template <int NCH8>
 __device__ __forceinline__ void sample_chunk_packed(const ChaChaKey& key, u32 s_lo, u32 s_hi, u32 tau, u32 P, u32 sbits,
                                                     const CdtLanes<NCH8>& cdtl, u32 (&pk)[4]) {
     pk[0] = pk[1] = pk[2] = pk[3] = 0u;
-#pragma unroll
-    for (u32 h = 0; h < 2; h++) {
+#pragma unroll 1
+    for (u32 h = 0; h < 2; h++) {                 // one copy of the block + searches in the code, run twice
         u32 x[16];
         chacha_block(key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
+        const u32 sb = sbits >> (8u * h);
+        u32 a = 0u, b = 0u;
 #pragma unroll
         for (u32 w = 0; w < 8; w++) {
-            const u32 j = 8 * h + w;
             const u32 mag = cdtl((u64)x[2 * w] | ((u64)x[2 * w + 1] << 32));
-            const int sv = ((sbits >> j) & 1u) ? -(int)mag : (int)mag;        // -0 == 0: no test of mag needed
-            pk[j >> 2] |= ((u32)sv & 0xffu) << (8u * (j & 3u));
+            const int sv = ((sb >> w) & 1u) ? -(int)mag : (int)mag;           // -0 == 0: no test of mag needed
+            const u32 byte = ((u32)sv & 0xffu) << (8u * (w & 3u));
+            if (w < 4) a |= byte; else b |= byte;
         }
+        if (h == 0) { pk[0] = a; pk[1] = b; } else { pk[2] = a; pk[3] = b; }
     }
 }
 __device__ __forceinline__ int unpack_s8(const u32 (&pk)[4], u32 j) {
@@ -178,10 +183,9 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const size_t b = blockIdx.x;
     const u64 seed = fp.seeds[b];
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
-    const bool compact = cdt.compact != 0;                           // a property of the table, uniform over the grid
-    const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
-                                   : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
-    const CdtLanes<NCH8> cdtl{cdt, compact, lane_entry, cdt.dcum[threadIdx.x & 31u]};
+    const u64 lane_entry = NCH8 == 0 ? cdt.dval[threadIdx.x & 31u]
+                                     : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
+    const CdtLanes<NCH8> cdtl{cdt, lane_entry, cdt.dcum[threadIdx.x & 31u]};
 
     // the message is consumed by the last pass only: pull it towards L2 now (one 128-byte line per thread)
     // so that the epilogue's loads do not wait on HBM
@@ -474,6 +478,7 @@ static bool launch_fused_pol(const FusedParams& fp, const CdtParam& cdt, size_t 
         kernel<<<(unsigned)count, kNttThreads, smem, s>>>(fp, cdt);
         return cuda_ok(cudaGetLastError(), "fused_commit_kernel launch");
     };
+    if (cdt.compact) return run(fused_commit_kernel<LOGN, K, 0, POL>);
     if (nch8 <= 5) return run(fused_commit_kernel<LOGN, K, 5, POL>);
     return run(fused_commit_kernel<LOGN, K, 8, POL>);
 }
