@@ -4,7 +4,7 @@ from pathlib import Path
 import numpy as np
 import torch
 ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT))
 from lambda_snark_r_b200 import api, capi
 import ctypes as C
 
@@ -31,9 +31,13 @@ for count in (32, 1024, 16384):
           f"{2 * count * words * 8 / ms / 1e6:.1f} GB/s hashed")
 # whole proofs, m = 4096
 import random
-from test_oracle_quotient import mult_gates
 m = 4096
-cols, A, B, Cm, z = mult_gates(m, P, random.Random(1))
+rng = random.Random(1)
+cols, z, A, B, Cm = 3 * m + 1, [1] + [0] * (3 * m), [], [], []
+for i in range(m):                      # gates z[3i+1] * z[3i+2] = z[3i+3]
+    a, b = rng.randrange(P), rng.randrange(P)
+    z[3 * i + 1], z[3 * i + 2], z[3 * i + 3] = a, b, (a * b) % P
+    A.append((i, 3 * i + 1, 1)); B.append((i, 3 * i + 2, 1)); Cm.append((i, 3 * i + 3, 1))
 r = api.R1CS(m, cols, A, B, Cm, P)
 ctx = api.LweContext(api.Params(n=4096, k=2, q=Q0, sigma=3.19), seed32=bytes(range(32)))
 for count in (64, 1024):

@@ -5,7 +5,7 @@ from pathlib import Path
 import numpy as np
 import torch
 ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT))
 from lambda_snark_r_b200 import api
 
 P = 2**64 - 2**32 + 1
