@@ -228,6 +228,12 @@ int         lsr_set_device(int device) LSR_NOEXCEPT;   /* device new contexts bi
 const char* lsr_version(void) LSR_NOEXCEPT;
 const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnostic string */
 
+/* Page-locked host buffers for the batched host-pointer entry points.  They accept any host memory, but ordinary
+ * (pageable) memory is staged by the driver at ~10 GB/s, 5x below PCIe 5 x16: lwe_commit_batch runs at 0.10 M
+ * commitments/s from pageable buffers and 0.79 M/s from these (tools/latency.py, bench.py e2e).  NULL on failure.    */
+void* lsr_host_alloc(size_t bytes) LSR_NOEXCEPT;
+void  lsr_host_free(void* p) LSR_NOEXCEPT;
+
 /* Integer-multiply roofline denominator: dependency-free mad.wide.u32 (wide=1)
  * or mad.lo.u32 (wide=0) on every SM, timed with CUDA events; result in
  * 10^9 IMAD per second.  sm_mhz_effective (optional) = the SM clock implied by

@@ -120,6 +120,8 @@ SIGNATURES = {
                                       u64p, u64p, u64p, u64p, C.POINTER(C.c_int)]),
     "lsr_verify_r1cs_batch": (C.c_int, [C.c_uint64, C.c_uint64, u64p, C.c_size_t, u64p, C.c_size_t, u64p, u64p, C.c_size_t,
                                        C.POINTER(C.c_int)]),
+    "lsr_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "lsr_host_free": (None, [C.c_void_p]),
     "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
     "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),

@@ -277,6 +277,18 @@ int lsr_verify_r1cs_batch(uint64_t n_constraints, uint64_t modulus, const uint64
     LSR_CATCH(-1)
 }
 
+void* lsr_host_alloc(size_t bytes) LSR_NOEXCEPT {
+    LSR_TRY
+    void* p = nullptr;
+    if (bytes == 0 || !lsr::cuda_ok(cudaHostAlloc(&p, bytes, cudaHostAllocPortable), "cudaHostAlloc")) return nullptr;
+    return p;
+    LSR_CATCH(nullptr)
+}
+
+void lsr_host_free(void* p) LSR_NOEXCEPT {
+    if (p) cudaFreeHost(p);
+}
+
 int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,
                             size_t total) LSR_NOEXCEPT {
     LSR_TRY

@@ -351,3 +351,25 @@ def test_cdt_search_variants_on_boundaries(gpu, rng):
                                               out.ctypes.data_as(C.POINTER(C.c_uint32)), variant)
             assert rc == 0, (sigma, variant)
             assert np.array_equal(out, want), (sigma, variant, np.nonzero(out != want)[0][:5])
+
+
+def test_page_locked_host_buffers(gpu, rng):
+    """lsr_host_alloc / lsr_host_free: the batched entry point gives the same containers from page-locked buffers."""
+    lib = capi.load()
+    ctx = api.LweContext(api.Params(n=4096, k=2, q=Q0, sigma=3.19), seed32=SEED32)
+    count, n, words = 5, 4096, ctx.words
+    msgs = rng.integers(0, Q0, size=(count, n), dtype=np.uint64)
+    seeds = np.arange(11, 11 + count, dtype=np.uint64)
+    want = ctx.commit_batch(msgs, seeds)
+    pm, ps, po = (lib.lsr_host_alloc(b) for b in (msgs.nbytes, seeds.nbytes, count * words * 8))
+    assert pm and ps and po
+    C.memmove(pm, msgs.ctypes.data, msgs.nbytes)
+    C.memmove(ps, seeds.ctypes.data, seeds.nbytes)
+    ctx.commit_batch_ptr(pm, n, ps, count, po)
+    got = np.ctypeslib.as_array(C.cast(po, capi.u64p), shape=(count, words)).copy()
+    assert np.array_equal(got, want)
+    for p in (pm, ps, po):
+        lib.lsr_host_free(p)
+    lib.lsr_host_free(None)
+    assert lib.lsr_host_alloc(0) is None
+    ctx.close()
