@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "lsr_arith.cuh"
+#include "lsr_copy_pool.h"
 #include "lsr_engine.h"
 #include "lsr_sampler.cuh"
 
@@ -277,6 +278,7 @@ void lwe_destroy(LweContext* c) {
     if (c->d_A2f) cudaFree(c->d_A2f);
     if (c->d_cdf) cudaFree(c->d_cdf);
     for (auto& s : c->scratch) s.release();
+    for (auto& s : c->staging) s.release();
     ntt_destroy(c->ntt);
     volatile uint32_t* kp = c->key;
     for (int i = 0; i < 8; i++) kp[i] = 0;
@@ -327,11 +329,64 @@ bool lwe_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, c
 // H2D (messages + seeds) -> kernel(s) -> D2H (containers) in order, so the D2H
 // copy engine -- the bound: 64 KiB out per commitment -- never idles.  The
 // generic path shares one S scratch buffer and therefore stays on one stream.
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Pageable caller memory, fused path, batches of at least one chunk: three slots of page-locked staging, the copy pool
+// moves chunk i in and chunk i-3 out while the GPU works on the chunks in between (the calling thread orchestrates and
+// copies too).  ~4x the driver's own pageable staging.
+static bool lwe_commit_host_staged(const LweContext* c, const u64* msgs, size_t msg_len, const u64* seeds,
+                                   size_t count, u64* out) {
+    constexpr int NB = 3;
+    const size_t words = lwe_words(c);
+    const size_t chunk = count >= 1024 ? 256 : 64;
+    const size_t in_words = chunk * (msg_len + 1);                         // messages, then the seeds
+    for (int b = 0; b < NB; b++) {
+        if (!c->staging[2 * b].reserve(in_words * sizeof(u64))) return false;
+        if (!c->staging[2 * b + 1].reserve(chunk * words * sizeof(u64))) return false;
+        if (!c->scratch[1 + 3 * b].reserve(in_words * sizeof(u64))) return false;
+        if (!c->scratch[3 + 3 * b].reserve(chunk * words * sizeof(u64))) return false;
+    }
+    cudaStream_t streams[NB] = {c->ntt->copy_streams[0], c->ntt->copy_streams[1], c->ntt->stream};
+    CopyPool& pool = CopyPool::get();
+    const size_t nchunks = (count + chunk - 1) / chunk;
+    bool ok = true;
+    for (size_t i = 0; ok && i < nchunks + NB; i++) {
+        const int b = (int)(i % NB);
+        cudaStream_t s = streams[b];
+        u64* pin_in = static_cast<u64*>(c->staging[2 * b].ptr);
+        u64* pin_out = static_cast<u64*>(c->staging[2 * b + 1].ptr);
+        if (i >= NB) {                                                     // retire chunk i - NB from this slot
+            const size_t j = i - NB, done = j * chunk, cnt = std::min(chunk, count - done);
+            ok = cuda_ok(cudaStreamSynchronize(s), "sync");
+            if (ok) pool.copy(out + done * words, pin_out, cnt * words * sizeof(u64));
+        }
+        if (ok && i < nchunks) {
+            const size_t done = i * chunk, cnt = std::min(chunk, count - done);
+            u64* din = static_cast<u64*>(c->scratch[1 + 3 * b].ptr);
+            u64* dout = static_cast<u64*>(c->scratch[3 + 3 * b].ptr);
+            if (msg_len) pool.copy(pin_in, msgs + done * msg_len, cnt * msg_len * sizeof(u64));
+            std::memcpy(pin_in + cnt * msg_len, seeds + done, cnt * sizeof(u64));
+            ok = cuda_ok(cudaMemcpyAsync(din, pin_in, cnt * (msg_len + 1) * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D") &&
+                 lwe_commit_launch(c, din, msg_len, din + cnt * msg_len, cnt, dout, s) &&
+                 cuda_ok(cudaMemcpyAsync(pin_out, dout, cnt * words * sizeof(u64), cudaMemcpyDeviceToHost, s), "D2H");
+        }
+    }
+    for (int b = 0; b < NB; b++) ok = cuda_ok(cudaStreamSynchronize(streams[b]), "sync") && ok;
+    return ok;
+}
+
 bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const u64* seeds,
                      size_t count, u64* out) {
     if (count == 0) return true;
     std::lock_guard<std::mutex> lock(c->mu);
     if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    if (count >= 128 && fused_commit_supported(c) && c->commit_path != 1 && (is_pageable(out) || is_pageable(msgs)))
+        return lwe_commit_host_staged(c, msgs, msg_len, seeds, count, out);
     const size_t words = lwe_words(c);
     const size_t eff_len = std::max<size_t>(msg_len, 1);
     const size_t chunk = std::min<size_t>(count, 256);

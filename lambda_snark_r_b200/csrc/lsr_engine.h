@@ -83,6 +83,7 @@ struct LweContext {
     int commit_path = 0;              // 0 auto, 1 generic, 2 fused
     mutable std::mutex mu;
     mutable lsr::DeviceScratch scratch[10];
+    mutable lsr::PinnedScratch staging[6];   // pageable callers: 3 slots x (messages + seeds | containers)
 };
 
 namespace lsr {

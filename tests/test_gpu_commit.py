@@ -373,3 +373,16 @@ def test_page_locked_host_buffers(gpu, rng):
     lib.lsr_host_free(None)
     assert lib.lsr_host_alloc(0) is None
     ctx.close()
+
+
+def test_pageable_batches_take_the_staged_path_and_agree(gpu, rng):
+    """count >= 128 from ordinary (pageable) numpy memory goes through the page-locked staging pipeline and the copy
+    pool; the containers equal those of small (unstaged) calls, including a ragged last chunk and short messages."""
+    ctx = api.LweContext(api.Params(n=4096, k=2, q=Q0, sigma=3.19), seed32=SEED32)
+    for count, msg_len in ((1100, 4096), (513, 7), (130, 4096)):
+        msgs = rng.integers(0, Q0, size=(count, msg_len), dtype=np.uint64)
+        seeds = np.arange(1, count + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        big = ctx.commit_batch(msgs, seeds)
+        parts = [ctx.commit_batch(msgs[a:a + 100], seeds[a:a + 100]) for a in range(0, count, 100)]     # unstaged calls
+        assert np.array_equal(big, np.concatenate(parts))
+    ctx.close()

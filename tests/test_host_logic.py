@@ -230,3 +230,13 @@ def test_transcript_hash_source_matches_sha3_256(tmp_path):
             h = hashlib.sha3_256(b"LAMBDA-SNARK-R-FS-v1" + struct.pack("<Q", n_pub) + pub.tobytes() +
                                  struct.pack("<Q", n_words) + words.tobytes())
             assert out.tobytes() == h.digest(), (n_pub, n_words)
+
+
+def test_copy_pool_stress(tmp_path):
+    """csrc/lsr_copy_pool.h: parallel memcpy used by the staged pageable path of lwe_commit_batch."""
+    import subprocess
+    exe = tmp_path / "copy_pool_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", str(ROOT / "lambda_snark_r_b200" / "csrc"), "-o", str(exe),
+                    str(ROOT / "tests" / "cabi" / "copy_pool_test.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "copy pool ok" in r.stderr, r.stderr
