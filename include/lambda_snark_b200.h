@@ -389,6 +389,21 @@ int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, siz
                                 const uint64_t* d_seeds, size_t count, uint64_t* d_out_words,
                                 void* stream) LSR_NOEXCEPT;
 
+/* Explicit mode: t = A*s + e + Delta*m for CALLER-SUPPLIED s, e instead of
+ * sampled ones -- the parity entry (any s, e can be put through the kernels and compared with the
+ * oracle) and the way to commit under externally generated randomness.  s, e: [count][k][n]
+ * two's-complement words, any int64 (reduced mod q); messages / out_words as lwe_commit_batch.
+ * Runs the un-fused kernels (transforms, mat-vec, finalize); lsr_lwe_sample_se(seed) fed back
+ * through it reproduces lwe_commit(seed) bit for bit.  HOST memory.          */
+int lsr_lwe_commit_explicit(LweContext* ctx, const uint64_t* messages, size_t msg_len,
+                            const int64_t* s, const int64_t* e, size_t count,
+                            uint64_t* out_words) LSR_NOEXCEPT;
+
+/* same, DEVICE memory; asynchronous on `stream` */
+int lsr_lwe_commit_explicit_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len,
+                                   const int64_t* d_s, const int64_t* d_e, size_t count,
+                                   uint64_t* d_out_words, void* stream) LSR_NOEXCEPT;
+
 /* results[i] in {1, 0, -1} as lwe_verify_opening; commitments: [count][1+k*n]
  * container words, messages: [count][msg_len].  HOST memory.                */
 int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words,

@@ -394,6 +394,20 @@ class LweContext:
             raise LambdaSnarkError("lsr_lwe_sample_se failed")
         return s, e
 
+    def commit_explicit(self, messages, s, e) -> np.ndarray:
+        """Explicit mode: containers of t = A*s + e + Delta*m for caller-supplied s, e.
+        messages [count][msg_len], s / e [count][k][n] int64 -> [count][words]."""
+        m = _u64(messages)
+        count, msg_len = m.shape
+        s = np.ascontiguousarray(s, dtype=np.int64).reshape(count, self.k, self.n)
+        e = np.ascontiguousarray(e, dtype=np.int64).reshape(count, self.k, self.n)
+        out = np.zeros((count, self.words), dtype=np.uint64)
+        rc = _lib().lsr_lwe_commit_explicit(self._h, _p(m) if m.size else None, msg_len, s.ctypes.data_as(capi.i64p),
+                                            e.ctypes.data_as(capi.i64p), count, _p(out))
+        if rc != 0:
+            raise LambdaSnarkError(f"lsr_lwe_commit_explicit failed: {last_error()}")
+        return out
+
     # batched extension: messages [count][msg_len], seeds [count] -> containers [count][words]
     def commit_batch(self, messages, seeds, out: np.ndarray | None = None) -> np.ndarray:
         m = _u64(messages)

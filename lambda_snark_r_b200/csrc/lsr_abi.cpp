@@ -430,6 +430,24 @@ int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, siz
     LSR_CATCH(-1)
 }
 
+int lsr_lwe_commit_explicit(LweContext* ctx, const uint64_t* messages, size_t msg_len, const int64_t* s,
+                            const int64_t* e, size_t count, uint64_t* out_words) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !s || !e || !out_words || (!messages && msg_len)) return -1;
+    return lsr::lwe_commit_explicit_host(ctx, reinterpret_cast<const u64*>(messages), msg_len, s, e, count,
+                                         reinterpret_cast<u64*>(out_words)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_lwe_commit_explicit_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len, const int64_t* d_s,
+                                   const int64_t* d_e, size_t count, uint64_t* d_out_words, void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d_s || !d_e || !d_out_words || (!d_messages && msg_len)) return -1;
+    return lsr::lwe_commit_explicit_launch(ctx, reinterpret_cast<const u64*>(d_messages), msg_len, d_s, d_e, count,
+                                           reinterpret_cast<u64*>(d_out_words), static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
 void lwe_commitment_free(LweCommitment* comm) LSR_NOEXCEPT {
     if (!comm) return;                                    // commitment.cpp:167
     if (comm->data) {

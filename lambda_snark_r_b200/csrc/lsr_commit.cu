@@ -68,6 +68,23 @@ sample_se_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, u6
     }
 }
 
+// explicit mode: caller-supplied s, e (two's complement, any int64) -> residues;
+// s -> S[b][P][n], e -> out payload, exactly where sample_se_kernel leaves its samples
+__global__ void __launch_bounds__(256)
+load_se_kernel(u64 q, size_t kn, const long long* __restrict__ s, const long long* __restrict__ e, size_t count,
+               u64* __restrict__ S, u64* __restrict__ out, size_t out_stride) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count * kn) return;
+    const size_t b = idx / kn, r = idx % kn;
+    auto residue = [q](long long v) -> u64 {
+        const u64 mag = v < 0 ? 0ull - (u64)v : (u64)v;
+        const u64 m = mag % q;
+        return (v < 0 && m) ? q - m : m;
+    };
+    S[idx] = residue(s[idx]);
+    out[b * out_stride + 1 + r] = residue(e[idx]);
+}
+
 // S[b][.][x] <- A[.][.][x] * S[b][.][x]   (NTT-domain mat-vec, in place)
 template <int KMAX>
 __global__ void __launch_bounds__(256)
@@ -287,7 +304,8 @@ void lwe_destroy(LweContext* c) {
 
 // ------------------------------------------------------------------- generic
 static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
-                                  const u64* d_seeds, size_t count, u64* d_out, cudaStream_t s) {
+                                  const u64* d_seeds, size_t count, u64* d_out, cudaStream_t s,
+                                  const long long* d_s = nullptr, const long long* d_e = nullptr) {
     const uint32_t n = c->n, k = c->k;
     const size_t words = lwe_words(c);
     const size_t L = std::min<size_t>(msg_len, n);
@@ -300,9 +318,15 @@ static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t
     for (size_t done = 0; done < count; done += chunk) {
         const size_t cnt = std::min(chunk, count - done);
         u64* out = d_out + done * words;
-        sample_se_kernel<<<grid_for(cnt * (n >> 4), 128), 128, 0, s>>>(key, c->d_cdf, (u32)c->cdf.size(), c->q, n, k,
-                                                                      d_seeds + done, cnt, S, out, words);
-        if (!cuda_ok(cudaGetLastError(), "sample_se_kernel")) return false;
+        if (d_s) {
+            load_se_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->q, (size_t)k * n, d_s + done * k * n, d_e + done * k * n,
+                                                                     cnt, S, out, words);
+            if (!cuda_ok(cudaGetLastError(), "load_se_kernel")) return false;
+        } else {
+            sample_se_kernel<<<grid_for(cnt * (n >> 4), 128), 128, 0, s>>>(key, c->d_cdf, (u32)c->cdf.size(), c->q, n, k,
+                                                                          d_seeds + done, cnt, S, out, words);
+            if (!cuda_ok(cudaGetLastError(), "sample_se_kernel")) return false;
+        }
         if (!ntt_forward_launch(c->ntt, S, cnt * k, s)) return false;
         matvec_kernel<16><<<grid_for(cnt * n, 256), 256, 0, s>>>(c->ntt->mp, c->d_A, n, k, cnt, S);
         if (!cuda_ok(cudaGetLastError(), "matvec_kernel")) return false;
@@ -314,6 +338,44 @@ static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t
         (void)L;
     }
     return true;
+}
+
+// explicit mode: s, e supplied by the caller (device pointers, [count][k][n] two's complement)
+bool lwe_commit_explicit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const int64_t* d_s,
+                                const int64_t* d_e, size_t count, u64* d_out, cudaStream_t stream) {
+    if (count == 0) return true;
+    return generic_commit_launch(c, d_msgs, msg_len, nullptr, count, d_out, stream,
+                                 reinterpret_cast<const long long*>(d_s), reinterpret_cast<const long long*>(d_e));
+}
+
+// explicit mode from host memory: a parity / measurement entry, so plain synchronous staging per chunk
+bool lwe_commit_explicit_host(const LweContext* c, const u64* msgs, size_t msg_len, const int64_t* s_in,
+                              const int64_t* e_in, size_t count, u64* out) {
+    if (count == 0) return true;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
+    const size_t words = lwe_words(c), kn = (size_t)c->k * c->n;
+    const size_t chunk = std::min<size_t>(count, 64);
+    cudaStream_t st = c->ntt->stream;
+    if (!c->scratch[1].reserve(chunk * std::max<size_t>(msg_len, 1) * sizeof(u64))) return false;
+    if (!c->scratch[2].reserve(chunk * kn * 2 * sizeof(int64_t))) return false;
+    if (!c->scratch[3].reserve(chunk * words * sizeof(u64))) return false;
+    u64* dm = static_cast<u64*>(c->scratch[1].ptr);
+    int64_t* ds = static_cast<int64_t*>(c->scratch[2].ptr);
+    int64_t* de = ds + chunk * kn;
+    u64* dout = static_cast<u64*>(c->scratch[3].ptr);
+    bool ok = true;
+    for (size_t done = 0; ok && done < count; done += chunk) {
+        const size_t cnt = std::min(chunk, count - done);
+        if (msg_len) ok = cuda_ok(cudaMemcpyAsync(dm, msgs + done * msg_len, cnt * msg_len * sizeof(u64), cudaMemcpyHostToDevice, st), "H2D msgs");
+        ok = ok && cuda_ok(cudaMemcpyAsync(ds, s_in + done * kn, cnt * kn * sizeof(int64_t), cudaMemcpyHostToDevice, st), "H2D s") &&
+             cuda_ok(cudaMemcpyAsync(de, e_in + done * kn, cnt * kn * sizeof(int64_t), cudaMemcpyHostToDevice, st), "H2D e") &&
+             generic_commit_launch(c, dm, msg_len, nullptr, cnt, dout, st, reinterpret_cast<const long long*>(ds),
+                                   reinterpret_cast<const long long*>(de)) &&
+             cuda_ok(cudaMemcpyAsync(out + done * words, dout, cnt * words * sizeof(u64), cudaMemcpyDeviceToHost, st), "D2H") &&
+             cuda_ok(cudaStreamSynchronize(st), "sync");
+    }
+    return ok;
 }
 
 bool lwe_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const u64* d_seeds,

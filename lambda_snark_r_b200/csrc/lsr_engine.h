@@ -104,6 +104,10 @@ bool lwe_verify_host(const LweContext* ctx, const u64* comm_words, const u64* ms
 bool lwe_lincomb_host(const LweContext* ctx, const u64* payloads, const u64* coeffs, size_t count,
                       u64* out_payload);
 bool lwe_sample_se_host(const LweContext* ctx, u64 seed, int64_t* s, int64_t* e);
+bool lwe_commit_explicit_host(const LweContext* ctx, const u64* msgs, size_t msg_len, const int64_t* s, const int64_t* e,
+                              size_t count, u64* out);
+bool lwe_commit_explicit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const int64_t* d_s,
+                                const int64_t* d_e, size_t count, u64* d_out, cudaStream_t stream);
 bool sample_gaussian_host(u64* out, size_t len, double sigma, const uint8_t seed32[32]);
 bool fused_commit_supported(const LweContext* ctx);
 bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant);

@@ -626,14 +626,21 @@ void lsro_lwe_sample_se(const lsro_lwe *c, uint64_t seed, int64_t *s, int64_t *e
     }
 }
 
-static int commit_one(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
-                      uint64_t seed, uint64_t *out, int64_t *s, int64_t *e, uint64_t *sh,
-                      uint64_t *acc) {
+/* any int64 -> [0,q) (explicit mode takes caller-supplied values, not only CDT samples) */
+static inline uint64_t to_residue_any(int64_t v, uint64_t q) {
+    const uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+    const uint64_t r = mag % q;
+    return (v < 0 && r) ? q - r : r;
+}
+
+/* t = A*s + e + Delta*m for given s, e (the embedding of the message follows
+ * commitment.cpp:146-149: first min(len, n) slots, the rest zero) */
+static int commit_core(const lsro_lwe *c, const uint64_t *msg, size_t msg_len, uint64_t *out,
+                       const int64_t *s, const int64_t *e, uint64_t *sh, uint64_t *acc) {
     const uint32_t n = c->n, k = c->k;
     const uint64_t q = c->q;
-    lsro_lwe_sample_se(c, seed, s, e);
     for (uint32_t j = 0; j < k; j++) {
-        for (uint32_t x = 0; x < n; x++) sh[(size_t)j * n + x] = to_residue(s[(size_t)j * n + x], q);
+        for (uint32_t x = 0; x < n; x++) sh[(size_t)j * n + x] = to_residue_any(s[(size_t)j * n + x], q);
         fwd_one(c->ntt, sh + (size_t)j * n);
     }
     out[0] = (uint64_t)k * n * 8;
@@ -650,7 +657,7 @@ static int commit_one(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
         inv_one(c->ntt, acc);
         uint64_t *t = out + 1 + (size_t)i * n;
         for (uint32_t x = 0; x < n; x++) {
-            uint64_t v = acc[x] + to_residue(e[(size_t)i * n + x], q);
+            uint64_t v = acc[x] + to_residue_any(e[(size_t)i * n + x], q);
             if (v >= q) v -= q;
             if (i == k - 1 && x < L) {
                 v += lsro_mulmod(c->delta, msg[x] % c->p, q);
@@ -660,6 +667,24 @@ static int commit_one(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
         }
     }
     return 0;
+}
+
+static int commit_one(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
+                      uint64_t seed, uint64_t *out, int64_t *s, int64_t *e, uint64_t *sh,
+                      uint64_t *acc) {
+    lsro_lwe_sample_se(c, seed, s, e);
+    return commit_core(c, msg, msg_len, out, s, e, sh, acc);
+}
+
+int lsro_lwe_commit_explicit(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
+                             const int64_t *s, const int64_t *e, uint64_t *out_words) {
+    if (!c || (!msg && msg_len) || !s || !e || !out_words) return -1;
+    const size_t kn = (size_t)c->k * c->n;
+    uint64_t *sh = (uint64_t *)malloc(sizeof(uint64_t) * (kn + c->n));
+    if (!sh) return -1;
+    int rc = commit_core(c, msg, msg_len, out_words, s, e, sh, sh + kn);
+    free(sh);
+    return rc;
 }
 
 int lsro_lwe_commit(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,

@@ -99,6 +99,9 @@ void lsro_lwe_sample_se(const lsro_lwe *c, uint64_t seed, int64_t *s, int64_t *e
 /* out = [byte_len, t row-major]; message truncated to n (commitment.cpp:146-149) */
 int  lsro_lwe_commit(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
                      uint64_t seed, uint64_t *out_words);
+/* explicit mode: s, e supplied ([k][n] two's complement, any int64, reduced mod q) */
+int  lsro_lwe_commit_explicit(const lsro_lwe *c, const uint64_t *msg, size_t msg_len,
+                              const int64_t *s, const int64_t *e, uint64_t *out_words);
 int  lsro_lwe_commit_batch(const lsro_lwe *c, const uint64_t *msgs, size_t msg_len,
                            const uint64_t *seeds, size_t count, uint64_t *out_words,
                            int threads);

@@ -96,6 +96,8 @@ class _Lib:
         lib.lsro_lwe_sample_se.argtypes = [C.c_void_p, C.c_uint64, i64p, i64p]
         lib.lsro_lwe_commit.restype = C.c_int
         lib.lsro_lwe_commit.argtypes = [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p]
+        lib.lsro_lwe_commit_explicit.restype = C.c_int
+        lib.lsro_lwe_commit_explicit.argtypes = [C.c_void_p, u64p, C.c_size_t, i64p, i64p, u64p]
         lib.lsro_lwe_commit_batch.restype = C.c_int
         lib.lsro_lwe_commit_batch.argtypes = [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, u64p, C.c_int]
         lib.lsro_lwe_verify.restype = C.c_int
@@ -278,6 +280,17 @@ class OracleLwe:
         out = np.zeros(self.words, dtype=np.uint64)
         mp = _ptr(m) if m.size else C.cast(C.c_void_p(1), u64p)   # non-NULL for empty msg
         rc = self._l.lsro_lwe_commit(self._h, mp, m.size, seed, _ptr(out))
+        assert rc == 0
+        return out
+
+    def commit_explicit(self, msg, s, e) -> np.ndarray:
+        """explicit mode: t = A*s + e + Delta*m for caller-supplied s, e ([k][n] int64)"""
+        m = _np_u64(msg)
+        s = np.ascontiguousarray(s, dtype=np.int64).reshape(self.k, self.n)
+        e = np.ascontiguousarray(e, dtype=np.int64).reshape(self.k, self.n)
+        out = np.zeros(self.words, dtype=np.uint64)
+        mp = _ptr(m) if m.size else C.cast(C.c_void_p(1), u64p)
+        rc = self._l.lsro_lwe_commit_explicit(self._h, mp, m.size, s.ctypes.data_as(i64p), e.ctypes.data_as(i64p), _ptr(out))
         assert rc == 0
         return out
 

@@ -173,6 +173,85 @@ def test_commit_matches_oracle_on_both_paths(gpu, rng, n, k, q):
     ctx.close()
 
 
+# ------------------------------------------------------------ explicit mode (s, e supplied)
+@pytest.mark.parametrize("n,k,q", [(4096, 2, Q0), (4096, 3, Q0), (1024, 2, Q0), (8192, 2, Q1), (64, 1, Q0),
+                                   (16384, 2, Q1), (4096, 2, Q60)])
+def test_explicit_mode_matches_oracle_and_the_seeded_paths(gpu, rng, n, k, q):
+    ctx = mk(n, k, q)
+    orc = O.OracleLwe(q, n, k, 3.19, SEED32)
+    count = 5
+    rq = ctx.q
+    msgs = rng.integers(0, 2**64, size=(count, n), dtype=np.uint64)
+    # 0: the sampled s, e of a seed (must reproduce the seeded commitment of every path)
+    # 1: uniform over the whole residue range, both signs; 2: extremes of int64 and of the residue range
+    # 3: all-zero (commitment = Delta * m);  4: s = -1, e = q - 1 everywhere
+    s = rng.integers(-(rq - 1), rq, size=(count, k, n), dtype=np.int64)
+    e = rng.integers(-(rq - 1), rq, size=(count, k, n), dtype=np.int64)
+    s[0], e[0] = orc.sample_se(0xC0FFEE)
+    ext = np.array([np.iinfo(np.int64).min, np.iinfo(np.int64).max, -rq, rq, rq - 1, 1 - rq, rq // 2, -(rq // 2) - 1],
+                   dtype=np.int64)
+    s[2] = np.resize(ext, (k, n))
+    e[2] = np.resize(ext[::-1], (k, n))
+    s[3], e[3] = 0, 0
+    s[4], e[4] = -1, rq - 1
+    want = np.stack([orc.commit_explicit(msgs[i], s[i], e[i]) for i in range(count)])
+    for arith in ((0, 1) if q < 2**45 else (0,)):
+        ctx.set_arith(arith)
+        got = ctx.commit_explicit(msgs, s, e)
+        assert np.array_equal(got, want), f"arith {arith}"
+        seeded = ctx.commit_batch(msgs[:1], np.array([0xC0FFEE], dtype=np.uint64))     # fused where supported
+        assert np.array_equal(seeded[0], got[0]), f"arith {arith}"
+    kn = k * n
+    assert not got[3, 1:1 + kn - n].any()
+    assert np.array_equal(got[3, 1 + kn - n:], (msgs[3] % np.uint64(ctx.p)) * np.uint64(ctx.delta))
+    ctx.close()
+
+
+def test_explicit_mode_linearity_and_ragged_messages(gpu, rng):
+    ctx = mk()
+    q = ctx.q
+    count = 70                                                                  # more than one staging chunk of 64
+    s = rng.integers(-50, 50, size=(2, count, 2, 4096), dtype=np.int64)
+    e = rng.integers(-50, 50, size=(2, count, 2, 4096), dtype=np.int64)
+    m = rng.integers(0, 1000, size=(2, count, 33), dtype=np.uint64)             # short messages: padded with zeros
+    a = ctx.commit_explicit(m[0], s[0], e[0])
+    b = ctx.commit_explicit(m[1], s[1], e[1])
+    both = ctx.commit_explicit(m[0] + m[1], s[0] + s[1], e[0] + e[1])
+    assert np.array_equal((a[:, 1:].astype(object) + b[:, 1:].astype(object)) % q, both[:, 1:].astype(object))
+    assert (both[:, 0] == 8 * 2 * 4096).all()
+    assert ctx.verify_batch(both, m[0] + m[1]).tolist() == [1] * count           # small s, e: still opens
+    long = rng.integers(0, 2**64, size=(3, 5000), dtype=np.uint64)              # longer than n: truncated
+    assert np.array_equal(ctx.commit_explicit(long, s[0][:3], e[0][:3]), ctx.commit_explicit(long[:, :4096], s[0][:3], e[0][:3]))
+    empty = np.zeros((2, 0), dtype=np.uint64)
+    assert np.array_equal(ctx.commit_explicit(empty, s[0][:2], e[0][:2]),
+                          ctx.commit_explicit(np.zeros((2, 1), dtype=np.uint64), s[0][:2], e[0][:2]))
+    lib = capi.load()
+    assert lib.lsr_lwe_commit_explicit(ctx.as_ptr(), None, 4, None, None, 1, None) == -1
+    ctx.close()
+
+
+def test_explicit_mode_device_pointers(gpu, rng):
+    import torch
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    count = 3
+    msgs = rng.integers(0, 2**64, size=(count, 4096), dtype=np.uint64)
+    s = rng.integers(-(Q0 - 1), Q0, size=(count, 2, 4096), dtype=np.int64)
+    e = rng.integers(-(Q0 - 1), Q0, size=(count, 2, 4096), dtype=np.int64)
+    dm, ds, de = (torch.from_numpy(x.view(np.int64)).cuda() for x in (msgs, s, e))
+    out = torch.zeros((count, ctx.words), dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream().cuda_stream
+    rc = capi.load().lsr_lwe_commit_explicit_device(ctx.as_ptr(), dm.data_ptr(), 4096, ds.data_ptr(), de.data_ptr(), count,
+                                                    out.data_ptr(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint64)
+    for i in range(count):
+        assert np.array_equal(got[i], orc.commit_explicit(msgs[i], s[i], e[i]))
+    ctx.close()
+
+
 @pytest.mark.parametrize("msg_len", [0, 1, 5, 4095, 4096, 4097, 5000])
 def test_ragged_messages_truncate_and_pad(gpu, rng, msg_len):
     ctx = mk()

@@ -152,3 +152,68 @@ def test_batch_equals_single_and_thread_count_is_irrelevant(ctx, rng):
     assert np.array_equal(one, many)
     for i in range(6):
         assert np.array_equal(one[i], ctx.commit(msgs[i], int(seeds[i])))
+
+
+# ------------------------------------------------------------ explicit mode (s, e supplied)
+def _schoolbook_negacyclic(a, b, q):
+    n = len(a)
+    out = [0] * n
+    for i, x in enumerate(a):
+        if x == 0:
+            continue
+        for j, y in enumerate(b):
+            t = i + j
+            if t < n:
+                out[t] = (out[t] + x * y) % q
+            else:
+                out[t - n] = (out[t - n] - x * y) % q
+    return out
+
+
+def test_explicit_mode_reproduces_the_seeded_commitment(ctx):
+    msg = np.arange(50, dtype=np.uint64) * 977
+    for seed in (1, 0xC0FFEE):
+        s, e = ctx.sample_se(seed)
+        assert np.array_equal(ctx.commit_explicit(msg, s, e), ctx.commit(msg, seed))
+
+
+def test_explicit_mode_is_A_s_plus_e_plus_delta_m_by_schoolbook_products():
+    # small ring so that the O(n^2) negacyclic product finishes; A is taken back to coefficients with the
+    # oracle's own inverse transform (pinned in test_oracle_pinning.py)
+    n, k = 64, 2
+    o = O.OracleLwe(Q0, n, k, 3.19, SEED32)
+    ntt = O.OracleNtt(o.q, n)
+    q = o.q
+    rng = np.random.Generator(np.random.PCG64(7))
+    s = rng.integers(-(q - 1), q, size=(k, n), dtype=np.int64)          # the whole residue range, both signs
+    e = rng.integers(-(q - 1), q, size=(k, n), dtype=np.int64)
+    s[0, 0], s[0, 1], e[1, 0], e[1, 1] = np.iinfo(np.int64).min, np.iinfo(np.int64).max, np.iinfo(np.int64).min, -q
+    msg = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    cm = o.commit_explicit(msg, s, e)
+    assert int(cm[0]) == 8 * k * n
+    A = [[[int(v) for v in ntt.inverse(o.matrix()[i, j])] for j in range(k)] for i in range(k)]
+    for i in range(k):
+        t = [int(v) % q for v in e[i]]
+        for j in range(k):
+            prod = _schoolbook_negacyclic(A[i][j], [int(v) % q for v in s[j]], q)
+            t = [(a + b) % q for a, b in zip(t, prod)]
+        if i == k - 1:
+            t = [(a + o.delta * (int(m) % o.p)) % q for a, m in zip(t, msg)]
+        assert [int(v) for v in cm[1 + i * n: 1 + (i + 1) * n]] == t
+
+
+def test_explicit_mode_is_linear_in_s_and_e(ctx, rng):
+    q = ctx.q
+    s1, e1 = ctx.sample_se(5)
+    s2 = rng.integers(-1000, 1000, size=s1.shape, dtype=np.int64)
+    e2 = rng.integers(-1000, 1000, size=s1.shape, dtype=np.int64)
+    m1 = rng.integers(0, 1000, size=4096, dtype=np.uint64)                # no wrap of the plaintext modulus
+    m2 = rng.integers(0, 1000, size=4096, dtype=np.uint64)
+    a = ctx.commit_explicit(m1, s1, e1)[1:].astype(object)
+    b = ctx.commit_explicit(m2, s2, e2)[1:].astype(object)
+    both = ctx.commit_explicit(m1 + m2, s1 + s2, e1 + e2)[1:].astype(object)
+    assert np.array_equal((a + b) % q, both)
+    zero = np.zeros_like(s1)
+    only_m = ctx.commit_explicit(m1, zero, zero)
+    assert not only_m[1:1 + 4096].any()
+    assert np.array_equal(only_m[1 + 4096:], (m1 % np.uint64(ctx.p)) * np.uint64(ctx.delta))
