@@ -43,9 +43,9 @@ SEED_BASE = 0xC0FFEE
 ALG_BYTES_COMMIT = 8 * N_RING + 8 * K_RANK * N_RING + 8          # message in + container out
 ALG_BYTES_NTT = 16 * N_RING                                       # read + write, in place
 # quotient pipeline, every stage touching its operands once (multiplication-gate R1CS: 3 non-zeros per constraint):
-# mat-vec 24 (witness) + 48 (CSR: 3 x (col 4 + val 8) + 3 row pointers) + 24 (evaluations out) = 96; 3 inverse + 3 forward
-# size-m transforms 16 each = 96; pointwise 24 in + 8 out = 32; inverse transform of Q 16
-QUOTIENT_BYTES_PER_CONSTRAINT = 96 + 96 + 32 + 16
+# mat-vec 24 (witness) + 48 (CSR: 3 x (col 4 + val 8) + 3 row pointers) + 24 (evaluations out) = 96; 3 inverse + 2 forward
+# + 1 inverse size-m transforms 16 each = 96; coset product 16 in + 8 out = 24; (C - N) / 2 on coefficients 16 in + 8 out = 24
+QUOTIENT_BYTES_PER_CONSTRAINT = 96 + 96 + 24 + 24
 BUTTERFLIES_NTT = (N_RING // 2) * 12
 IMAD_PER_MODMUL = 10                                              # SURVEY 8d normalisation
 MODMUL_COMMIT = 2 * K_RANK * BUTTERFLIES_NTT + K_RANK * (N_RING // 2) + K_RANK * K_RANK * N_RING   # 118784

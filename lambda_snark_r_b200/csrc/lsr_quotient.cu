@@ -17,10 +17,14 @@
 //                order (the order the inverse transform consumes); the same kernel checks
 //                a_i * b_i = c_i (is_satisfied, r1cs.rs:477-481  <=>  zero remainder, :1054-1060)
 //   -> inverse cyclic transform (size m, batch 3W)      coefficients of A_z, B_z, C_z
-//   -> forward negacyclic transform (size m, batch 3W)  values on psi * H (bit-reversed order)
-//   Q^[W][m]     (a * b - c) * (-2)^-1 pointwise
-//   -> inverse negacyclic transform (size m, batch W)   Q, natural order
-// 7 W transforms of size m and no zero padding, against 3 W of size m + 4 W of size 2m.
+//   -> forward negacyclic transform (size m, batch 2W)  values of A_z, B_z on psi * H (bit-reversed order)
+//   N^[W][m]     a * b pointwise
+//   -> inverse negacyclic transform (size m, batch W)   N = A_z * B_z mod (X^m + 1), natural order
+//   Q[W][m]      (C_z - N) / 2 pointwise on coefficients: the transforms are linear, so the coset values of C_z
+//                ((a * b - c) * (-2)^-1 on the coset) are never needed; equivalently, with
+//                A_z * B_z = P_lo + X^m * P_hi:  C_z = P_lo + P_hi (it agrees with the product on H),
+//                N = P_lo - P_hi, and Q = P_hi
+// 6 W transforms of size m and no zero padding, against 3 W of size m + 4 W of size 2m.
 #include <algorithm>
 #include <new>
 
@@ -145,13 +149,24 @@ spmv3_tiled_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, con
     }
 }
 
-// Q^ = (A * B - C) * h on the coset values (any order: pointwise), h = (-2)^-1 = (q - 1) / 2
+// N^ = A * B on the coset values (any order: pointwise).  C takes no part on the coset: the transforms are
+// linear, so its share of the quotient is subtracted in the coefficient domain (quotient_finish_kernel) and
+// its forward transform is never computed.
 __global__ void __launch_bounds__(256)
-coset_quotient_kernel(const ModParams mp, const u64* __restrict__ E, u64* __restrict__ Qh, size_t per_matrix, u64 h) {
+coset_product_kernel(const ModParams mp, const u64* __restrict__ E, u64* __restrict__ Nh, size_t per_matrix) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per_matrix) return;
-    const u64 num = field_sub(field_mul(E[idx], E[per_matrix + idx], mp), E[2 * per_matrix + idx], mp);
-    Qh[idx] = field_mul(num, h, mp);
+    Nh[idx] = field_mul(E[idx], E[per_matrix + idx], mp);
+}
+
+// Q = (C - N) / 2, in place over N.  N = A_z * B_z mod (X^m + 1) (the inverse negacyclic transform of N^),
+// C = A_z * B_z mod (X^m - 1) for a satisfied witness; with A_z * B_z = P_lo + X^m * P_hi that is
+// C - N = 2 * P_hi = 2 * Q.  For any witness it equals the inverse transform of (A * B - C) * (-2)^-1 on the coset.
+__global__ void __launch_bounds__(256)
+quotient_finish_kernel(const ModParams mp, const u64* __restrict__ C, u64* __restrict__ Q, size_t per_matrix, u64 inv2) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= per_matrix) return;
+    Q[idx] = field_mul(field_sub(C[idx], Q[idx], mp), inv2, mp);
 }
 
 // ------------------------------------------------------------------ host side
@@ -264,17 +279,21 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
         ok = cuda_ok(cudaGetLastError(), "spmv3_kernel");
     }
     if (ok && m >= 2) {
-        const u64 half = (h->q - 1) / 2;                       // (-2) * half = -(q - 1) = 1 (mod q)
+        const u64 inv2 = h->q / 2 + 1;                         // 2 * (q + 1) / 2 = q + 1 = 1 (mod q), q odd
         ok = ntt_inverse_launch(st->small, dE, 3 * W, s);
         if (ok && keep_coeffs)      // A_z, B_z, C_z as coefficient vectors [3][W][m] for the evaluations of prove_r1cs
             ok = st->coef.reserve(em * 8) &&
                  cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
-        ok = ok && ntt_forward_launch(st->coset, dE, 3 * W, s);
+        ok = ok && ntt_forward_launch(st->coset, dE, 2 * W, s);            // A_z, B_z only (C_z stays as coefficients)
         if (ok) {
-            coset_quotient_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m, half);
-            ok = cuda_ok(cudaGetLastError(), "coset_quotient_kernel");
+            coset_product_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m);
+            ok = cuda_ok(cudaGetLastError(), "coset_product_kernel");
         }
         ok = ok && ntt_inverse_launch(st->coset, dQ, W, s);
+        if (ok) {
+            quotient_finish_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE + 2 * W * (size_t)m, dQ, W * (size_t)m, inv2);
+            ok = cuda_ok(cudaGetLastError(), "quotient_finish_kernel");
+        }
     } else if (ok) {
         // m = 1: A_z, B_z, C_z are constants; the numerator a*b - c has degree 0 < deg(X - 1), so the quotient is 0
         // and the division is exact iff the numerator vanishes (r1cs.rs:1010-1020): the flag of the mat-vec
