@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "lsr_engine.h"
 #include "lsr_ntt.cuh"
 
@@ -123,6 +125,25 @@ static bool launch_column_s(int S, const NttContext* c, u64* d, size_t batch, cu
     }
 }
 
+// S1 + S2 column stages in one HBM round trip (ntt_column2_kernel)
+template <int S1, int S2, bool INV, bool FIRST>
+static bool launch_column2(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+    const size_t blocks = batch << (logn - 12);          // 4096 coefficients per CTA
+    if (blocks == 0) return true;
+    if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    const int pol = policy_of(c, INV);
+    if (pol == POL_F64)       ntt_column2_kernel<S1, S2, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0);
+    else if (pol == POL_LAZY) ntt_column2_kernel<S1, S2, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    else if (pol == POL_GOLD) ntt_column2_kernel<S1, S2, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    else                      ntt_column2_kernel<S1, S2, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    return cuda_ok(cudaGetLastError(), "ntt_column2_kernel launch");
+}
+
+static bool column2_enabled() {
+    static const bool on = [] { const char* e = std::getenv("LSR_NTT_COLUMN2"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // n <= 2^13: one kernel, the polynomial never leaves shared memory.
 // n >= 2^14: column passes (first log n - 12 stages, at most 5 per pass: one pass up to 2^17, two up to
 // 2^22, three up to 2^24) + tile kernel on 4096-blocks.
@@ -149,6 +170,24 @@ static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s
         left -= S[i];
     }
     const size_t total = batch << logn;
+    if (C >= 6 && column2_enabled()) {
+        // 6 .. 8 column stages: one shared-memory pass; 9 .. 12: a register pass of C - 8 stages + one of 8
+        const int head = C > 8 ? C - 8 : 0;
+        auto fused = [&](bool first) -> bool {
+            if (C == 6) return launch_column2<3, 3, INV, true>(c, d, batch, s, logn, 0u);
+            if (C == 7) return launch_column2<4, 3, INV, true>(c, d, batch, s, logn, 0u);
+            return first ? launch_column2<4, 4, INV, true>(c, d, batch, s, logn, 0u)
+                         : launch_column2<4, 4, INV, false>(c, d, batch, s, logn, (u32)head);
+        };
+        if (!INV) {
+            if (head && !launch_column_s<false, true>(head, c, d, batch, s, logn, 0u)) return false;
+            if (!fused(head == 0)) return false;
+            return launch_tile<12, false, false>(c, d, total, s, (u32)C);
+        }
+        if (!launch_tile<12, false, true>(c, d, total, s, (u32)C)) return false;
+        if (!fused(head == 0)) return false;
+        return head ? launch_column_s<true, true>(head, c, d, batch, s, logn, 0u) : true;
+    }
     if (!INV) {
         for (int i = 0; i < passes; i++) {
             const bool ok = i == 0 ? launch_column_s<false, true>(S[i], c, d, batch, s, logn, (u32)s0[i])

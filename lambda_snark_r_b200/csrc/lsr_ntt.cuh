@@ -588,6 +588,99 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
 }
 
 // ---------------------------------------------------------------------------
+// Big-n helper for n >= 2^18: S1 + S2 column stages (6 .. 8) in ONE HBM round trip.  A CTA takes the
+// 2^(S1+S2) rows x COLS adjacent columns (rows are g = n >> (s0 + S1 + S2) apart, COLS * 8 >= 128 bytes of
+// every row are contiguous) = 4096 coefficients through shared memory: phase A is the register pass of
+// ntt_column_kernel<S1> on rows r0 + (j << S2), phase B the one of ntt_column_kernel<S2> on rows
+// (b << S2) + j of sub-block b (twiddle group blk * 2^S1 + b), i.e. exactly the two chained register passes,
+// with the exchange between them on chip.  Inverse: phase B first, then phase A.
+// ---------------------------------------------------------------------------
+template <int S1, int S2, int POL, bool INVERSE, bool FIRST>
+__global__ void __launch_bounds__(kNttThreads)
+ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0) {
+    constexpr u32 LR = S1 + S2, ROWS = 1u << LR, ELEMS = 4096u, COLS = ELEMS / ROWS, LC = 12 - LR;
+    static_assert(S1 >= S2 && S1 <= 4 && COLS >= 16, "row segments of at least 128 bytes");
+    __shared__ __align__(16) u64 sm[ELEMS];
+    const u32 LG = logn - s0 - LR;                       // log2 g
+    const size_t grp = blockIdx.x;                       // (polynomial, block, column group) triples
+    const size_t pb = grp >> (LG - LC);                  // polynomial * 2^s0 + block
+    const u32 c0 = (u32)(grp & (((size_t)1 << (LG - LC)) - 1u)) << LC;
+    const u32 blk = (u32)(pb & (((size_t)1 << s0) - 1u));
+    u64* __restrict__ g = data + (pb << (LG + LR)) + c0;
+    (void)batch;
+
+    auto phaseA = [&](bool from_global, bool to_global) {
+        const u32 T0 = (1u << s0) + blk;
+#pragma unroll 1
+        for (u32 it = threadIdx.x; it < (ELEMS >> S1); it += kNttThreads) {
+            const u32 cc = it & (COLS - 1u), r0 = it >> LC;          // r0 < 2^S2
+            u64 v[1 << S1];
+            if (from_global) {
+#pragma unroll
+                for (int j = 0; j < (1 << S1); j++) v[j] = g[((size_t)(r0 + ((u32)j << S2)) << LG) + cc];
+                if (FIRST && !INVERSE) {                             // raw caller data (see ntt_column_kernel)
+                    const u64 limit = POL == POL_GOLD ? mp.q : mp.q4;
+                    u64 any = 0;
+#pragma unroll
+                    for (int j = 0; j < (1 << S1); j++) any |= v[j];
+                    if (__builtin_expect(any >= limit, 0)) {
+#pragma unroll
+                        for (int j = 0; j < (1 << S1); j++) v[j] = sanitize(v[j], limit, mp);
+                    }
+#pragma unroll
+                    for (int j = 0; j < (1 << S1); j++) v[j] = to_working<POL>(v[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < (1 << S1); j++) v[j] = sm[((r0 + ((u32)j << S2)) << LC) + cc];
+            }
+            if (!INVERSE) fwd_network<S1, POL>(v, tbl.fwd, T0, mp);
+            else inv_network<S1, POL, FIRST>(v, tbl.inv, T0, (int)(LG + S2), tbl.n_inv, mp);
+            if (to_global) {
+#pragma unroll
+                for (int j = 0; j < (1 << S1); j++) g[((size_t)(r0 + ((u32)j << S2)) << LG) + cc] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < (1 << S1); j++) sm[((r0 + ((u32)j << S2)) << LC) + cc] = v[j];
+            }
+        }
+    };
+    auto phaseB = [&](bool from_global, bool to_global) {
+#pragma unroll 1
+        for (u32 it = threadIdx.x; it < (ELEMS >> S2); it += kNttThreads) {
+            const u32 cc = it & (COLS - 1u), b = it >> LC;           // b < 2^S1
+            const u32 T0 = (1u << (s0 + S1)) + (blk << S1) + b;
+            u64 v[1 << S2];
+            if (from_global) {
+#pragma unroll
+                for (int j = 0; j < (1 << S2); j++) v[j] = g[((size_t)((b << S2) + (u32)j) << LG) + cc];
+            } else {
+#pragma unroll
+                for (int j = 0; j < (1 << S2); j++) v[j] = sm[(((b << S2) + (u32)j) << LC) + cc];
+            }
+            if (!INVERSE) fwd_network<S2, POL>(v, tbl.fwd, T0, mp);
+            else inv_network<S2, POL, false>(v, tbl.inv, T0, (int)LG, tbl.n_inv, mp);
+            if (to_global) {
+#pragma unroll
+                for (int j = 0; j < (1 << S2); j++) g[((size_t)((b << S2) + (u32)j) << LG) + cc] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < (1 << S2); j++) sm[(((b << S2) + (u32)j) << LC) + cc] = v[j];
+            }
+        }
+    };
+    if (!INVERSE) {
+        phaseA(true, false);
+        __syncthreads();
+        phaseB(false, true);
+    } else {
+        phaseB(true, false);
+        __syncthreads();
+        phaseA(false, true);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K3: result[i] = a[i] * b[i] mod q, exact for any u64 inputs
 // (ntt.cpp:106-119).  Grid-stride, 16-byte accesses, result may alias a or b.
 // ---------------------------------------------------------------------------

@@ -5,7 +5,7 @@ import random
 import numpy as np
 import pytest
 
-from conftest import Q0, Q1
+from conftest import Q0, Q1, Q45, Q50, Q60
 from lambda_snark_r_b200 import api, capi
 from oracle import quotient as QO
 from test_oracle_quotient import mult_gates
@@ -169,10 +169,12 @@ def np_mult_gates(m, q, seed):
     return 3 * m + 1, (rows, 3 * rows + 1, one), (rows, 3 * rows + 2, one), (rows, 3 * rows + 3, one), z
 
 
-@pytest.mark.parametrize("q,logn", [(P, 18), (P, 20), (P, 21), (P, 23), (Q1, 18)])
+@pytest.mark.parametrize("q,logn", [(P, 18), (P, 19), (P, 20), (P, 21), (P, 23), (P, 24), (Q1, 18), (Q45, 19), (Q50, 19),
+                                    (Q60, 18)])
 def test_big_cyclic_transform_matches_c_oracle(gpu, q, logn):
-    """One, two and three column passes ahead of the 4096-blocks (log n - 12 = 6, 8, 9, 11 stages), against
-    the C restatement of ntt.rs."""
+    """Column stages ahead of the 4096-blocks: log n - 12 = 6, 7, 8 (one shared-memory pass of 3+3, 4+3, 4+4
+    stages), 9, 11, 12 (a register pass + the 4+4 pass), under all four arithmetic policies (Goldilocks, FP64,
+    lazy u64, guarded u64), against the C restatement of ntt.rs."""
     from oracle import oracle as O
     n = 1 << logn
     rng = np.random.Generator(np.random.PCG64(logn))
