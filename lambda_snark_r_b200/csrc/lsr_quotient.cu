@@ -26,7 +26,9 @@
 //                N = P_lo - P_hi, and Q = P_hi
 // 6 W transforms of size m and no zero padding, against 3 W of size m + 4 W of size 2m.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
+#include <utility>
 
 #include "lsr_arith.cuh"
 #include "lsr_engine.h"
@@ -53,6 +55,11 @@ struct QuotientState {
     PinnedScratch h_flags;
     u64 omega = 0;
     int device = 0;
+    // host-io pipeline of prover_commit_quotient: copy-in / compute / copy-out streams, two buffers each
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr},
+                ev_zfree[2] = {nullptr, nullptr};
+    bool pipe_ready = false;
 };
 
 void quotient_state_free(QuotientState* s) {
@@ -65,6 +72,9 @@ void quotient_state_free(QuotientState* s) {
     if (s->csr.val) cudaFree(s->csr.val);
     s->z.release(); s->e.release(); s->qbuf.release(); s->flags.release(); s->h_flags.release();
     s->seeds.release(); s->containers.release(); s->coef.release(); s->fs.release();
+    for (auto& st : s->pipe) if (st) cudaStreamDestroy(st);
+    for (int b = 0; b < 2; b++)
+        for (cudaEvent_t e : {s->ev_in[b], s->ev_comp[b], s->ev_out[b], s->ev_zfree[b]}) if (e) cudaEventDestroy(e);
     delete s;
 }
 
@@ -238,38 +248,17 @@ static QuotientState* get_state(R1csHandle* h, u64 omega) {
     return st;
 }
 
-// Device part of the pipeline: witnesses [count][cols] (HOST words, or DEVICE words when witnesses_on_device)
-// -> Q [count][m] zero-padded, left in st->qbuf on the device, status[count] on the host (0 ok, 1 the witness
-// does not satisfy the constraints).  The caller holds h->mu.  Synchronises the stream before returning.
-static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_on_device, size_t count, u64 omega,
-                           int* status, QuotientState** out_state, bool keep_coeffs = false) {
+// Witnesses dz [W][cols] on the device -> evaluations / coefficients in dE [3][W][m], Q in dQ [W][m] (zero-padded),
+// dF[w] != 0 when witness w does not satisfy the constraints.  Asynchronous on s.
+static bool quotient_compute(R1csHandle* h, QuotientState* st, const u64* dz, size_t W, u64* dE, u64* dQ, unsigned* dF,
+                             bool keep_coeffs, cudaStream_t s) {
     const uint32_t m = h->rows, cols = h->cols;
-    if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxEngineLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^23"); return 2; }
-    if (h->q != kGoldilocks && (h->q >> 61)) { set_error("quotient: unsupported modulus"); return 2; }
-    if (m >= 2 && omega == 0) omega = reference_root_of_unity(h->q, m);
-    if (m >= 2 && !host::cyclic_params_ok(h->q, m, omega)) { set_error("quotient: omega is not a primitive m-th root of unity"); return 2; }
-    QuotientState* st = get_state(h, m >= 2 ? omega : 0);
-    if (!st) return 4;
-    *out_state = st;
-    if (count == 0) return 0;
-    if (!cuda_ok(cudaSetDevice(st->device), "cudaSetDevice")) return 4;
     const ModParams mp = host::make_mod_params(h->q, 1);
-    cudaStream_t s = nullptr;      // legacy default stream: the cyclic contexts are private to this handle
-    const size_t W = count;
     const size_t em = (size_t)3 * W * m;
     int logm = 0;
     while ((1u << logm) < m) ++logm;
-    bool ok = st->z.reserve(W * cols * 8) && st->e.reserve(em * 8) &&
-              st->qbuf.reserve(W * m * 8) && st->flags.reserve(W * 4) && st->h_flags.reserve(W * 4);
-    if (!ok) return 3;
-    u64* dz = static_cast<u64*>(st->z.ptr);
-    u64* dE = static_cast<u64*>(st->e.ptr);
-    u64* dQ = static_cast<u64*>(st->qbuf.ptr);
-    unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
     auto grid = [](size_t n) { return (unsigned)((n + 255) / 256); };
-    ok = cuda_ok(cudaMemcpyAsync(dz, witnesses, W * cols * 8,
-                                 witnesses_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D witness") &&
-         cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
+    bool ok = cuda_ok(cudaMemsetAsync(dF, 0, W * 4, s), "memset");
     if (ok) {
         if (logm >= 10 && W <= 65535)
             spmv3_tiled_kernel<<<dim3(m >> 10, (unsigned)W), dim3(32, 8), 0, s>>>(mp, st->csr.row_ptr, st->csr.col, st->csr.val,
@@ -302,6 +291,42 @@ static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_o
             ok = st->coef.reserve(em * 8) &&
                  cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
     }
+    return ok;
+}
+
+// Device part of the pipeline: witnesses [count][cols] (HOST words, or DEVICE words when witnesses_on_device)
+// -> Q [count][m] zero-padded, left in st->qbuf on the device, status[count] on the host (0 ok, 1 the witness
+// does not satisfy the constraints).  The caller holds h->mu.  Synchronises the stream before returning.
+static int quotient_prepare(R1csHandle* h, u64 omega, QuotientState** out_state) {
+    const uint32_t m = h->rows, cols = h->cols;
+    if (m == 0 || (m & (m - 1)) || m > (1u << (kMaxEngineLogN - 1)) || cols == 0) { set_error("quotient: m must be a power of two <= 2^23"); return 2; }
+    if (h->q != kGoldilocks && (h->q >> 61)) { set_error("quotient: unsupported modulus"); return 2; }
+    if (m >= 2 && omega == 0) omega = reference_root_of_unity(h->q, m);
+    if (m >= 2 && !host::cyclic_params_ok(h->q, m, omega)) { set_error("quotient: omega is not a primitive m-th root of unity"); return 2; }
+    QuotientState* st = get_state(h, m >= 2 ? omega : 0);
+    if (!st) return 4;
+    *out_state = st;
+    return cuda_ok(cudaSetDevice(st->device), "cudaSetDevice") ? 0 : 4;
+}
+
+static int quotient_device(R1csHandle* h, const u64* witnesses, bool witnesses_on_device, size_t count, u64 omega,
+                           int* status, QuotientState** out_state, bool keep_coeffs = false) {
+    const int rc = quotient_prepare(h, omega, out_state);
+    if (rc != 0 || count == 0) return rc;
+    QuotientState* st = *out_state;
+    const uint32_t m = h->rows, cols = h->cols;
+    cudaStream_t s = nullptr;      // legacy default stream: the cyclic contexts are private to this handle
+    const size_t W = count;
+    bool ok = st->z.reserve(W * cols * 8) && st->e.reserve((size_t)3 * W * m * 8) &&
+              st->qbuf.reserve(W * m * 8) && st->flags.reserve(W * 4) && st->h_flags.reserve(W * 4);
+    if (!ok) return 3;
+    u64* dz = static_cast<u64*>(st->z.ptr);
+    u64* dE = static_cast<u64*>(st->e.ptr);
+    u64* dQ = static_cast<u64*>(st->qbuf.ptr);
+    unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
+    ok = cuda_ok(cudaMemcpyAsync(dz, witnesses, W * cols * 8,
+                                 witnesses_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D witness") &&
+         quotient_compute(h, st, dz, W, dE, dQ, dF, keep_coeffs, s);
     ok = ok && cuda_ok(cudaMemcpyAsync(st->h_flags.ptr, dF, W * 4, cudaMemcpyDeviceToHost, s), "D2H flags") &&
          cuda_ok(cudaStreamSynchronize(s), "sync");
     if (!ok) return 4;
@@ -320,6 +345,85 @@ int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 o
     return cuda_ok(cudaMemcpy(out, st->qbuf.ptr, count * (size_t)h->rows * 8, cudaMemcpyDeviceToHost), "D2H quotient") ? 0 : 4;
 }
 
+// Host-io pipeline of the commitment phase: witnesses are taken in groups; while group g is computed, the witnesses of
+// group g + 1 come in and the containers of group g - 1 go out (three streams, two buffers of each kind).  With
+// page-locked caller buffers the call is bound by the slower PCIe direction instead of the sum of both copies and the
+// compute.  Groups hold at least ~8 MB of witness words so that the copies run at full link rate.
+static std::pair<size_t, size_t> pipeline_groups(const R1csHandle* h, size_t count) {
+    if (std::getenv("LSR_PROVER_PIPELINE") && std::getenv("LSR_PROVER_PIPELINE")[0] == '0') return {count, count ? 1 : 0};
+    const size_t wbytes = (size_t)h->cols * 8;
+    const size_t G = std::max<size_t>(1, std::min<size_t>(count, ((size_t)8 << 20) / std::max<size_t>(wbytes, 1)));
+    return {G, G ? (count + G - 1) / G : 0};
+}
+
+static bool pipeline_init(QuotientState* st) {
+    if (st->pipe_ready) return true;
+    bool ok = true;
+    for (auto& s : st->pipe) ok = ok && cuda_ok(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int b = 0; b < 2 && ok; b++)
+        for (cudaEvent_t* e : {&st->ev_in[b], &st->ev_comp[b], &st->ev_out[b], &st->ev_zfree[b]})
+            ok = ok && cuda_ok(cudaEventCreateWithFlags(e, cudaEventDisableTiming), "cudaEventCreate");
+    st->pipe_ready = ok;
+    return ok;
+}
+
+static int prover_commit_pipelined(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
+                                   const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, int* status) {
+    QuotientState* st = nullptr;
+    const int rc = quotient_prepare(h, omega, &st);
+    if (rc != 0) return rc;
+    if (st->device != lwe->device) { set_error("prover_commit_quotient: R1CS and LWE context live on different devices"); return 2; }
+    if (!pipeline_init(st)) return 4;
+    const uint32_t m = h->rows, cols = h->cols, n = lwe->n;
+    const size_t chunks = (size_t)m / n, mine = chunk_hi - chunk_lo, words = lwe_words(lwe);
+    const auto [G, NG] = pipeline_groups(h, count);
+    bool ok = st->z.reserve(2 * G * cols * 8) && st->e.reserve((size_t)3 * G * m * 8) && st->qbuf.reserve(G * (size_t)m * 8) &&
+              st->flags.reserve(count * 4) && st->h_flags.reserve(count * 4) && st->seeds.reserve(2 * G * mine * 8) &&
+              st->containers.reserve(2 * G * mine * words * 8);
+    if (!ok) return 3;
+    u64* dE = static_cast<u64*>(st->e.ptr);
+    u64* dQ = static_cast<u64*>(st->qbuf.ptr);
+    unsigned* dF = static_cast<unsigned*>(st->flags.ptr);
+    cudaStream_t sin = st->pipe[0], scomp = st->pipe[1], sout = st->pipe[2];
+    for (size_t g = 0; ok && g < NG; g++) {
+        const int b = (int)(g & 1);
+        const size_t w0 = g * G, gw = std::min(G, count - w0);
+        u64* dz = static_cast<u64*>(st->z.ptr) + (size_t)b * G * cols;
+        u64* dseed = static_cast<u64*>(st->seeds.ptr) + (size_t)b * G * mine;
+        u64* dcont = static_cast<u64*>(st->containers.ptr) + (size_t)b * G * mine * words;
+        // copy-in: the buffers of group g - 2 must have been consumed
+        if (g >= 2) ok = cuda_ok(cudaStreamWaitEvent(sin, st->ev_zfree[b], 0), "wait");
+        ok = ok && cuda_ok(cudaMemcpyAsync(dz, witnesses + w0 * cols, gw * cols * 8, cudaMemcpyHostToDevice, sin), "H2D witness");
+        for (size_t w = 0; ok && w < gw; w++)
+            ok = cuda_ok(cudaMemcpyAsync(dseed + w * mine, seeds + (w0 + w) * chunks + chunk_lo, mine * 8, cudaMemcpyHostToDevice, sin), "H2D seeds");
+        ok = ok && cuda_ok(cudaEventRecord(st->ev_in[b], sin), "record");
+        // compute: quotient of the group, then its commitments into container buffer b (free once group g - 2 is out)
+        ok = ok && cuda_ok(cudaStreamWaitEvent(scomp, st->ev_in[b], 0), "wait");
+        if (ok && g >= 2) ok = cuda_ok(cudaStreamWaitEvent(scomp, st->ev_out[b], 0), "wait");
+        ok = ok && quotient_compute(h, st, dz, gw, dE, dQ, dF + w0, false, scomp);
+        if (ok && mine == chunks) {
+            ok = lwe_commit_launch(lwe, dQ, n, dseed, gw * chunks, dcont, scomp);
+        } else for (size_t w = 0; ok && w < gw; w++) {
+            ok = lwe_commit_launch(lwe, dQ + w * (size_t)m + chunk_lo * (size_t)n, n, dseed + w * mine, mine,
+                                   dcont + w * mine * words, scomp);
+        }
+        // the seeds live in the same double buffer as the witnesses: both are free after the commitments
+        ok = ok && cuda_ok(cudaEventRecord(st->ev_zfree[b], scomp), "record") &&
+             cuda_ok(cudaEventRecord(st->ev_comp[b], scomp), "record");
+        // copy-out
+        ok = ok && cuda_ok(cudaStreamWaitEvent(sout, st->ev_comp[b], 0), "wait") &&
+             cuda_ok(cudaMemcpyAsync(out + w0 * mine * words, dcont, gw * mine * words * 8, cudaMemcpyDeviceToHost, sout), "D2H containers") &&
+             cuda_ok(cudaEventRecord(st->ev_out[b], sout), "record");
+    }
+    ok = ok && cuda_ok(cudaMemcpyAsync(st->h_flags.ptr, dF, count * 4, cudaMemcpyDeviceToHost, scomp), "D2H flags");
+    // drain all three streams even after a failure: the buffers must be quiescent when the call returns
+    for (cudaStream_t s : {sin, scomp, sout}) ok = cuda_ok(cudaStreamSynchronize(s), "sync") && ok;
+    if (!ok) return 4;
+    const unsigned* hf = static_cast<const unsigned*>(st->h_flags.ptr);
+    for (size_t w = 0; w < count; w++) status[w] = hf[w] ? 1 : 0;
+    return 0;
+}
+
 // Commitment phase of the prover (BASELINE configs[4]; replaces compute_quotient_poly + Commitment::new of
 // prove_r1cs, rust-api/lambda-snark/src/lib.rs:747-757, for quotients longer than one ring element, which the
 // reference silently truncates -- SURVEY F6).  Q of every witness is cut into chunks = ceil(m / n) messages of
@@ -335,9 +439,11 @@ int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witn
     const size_t chunks = m <= n ? 1 : (size_t)m / n;
     if (chunk_lo > chunk_hi || chunk_hi > chunks) { set_error("prover_commit_quotient: bad chunk range"); return 2; }
     QuotientState* st = nullptr;
+    const size_t mine = chunk_hi - chunk_lo;
+    if (!io_on_device && mine > 0 && lwe->n <= m && pipeline_groups(h, count).second >= 2)
+        return prover_commit_pipelined(h, lwe, witnesses, count, omega, seeds, chunk_lo, chunk_hi, out, status);
     const int rc = quotient_device(h, witnesses, io_on_device, count, omega, status, &st);
     if (rc != 0) return rc;
-    const size_t mine = chunk_hi - chunk_lo;
     if (count == 0 || mine == 0) return 0;
     if (st->device != lwe->device) { set_error("prover_commit_quotient: R1CS and LWE context live on different devices"); return 2; }
     const size_t words = lwe_words(lwe);

@@ -239,3 +239,39 @@ def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
     with pytest.raises(api.LambdaSnarkError):
         r.commit_quotient(ctx, z[None, :], seeds[:1], 0, chunks + 1)
     ctx.close(); r.close()
+
+
+def test_prover_commit_pipeline_equals_the_serial_path(gpu):
+    """Host-io pipeline of lsr_prover_commit_quotient (groups of witnesses over copy-in / compute / copy-out streams, two
+    buffers each): five groups, an unsatisfied witness in the middle, whole quotients and a chunk slice -- bit-identical
+    to the one-shot path (LSR_PROVER_PIPELINE=0) and repeatable on the same handle."""
+    import os
+    q, m, n, k = P, 1 << 18, 4096, 2
+    cols, A, B, C, z = np_mult_gates(m, q, 99)
+    r = api.R1CS.from_arrays(m, cols, A, B, C, q)
+    ctx = api.LweContext(api.Params(n=n, k=k, q=Q0, sigma=3.19), seed32=bytes(range(32)))
+    chunks = r.quotient_chunks(ctx)
+    count = 5
+    zs = np.tile(z, (count, 1))
+    rng = np.random.Generator(np.random.PCG64(5))
+    for w in range(1, count):                           # different satisfied witnesses: a_i, b_i re-drawn per witness
+        a = rng.integers(0, q, size=m, dtype=np.uint64)
+        zs[w, 1::3] = a
+        zs[w, 3::3] = np.array([(int(x) * int(y)) % q for x, y in zip(a.tolist(), zs[w, 2::3].tolist())], dtype=np.uint64)
+    zs[2, 3] = (int(zs[2, 3]) + 1) % q                  # witness 2 violates constraint 0
+    seeds = (np.arange(1, count * chunks + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(count, chunks)
+    os.environ["LSR_PROVER_PIPELINE"] = "0"
+    try:
+        want, st_want = r.commit_quotient(ctx, zs, seeds)
+        want_slice, _ = r.commit_quotient(ctx, zs, seeds, 3, chunks - 5)
+    finally:
+        del os.environ["LSR_PROVER_PIPELINE"]
+    assert st_want.tolist() == [0, 0, 1, 0, 0]
+    for _ in range(2):
+        got, st = r.commit_quotient(ctx, zs, seeds)
+        assert st.tolist() == st_want.tolist() and np.array_equal(got, want)
+        got_slice, st = r.commit_quotient(ctx, zs, seeds, 3, chunks - 5)
+        assert st.tolist() == st_want.tolist() and np.array_equal(got_slice, want_slice)
+    assert np.array_equal(want[:, 3:chunks - 5], want_slice)
+    assert not np.array_equal(want[0], want[1])
+    ctx.close(); r.close()
