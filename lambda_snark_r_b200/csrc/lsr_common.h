@@ -78,8 +78,8 @@ struct NttTables {
     const ulonglong2* fwd_last;
     const ulonglong2* inv_last;
     ulonglong2 n_inv;   // (n^-1, shoup)
-    ulonglong2 head_fwd[16];   // fwd[0..15] / inv[0..15] by value: the twiddles of the
-    ulonglong2 head_inv[16];   // first forward pass are uniform over the whole grid
+    ulonglong2 head_fwd[32];   // fwd[0..31] / inv[0..31] by value: the twiddles of the
+    ulonglong2 head_inv[32];   // first forward pass (up to 5 stages) are uniform over the whole grid
 };
 
 }  // namespace lsr

@@ -361,7 +361,7 @@ static NttContext* ntt_create_from(const host::NttHostTables& ht, bool cyclic) {
         c->tables_f.inv = c->d_f_inv;
         c->tables_f.fwd_last = c->d_f_fwd_last;
         c->tables_f.inv_last = c->d_f_inv_last;
-        for (uint32_t i = 0; i < 16; ++i) {
+        for (uint32_t i = 0; i < 32; ++i) {
             c->tables_f.head_fwd[i] = i < n ? f_fwd[i] : ulonglong2{0, 0};
             c->tables_f.head_inv[i] = i < n ? f_inv[i] : ulonglong2{0, 0};
         }
@@ -369,7 +369,7 @@ static NttContext* ntt_create_from(const host::NttHostTables& ht, bool cyclic) {
     }
     c->tables.fwd = c->d_fwd;
     c->tables.inv = c->d_inv;
-    for (uint32_t i = 0; i < 16; ++i) {
+    for (uint32_t i = 0; i < 32; ++i) {
         c->tables.head_fwd[i] = i < n ? ht.fwd[i] : ulonglong2{0, 0};
         c->tables.head_inv[i] = i < n ? ht.inv[i] : ulonglong2{0, 0};
     }

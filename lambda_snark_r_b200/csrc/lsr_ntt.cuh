@@ -259,7 +259,14 @@ template <> struct plan<9>  { static constexpr int N = 3; static constexpr int R
 template <> struct plan<10> { static constexpr int N = 3; static constexpr int R[4] = {3, 3, 4, 0}; };
 template <> struct plan<11> { static constexpr int N = 3; static constexpr int R[4] = {4, 3, 4, 0}; };
 template <> struct plan<12> { static constexpr int N = 3; static constexpr int R[4] = {4, 4, 4, 0}; };
+#ifndef LSR_PLAN13_R5     // n = 8192: three passes (the first on 32 register values per thread) instead of four
+#define LSR_PLAN13_R5 1
+#endif
+#if LSR_PLAN13_R5
+template <> struct plan<13> { static constexpr int N = 3; static constexpr int R[4] = {5, 4, 4, 0}; };
+#else
 template <> struct plan<13> { static constexpr int N = 4; static constexpr int R[4] = {3, 3, 3, 4}; };
+#endif
 template <> struct plan<14> { static constexpr int N = 4; static constexpr int R[4] = {4, 3, 3, 4}; };
 
 // ---------------------------------------------------------------------------

@@ -42,9 +42,15 @@ def main():
     peak = hbm_peak()
     rows = []
     shapes = [(logn, Q_SMALL if logn <= 12 else Q_LARGE, False) for logn in range(10, 17)] + [(20, GOLD, True)]
+    only = [int(a) for a in sys.argv[1:] if a.isdigit()]          # optional: ring-degree exponents to run
+    arith = 1 if "--u64" in sys.argv else 0                       # --u64: integer butterflies instead of the FP64 default
+    if only:
+        shapes = [sh for sh in shapes if sh[0] in only]
     for logn, q, cyclic in shapes:
         n = 1 << logn
         ctx = api.CyclicNtt(q, n) if cyclic else api.NttContext(q, n)
+        if arith and not cyclic:
+            ctx.set_arith(arith)
         for batch in (1, 16, 256, 4096, 65536):
             if batch * n * 8 > (4 << 30):
                 continue
