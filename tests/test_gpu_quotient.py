@@ -241,17 +241,18 @@ def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
     ctx.close(); r.close()
 
 
-def test_prover_commit_pipeline_equals_the_serial_path(gpu):
+@pytest.mark.parametrize("logm,count", [(18, 5), (16, 12)])
+def test_prover_commit_pipeline_equals_the_serial_path(gpu, logm, count):
     """Host-io pipeline of lsr_prover_commit_quotient (groups of witnesses over copy-in / compute / copy-out streams, two
-    buffers each): five groups, an unsatisfied witness in the middle, whole quotients and a chunk slice -- bit-identical
-    to the one-shot path (LSR_PROVER_PIPELINE=0) and repeatable on the same handle."""
+    buffers each): five groups of one witness (2^18) and groups of 5, 5, 2 witnesses (2^16), an unsatisfied witness in
+    the middle, whole quotients and a chunk slice -- bit-identical to the one-shot path (LSR_PROVER_PIPELINE=0) and
+    repeatable on the same handle."""
     import os
-    q, m, n, k = P, 1 << 18, 4096, 2
+    q, m, n, k = P, 1 << logm, 4096, 2
     cols, A, B, C, z = np_mult_gates(m, q, 99)
     r = api.R1CS.from_arrays(m, cols, A, B, C, q)
     ctx = api.LweContext(api.Params(n=n, k=k, q=Q0, sigma=3.19), seed32=bytes(range(32)))
     chunks = r.quotient_chunks(ctx)
-    count = 5
     zs = np.tile(z, (count, 1))
     rng = np.random.Generator(np.random.PCG64(5))
     for w in range(1, count):                           # different satisfied witnesses: a_i, b_i re-drawn per witness
@@ -263,10 +264,10 @@ def test_prover_commit_pipeline_equals_the_serial_path(gpu):
     os.environ["LSR_PROVER_PIPELINE"] = "0"
     try:
         want, st_want = r.commit_quotient(ctx, zs, seeds)
-        want_slice, _ = r.commit_quotient(ctx, zs, seeds, 3, chunks - 5)
+        want_slice, _ = r.commit_quotient(ctx, zs, seeds, 3, chunks - 5)         # 2^16: chunks = 16
     finally:
         del os.environ["LSR_PROVER_PIPELINE"]
-    assert st_want.tolist() == [0, 0, 1, 0, 0]
+    assert st_want.tolist() == [0, 0, 1] + [0] * (count - 3)
     for _ in range(2):
         got, st = r.commit_quotient(ctx, zs, seeds)
         assert st.tolist() == st_want.tolist() and np.array_equal(got, want)
