@@ -424,6 +424,11 @@ int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out,
                              int variant) LSR_NOEXCEPT;
 
+/* Test hook for the Goldilocks (q = 2^64 - 2^32 + 1) primitives of the quotient pipeline's transforms, on any
+ * 64-bit operands: out[4i..4i+3] = { a*b mod q, (a + (b mod q)) mod q through the lazy sum of the forward
+ * butterflies, (a - (b mod q)) mod q, ((a mod q) + (b mod q)) mod q through the canonical sum }.  HOST memory. */
+int lsr_goldilocks_probe_device(const uint64_t* a, const uint64_t* b, size_t count, uint64_t* out) LSR_NOEXCEPT;
+
 /* s, e of the commitment (context, seed): two's-complement, each [k][n];
  * test hook for the fused sampler.  HOST memory.                            */
 int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LSR_NOEXCEPT;

@@ -26,6 +26,7 @@ bool verify_r1cs_host(u64 m, u64 modulus, const u64* pub, size_t n_pub, const u6
 bool poly_eval_host(u64 modulus, const u64* coeffs, size_t len, size_t polys, const u64* points, size_t npts, u64* out);
 int prove_r1cs_batch(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, size_t n_public,
                      u64 omega, const u64* seeds, u64* containers, u64* challenges, u64* hashes, u64* evals, int* status);
+bool gold_probe_host(const u64* a, const u64* b, size_t count, u64* out);
 int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
                            const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, bool io_on_device, int* status);
 }
@@ -517,6 +518,14 @@ int lsr_lwe_sample_se(LweContext* ctx, uint64_t seed, int64_t* s, int64_t* e) LS
     LSR_TRY
     if (!ctx || !s || !e) return -1;
     return lsr::lwe_sample_se_host(ctx, seed, s, e) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_goldilocks_probe_device(const uint64_t* a, const uint64_t* b, size_t count, uint64_t* out) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!a || !b || !out) return -1;
+    return lsr::gold_probe_host(reinterpret_cast<const u64*>(a), reinterpret_cast<const u64*>(b), count,
+                                reinterpret_cast<u64*>(out)) ? 0 : -1;
     LSR_CATCH(-1)
 }
 

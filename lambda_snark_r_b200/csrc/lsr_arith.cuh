@@ -106,8 +106,9 @@ __device__ __forceinline__ u64 barrett128(u64 z0, u64 z1, const ModParams& mp) {
 }
 
 // ---------------------------------------------------------------------------
-// POL_GOLD: q = 2^64 - 2^32 + 1.  Residues are canonical u64 in [0, q); sums that overflow 2^64
-// are fixed up with 2^64 = 2^32 - 1 (mod q), i.e. a wrapped subtraction of q.
+// POL_GOLD: q = 2^64 - 2^32 + 1.  Residues are canonical u64 in [0, q) at every interface and throughout the inverse
+// transforms; inside the forward transforms sums are any representative in [0, 2^64) (gold_add_lazy).  Sums that
+// overflow 2^64 are fixed up with 2^64 = 2^32 - 1 (mod q), i.e. a wrapped subtraction of q.
 // ---------------------------------------------------------------------------
 // Canonical residues in, canonical residue out.  Every correction is a carry / borrow folded back with
 // 2^64 = 2^32 - 1 (mod q): the borrow of a subtraction chain turned into the mask 0xffffffff (= eps) by
@@ -127,50 +128,69 @@ __device__ __forceinline__ u64 gold_neg_raw(u64 b) { return kGoldilocks - b; }  
 // a + b = a - (q - b); q - b = q for b = 0 is handled by the same borrow correction
 __device__ __forceinline__ u64 gold_add(u64 a, u64 b) { return gold_sub(a, gold_neg_raw(b)); }
 
-// full 64 x 64 -> 128 product: four 32 x 32 multiply-adds with 64-bit accumulators, two carry adds
-__device__ __forceinline__ void mul64_wide(u64 a, u64 b, u64& lo, u64& hi) {
-    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    const u64 p0 = (u64)a0 * b0;
-    const u64 t = (u64)a0 * b1 + (p0 >> 32);               // <= (2^32-1)^2 + 2^32 - 1 < 2^64
-    const u64 u = (u64)a1 * b0 + (u32)t;
-    hi = (u64)a1 * b1 + (t >> 32) + (u >> 32);             // the product is < 2^128: no overflow
-    lo = (u << 32) | (u32)p0;
+// a + b for a ANYWHERE in [0, 2^64) and b <= q: on carry the wrapped sum is 2^64 = eps too small; adding eps cannot carry
+// again (a + b - 2^64 <= q - 2).  The result is some representative in [0, 2^64), not necessarily canonical: the forward
+// (Cooley-Tukey) butterflies keep their sums this way -- X +- T with T canonical never needs X canonical, and products accept
+// any 64-bit operand -- and only the last pass canonicalises (gold_canonical).  gold_sub(a, b) has the same property: the
+// borrow correction a - b + 2^64 - eps cannot borrow again when b <= q, whatever a is.
+__device__ __forceinline__ u64 gold_add_lazy(u64 a, u64 b) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t.reg .u32 m;\n\t"
+        "add.cc.u32 %0, %0, %2;\n\taddc.cc.u32 %1, %1, %3;\n\taddc.u32 m, 0, 0;\n\tneg.s32 m, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+        : "+r"(a0), "+r"(a1) : "r"(b0), "r"(b1));
+    return ((u64)a1 << 32) | a0;
 }
-
-// (hi:lo) mod q for ANY 128-bit value:  hi = hh * 2^32 + hl  ->  lo + hl * (2^32 - 1) - hh   (2^96 = -1, 2^64 = eps)
-__device__ __forceinline__ u64 gold_reduce128(u64 lo, u64 hi) {
-    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32);
-    const u32 hl = (u32)hi, hh = (u32)(hi >> 32);
-    const u64 t1 = (u64)hl * 0xFFFFFFFFu;                   // < 2^64 - 2^33 + 2
-    u32 m;
-    // t0 = lo - hh, borrow -> - eps (cannot borrow again: lo - hh + 2^64 >= 2^64 - eps)
-    asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 %2, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
-        : "+r"(r0), "+r"(r1), "=r"(m) : "r"(hh));
-    (void)m;
-    // r = t0 + t1, carry -> + eps (cannot carry again: the sum is then <= 2^64 - 2^32 - 1 < q)
-    u32 c;
-    asm("{\n\tadd.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;\n\t}"
-        : "+r"(r0), "+r"(r1), "=r"(c) : "r"((u32)t1), "r"((u32)(t1 >> 32)));
-    u32 cm = 0u - c;
-    asm("{\n\tadd.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+r"(r0), "+r"(r1) : "r"(cm));
-    // canonical: r >= q  <=>  r + eps carries; then r - q = r + eps (mod 2^64)
-    u32 c3, s0, s1;
-    asm("{\n\tadd.cc.u32 %0, %3, 0xffffffff;\n\taddc.cc.u32 %1, %4, 0;\n\taddc.u32 %2, 0, 0;\n\t}"
-        : "=r"(s0), "=r"(s1), "=r"(c3) : "r"(r0), "r"(r1));
-    cm = 0u - c3;
-    asm("{\n\tadd.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, 0;\n\t}" : "+r"(r0), "+r"(r1) : "r"(cm));
+#ifndef LSR_GOLD_CANON_PRED
+#define LSR_GOLD_CANON_PRED 1
+#endif
+// r >= q  <=>  high word all ones and low word non-zero (q = 0xffffffff00000001); then r - q = low word - 1
+// (as carries, not compares: the butterfly networks keep every predicate register busy with carry chains, and
+// compare results that live across them get spilled into general registers)
+__device__ __forceinline__ u64 gold_canonical(u64 r) {
+    u32 r0 = (u32)r, r1 = (u32)(r >> 32);
+#if LSR_GOLD_CANON_PRED
+    if (r1 == 0xffffffffu && r0 != 0u) { r0 -= 1u; r1 = 0u; }
+#else
+    // r >= q  <=>  r + eps carries; then r - q = r + eps (mod 2^64)
+    asm("{\n\t.reg .u32 m, s0, s1;\n\t"
+        "add.cc.u32 s0, %0, 0xffffffff;\n\taddc.cc.u32 s1, %1, 0;\n\taddc.u32 m, 0, 0;\n\tneg.s32 m, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+        : "+r"(r0), "+r"(r1));
+#endif
     return ((u64)r1 << 32) | r0;
 }
+
+// (a * b) mod q for ANY 64-bit a, b, canonical result.  Product: four 32 x 32 -> 64 multiplies whose halves are summed
+// column-wise with two carry chains (4 IMAD.WIDE + 5 IADD3; the earlier form with 64-bit accumulators cost 12 instructions,
+// half of them moves that set up the accumulator register pairs).  Reduction of (r3 r2 r1 r0), 2^64 = eps, 2^96 = -1:
+// (r1 r0) - r3 + r2 * eps; the borrow of the subtraction is folded back as - eps (cannot borrow again:
+// lo - r3 + 2^64 >= 2^64 - eps), the carry of the addition as + eps (cannot carry again: the sum is then < q).
 __device__ __forceinline__ u64 gold_mul(u64 a, u64 b) {
-    u64 lo, hi;
-    mul64_wide(a, b, lo, hi);
-    return gold_reduce128(lo, hi);
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 r0, r1, r2, r3;
+    asm("{\n\t.reg .u64 p0, p1, p2, p3;\n\t.reg .u32 p0l, p0h, p1l, p1h, p2l, p2h, p3l, p3h;\n\t"
+        "mul.wide.u32 p0, %4, %6;\n\tmul.wide.u32 p1, %4, %7;\n\tmul.wide.u32 p2, %5, %6;\n\tmul.wide.u32 p3, %5, %7;\n\t"
+        "mov.b64 {p0l, p0h}, p0;\n\tmov.b64 {p1l, p1h}, p1;\n\tmov.b64 {p2l, p2h}, p2;\n\tmov.b64 {p3l, p3h}, p3;\n\t"
+        "mov.u32 %0, p0l;\n\t"
+        "add.cc.u32 %1, p0h, p1l;\n\taddc.cc.u32 %2, p1h, p3l;\n\taddc.u32 %3, p3h, 0;\n\t"
+        "add.cc.u32 %1, %1, p2l;\n\taddc.cc.u32 %2, %2, p2h;\n\taddc.u32 %3, %3, 0;\n\t}"
+        : "=r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3) : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "+r"(r0), "+r"(r1) : "r"(r3));
+    asm("{\n\t.reg .u32 m, t0, t1;\n\t.reg .u64 t;\n\t"
+        "mul.wide.u32 t, %2, 0xffffffff;\n\tmov.b64 {t0, t1}, t;\n\t"
+        "add.cc.u32 %0, %0, t0;\n\taddc.cc.u32 %1, %1, t1;\n\taddc.u32 m, 0, 0;\n\tneg.s32 m, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+        : "+r"(r0), "+r"(r1) : "r"(r2));
+    return gold_canonical(((u64)r1 << 32) | r0);
 }
 
 // exact (a * b) mod q for any u64 a, b  (ntt.cpp:116-118 -> multiply_uint_mod)
 __device__ __forceinline__ u64 mulmod_exact(u64 a, u64 b, const ModParams& mp) {
-    if (mp.gold) return gold_mul(a, b);       // gold_reduce128 accepts any 128-bit value
+    if (mp.gold) return gold_mul(a, b);       // any 64-bit operands
     return barrett128(a * b, __umul64hi(a, b), mp);
 }
 

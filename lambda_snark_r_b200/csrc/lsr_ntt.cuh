@@ -109,9 +109,10 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                     v[j] = as_u(__dadd_rn(X, T));
                     v[jj] = as_u(__dadd_rn(X, -T));
                 } else if (POL == POL_GOLD) {
+                    // T canonical, X any representative in [0, 2^64): sums stay lazy until fwd_final
                     const u64 T = gold_mul(v[jj], w.x);
                     const u64 X = v[j];
-                    v[j] = gold_add(X, T);
+                    v[j] = gold_add_lazy(X, T);
                     v[jj] = gold_sub(X, T);
                 } else if (POL == POL_LAZY) {
                     const u64 T = mulred4(v[jj], w.x, w.y, mp.nq);
@@ -228,7 +229,7 @@ __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* 
 template <int POL>
 __device__ __forceinline__ u64 fwd_final(u64 v, const ModParams& mp) {
     if (POL == POL_F64) return f_to_canonical(reduce_f(as_d(v), mp.invq, mp.qd), mp);
-    if (POL == POL_GOLD) return v;
+    if (POL == POL_GOLD) return gold_canonical(v);
     if (POL == POL_LAZY) return reduce_small(v, mp);
     return csub(csub(v, mp.q2), mp.q);
 }

@@ -179,6 +179,36 @@ quotient_finish_kernel(const ModParams mp, const u64* __restrict__ C, u64* __res
     Q[idx] = field_mul(field_sub(C[idx], Q[idx], mp), inv2, mp);
 }
 
+// Test hook: the Goldilocks primitives on caller-supplied operands (any 64-bit words), so that the carry / borrow
+// corner cases (operands and intermediate sums at 0, q - 1, q, 2^64 - 1, 2^32 boundaries) can be compared with
+// arbitrary-precision arithmetic.  out[i] = {a*b, canonical(a +lazy (b mod q)), canonical(a - (b mod q)), (a mod q) + (b mod q)}
+__global__ void gold_probe_kernel(const u64* __restrict__ a, const u64* __restrict__ b, size_t count, u64* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const u64 x = a[i], y = b[i];
+    const u64 yc = gold_canonical(y), xc = gold_canonical(x);     // y < 2^64 < 2q: one conditional subtraction
+    out[4 * i + 0] = gold_mul(x, y);
+    out[4 * i + 1] = gold_canonical(gold_add_lazy(x, yc));
+    out[4 * i + 2] = gold_canonical(gold_sub(x, yc));
+    out[4 * i + 3] = gold_add(xc, yc);
+}
+
+bool gold_probe_host(const u64* a, const u64* b, size_t count, u64* out) {
+    if (count == 0) return true;
+    if (!cuda_ok(cudaSetDevice(current_device_choice()), "cudaSetDevice")) return false;
+    u64 *da = nullptr, *db = nullptr, *dout = nullptr;
+    bool ok = cuda_ok(cudaMalloc(&da, count * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&db, count * 8), "cudaMalloc") &&
+              cuda_ok(cudaMalloc(&dout, count * 32), "cudaMalloc") &&
+              cuda_ok(cudaMemcpy(da, a, count * 8, cudaMemcpyHostToDevice), "H2D") &&
+              cuda_ok(cudaMemcpy(db, b, count * 8, cudaMemcpyHostToDevice), "H2D");
+    if (ok) {
+        gold_probe_kernel<<<(unsigned)((count + 255) / 256), 256>>>(da, db, count, dout);
+        ok = cuda_ok(cudaGetLastError(), "gold_probe_kernel") && cuda_ok(cudaMemcpy(out, dout, count * 32, cudaMemcpyDeviceToHost), "D2H");
+    }
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    return ok;
+}
+
 // ------------------------------------------------------------------ host side
 static bool build_csr(const R1csHandle* h, QuotientState* st) {
     const uint32_t rows = h->rows;

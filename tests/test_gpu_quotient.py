@@ -276,3 +276,30 @@ def test_prover_commit_pipeline_equals_the_serial_path(gpu, logm, count):
     assert np.array_equal(want[:, 3:chunks - 5], want_slice)
     assert not np.array_equal(want[0], want[1])
     ctx.close(); r.close()
+
+
+def test_goldilocks_primitives_on_boundary_operands(gpu):
+    """gold_mul / gold_add_lazy / gold_sub / gold_add on every pair of boundary words (0, 1, 2^32 +- 1, q - 1, q, q + 1,
+    2^64 - 1, ...) and on random pairs, against Python integers."""
+    q = P
+    eps = 2**32 - 1
+    edge = [0, 1, 2, eps - 1, eps, eps + 1, 2**32 + 1, 2**33, 2**63 - 1, 2**63, 2**63 + 1, q - eps - 1, q - eps, q - 2, q - 1, q,
+            q + 1, q + 2, 2**64 - eps - 1, 2**64 - eps, 2**64 - 2**32, 2**64 - 2, 2**64 - 1, (q - 1) // 2, (q + 1) // 2,
+            0xFFFFFFFF_00000000, 0x00000000_FFFFFFFF, 0xFFFFFFFE_FFFFFFFF, 0x80000000_80000000, 0xFFFF0000_0000FFFF]
+    rng = np.random.Generator(np.random.PCG64(64))
+    a = [x for x in edge for _ in edge] + rng.integers(0, 2**64, size=200000, dtype=np.uint64).tolist()
+    b = [y for _ in edge for y in edge] + rng.integers(0, 2**64, size=200000, dtype=np.uint64).tolist()
+    # random operands concentrated where the corrections fire: high words all ones / zero
+    hi = rng.integers(0, 2**32, size=50000, dtype=np.uint64).tolist()
+    a += [(0xFFFFFFFF << 32) | x for x in hi]
+    b += [(0xFFFFFFFF << 32) | y for y in reversed(hi)]
+    a += [x for x in hi]
+    b += [(0xFFFFFFFF << 32) | y for y in hi]
+    A, B = np.array(a, dtype=np.uint64), np.array(b, dtype=np.uint64)
+    out = np.zeros((A.size, 4), dtype=np.uint64)
+    lib = capi.load()
+    assert lib.lsr_goldilocks_probe_device(A.ctypes.data_as(capi.u64p), B.ctypes.data_as(capi.u64p), A.size,
+                                           out.ctypes.data_as(capi.u64p)) == 0
+    want = np.array([[x * y % q, (x + y % q) % q, (x - y % q) % q, (x % q + y % q) % q] for x, y in zip(a, b)], dtype=np.uint64)
+    bad = np.nonzero((out != want).any(axis=1))[0]
+    assert bad.size == 0, [(hex(a[i]), hex(b[i]), out[i].tolist(), want[i].tolist()) for i in bad[:5]]
