@@ -117,11 +117,11 @@ __device__ __forceinline__ u64 barrett128(u64 z0, u64 z1, const ModParams& mp) {
 // Chains are homogeneous (sub.cc ... subc, add.cc ... addc): the two flag conventions are never mixed.
 __device__ __forceinline__ u64 gold_sub(u64 a, u64 b) {
     // d = a - b; on borrow the wrapped value is 2^64 = eps too large
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), m;
-    asm("{\n\tsub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;\n\t"
-        "sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, 0;\n\t}"
-        : "+r"(a0), "+r"(a1), "=r"(m) : "r"(b0), "r"(b1));
-    (void)m;
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    asm("{\n\t.reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %0, %2;\n\tsubc.cc.u32 %1, %1, %3;\n\tsubc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+        : "+r"(a0), "+r"(a1) : "r"(b0), "r"(b1));
     return ((u64)a1 << 32) | a0;
 }
 __device__ __forceinline__ u64 gold_neg_raw(u64 b) { return kGoldilocks - b; }      // in [1, q] for canonical b

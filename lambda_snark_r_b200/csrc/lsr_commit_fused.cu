@@ -73,7 +73,7 @@ __device__ __forceinline__ u64 commit_finish(u32 idx, u64 v, int ev, const u64* 
                                              u64 p, u64 pinv, u32 msg_used) {
     v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                    // < 2q
     const u32 x = idx - ((u32)(K - 1) << LOGN);                                // wraps for earlier rows
-    if (idx >= ((u32)(K - 1) << LOGN) && x < msg_used) {
+    if ((K == 1 || idx >= ((u32)(K > 1 ? K - 1 : 1) << LOGN)) && x < msg_used) {
         // messages are field elements in practice (>= p more often than not): Barrett, not a 64-bit division
         const u64 m = p < (1ull << 21) ? (u64)mod_small(__ldcs(msg + x), (u32)p, pinv) : __ldcs(msg + x) % p;
         v = csub(v + delta * m, q);                                            // delta*m <= q-1
