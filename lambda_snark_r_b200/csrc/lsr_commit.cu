@@ -9,6 +9,7 @@
 // lsr_commit_fused.cu holds the single-kernel fused path used for the
 // headline configuration.
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 
@@ -451,7 +452,9 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
         return lwe_commit_host_staged(c, msgs, msg_len, seeds, count, out);
     const size_t words = lwe_words(c);
     const size_t eff_len = std::max<size_t>(msg_len, 1);
-    const size_t chunk = std::min<size_t>(count, 256);
+    size_t chunk_pref = 256;       // commitments per pipeline slot (16 MiB of containers at n = 4096, k = 2)
+    if (const char* e = std::getenv("LSR_COMMIT_CHUNK")) chunk_pref = std::max<size_t>(1, std::strtoull(e, nullptr, 0));
+    const size_t chunk = std::min<size_t>(count, chunk_pref);
     const bool fused = fused_commit_supported(c) && c->commit_path != 1;
     const int nbuf = (fused && count > chunk) ? 3 : 1;
     cudaStream_t streams[3] = {c->ntt->copy_streams[0], c->ntt->copy_streams[1], c->ntt->stream};
