@@ -74,6 +74,14 @@ def ntt_kat():
     (HERE / "ntt_kat.json").write_text(json.dumps(kat, indent=0))
 
 
+def explicit_inputs(q, n, k, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    s = rng.integers(-(q - 1), q, size=(k, n), dtype=np.int64)
+    e = rng.integers(-(q - 1), q, size=(k, n), dtype=np.int64)
+    msg = rng.integers(0, 2**64, size=n, dtype=np.uint64)
+    return s, e, msg
+
+
 def commit_kat():
     cases = []
     for (n, k, sigma, seed, msg) in [(4096, 2, 3.19, 0x1234, [1, 2, 3, 4]), (4096, 2, 3.19, 0xC0FFEE, list(range(100))),
@@ -84,7 +92,17 @@ def commit_kat():
                       "q": ctx.q, "p": ctx.p, "delta": ctx.delta, "words": int(c.size), "first": [str(int(v)) for v in c[:5]],
                       "sha256": hashlib.sha256(c.tobytes()).hexdigest(),
                       "matrix_sha256": hashlib.sha256(ctx.matrix().tobytes()).hexdigest()})
-    (HERE / "commit_kat.json").write_text(json.dumps({"source": "oracle/lsr_oracle.c (self-pin)", "cases": cases}, indent=0))
+    # explicit mode (s, e supplied): s, e uniform over (-q, q) and the message uniform over u64, all from PCG64(seed)
+    explicit = []
+    for (n, k, seed) in [(4096, 2, 1), (1024, 2, 2), (64, 3, 3)]:
+        ctx = O.OracleLwe(Q0, n, k, 3.19, bytes(range(32)))
+        s, e, msg = explicit_inputs(ctx.q, n, k, seed)
+        c = ctx.commit_explicit(msg, s, e)
+        explicit.append({"n": n, "k": k, "sigma": 3.19, "ctx_seed": "bytes(range(32))", "pcg64_seed": seed,
+                         "inputs": "tests/golden/make_golden.py::explicit_inputs", "first": [str(int(v)) for v in c[:5]],
+                         "sha256": hashlib.sha256(c.tobytes()).hexdigest()})
+    (HERE / "commit_kat.json").write_text(json.dumps({"source": "oracle/lsr_oracle.c (self-pin)", "cases": cases,
+                                                      "explicit": explicit}, indent=0))
 
 
 if __name__ == "__main__":

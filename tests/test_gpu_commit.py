@@ -282,6 +282,20 @@ def test_golden_digests_on_device(gpu):
         ctx.close()
 
 
+def test_golden_digests_explicit_mode_on_device(gpu):
+    import sys
+    if str(GOLD) not in sys.path:
+        sys.path.insert(0, str(GOLD))
+    from make_golden import explicit_inputs
+    g = json.loads((GOLD / "commit_kat.json").read_text())
+    for c in g["explicit"]:
+        ctx = mk(c["n"], c["k"], Q0, c["sigma"])
+        s, e, msg = explicit_inputs(ctx.q, c["n"], c["k"], c["pcg64_seed"])
+        cm = ctx.commit_explicit(msg[None, :], s[None], e[None])[0]
+        assert hashlib.sha256(cm.tobytes()).hexdigest() == c["sha256"]
+        ctx.close()
+
+
 def test_verify_and_lincomb_match_oracle(gpu, rng):
     ctx = mk()
     orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)

@@ -44,6 +44,22 @@ def test_golden_digests():
         assert hashlib.sha256(cm.tobytes()).hexdigest() == c["sha256"]
 
 
+def test_golden_digests_explicit_mode():
+    sys_path_golden = str(GOLD)
+    import sys
+    if sys_path_golden not in sys.path:
+        sys.path.insert(0, sys_path_golden)
+    from make_golden import explicit_inputs
+    g = json.loads((GOLD / "commit_kat.json").read_text())
+    assert len(g["explicit"]) >= 3
+    for c in g["explicit"]:
+        o = O.OracleLwe(Q0, c["n"], c["k"], c["sigma"], SEED32)
+        s, e, msg = explicit_inputs(o.q, c["n"], c["k"], c["pcg64_seed"])
+        cm = o.commit_explicit(msg, s, e)
+        assert [str(int(v)) for v in cm[:5]] == c["first"]
+        assert hashlib.sha256(cm.tobytes()).hexdigest() == c["sha256"]
+
+
 def test_container_layout(ctx):
     cm = ctx.commit([1, 2, 3, 4], 0x1234)                 # test_commitment.cpp:37-47
     assert cm.size == ctx.words and int(cm[0]) == 2 * 4096 * 8     # types.h:32-34
