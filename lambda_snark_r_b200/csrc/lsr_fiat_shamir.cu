@@ -14,6 +14,7 @@
 // source is checked on the host against hashlib by the CPU tests).  Evaluations: one CTA per
 // (polynomial, point), each thread a contiguous run of coefficients by Horner, scaled by x^start, tree sum.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "lsr_arith.cuh"
@@ -51,6 +52,36 @@ fs_challenge_kernel(const u64* __restrict__ pub, size_t n_pub, const u64* __rest
     for (int j = 0; j < 4; j++) hashes[8 * i + 4 + j] = g[j];
 }
 
+// Small batches: one WARP per statement (lsr_keccak.h, lane-parallel form).  A statement then takes ~1/3 of the time of
+// the one-thread form; at ~1 M statements/s the warps saturate the issue ports, so from kFsWarpMaxCount statements on the
+// one-thread-per-statement kernel above is the faster one again.
+constexpr int kFsWarpCta = 128;            // four statements per CTA
+constexpr size_t kFsWarpMaxCount = 4096;
+__global__ void __launch_bounds__(kFsWarpCta)
+fs_challenge_warp_kernel(const u64* __restrict__ pub, size_t n_pub, const u64* __restrict__ containers, size_t words,
+                         size_t count, u64 modulus, int chain, u64* __restrict__ ab, u64* __restrict__ hashes) {
+    const size_t i = (size_t)blockIdx.x * (kFsWarpCta / 32) + (threadIdx.x >> 5);     // uniform over the warp
+    if (i >= count) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64* w = containers + i * words;
+    u64 h[4];
+    fs_sha3_256_warp(FsTranscript{pub + i * n_pub, (u64)n_pub, w, (u64)words}, h);
+    const u64 alpha = h[0] % modulus;
+    u64 beta = 0;
+    u64 g[4] = {0, 0, 0, 0};
+    if (chain) {
+        const u64 one_pub[1] = {alpha};
+        fs_sha3_256_warp(FsTranscript{one_pub, 1, w, (u64)words}, g);
+        beta = g[0] % modulus;
+    }
+    if (lane == 0) {
+        ab[2 * i] = alpha;
+        ab[2 * i + 1] = beta;
+#pragma unroll
+        for (int j = 0; j < 4; j++) { hashes[8 * i + j] = h[j]; hashes[8 * i + 4 + j] = g[j]; }
+    }
+}
+
 // out[p][j] = sum_i coeffs[p][i] * x^i, x = points[(p % point_rows)][j];  grid = (npts, polys)
 __global__ void __launch_bounds__(kEvalThreads)
 poly_eval_kernel(const ModParams mp, const u64* __restrict__ coeffs, size_t len, const u64* __restrict__ points,
@@ -86,6 +117,15 @@ bool fs_challenge_launch(const u64* d_pub, size_t n_pub, const u64* d_containers
                          u64 modulus, bool chain, u64* d_ab, u64* d_hashes, cudaStream_t s) {
     if (count == 0) return true;
     if (modulus == 0) { set_error("fs_challenge: modulus 0"); return false; }
+    static const int force = [] { const char* e = std::getenv("LSR_FS_KERNEL"); return e ? std::atoi(e) : 0; }();   // 1 thread, 2 warp
+    const bool warp = force == 2 || (force != 1 && count < kFsWarpMaxCount);
+    if (warp) {
+        const size_t blocks = (count + kFsWarpCta / 32 - 1) / (kFsWarpCta / 32);
+        if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+        fs_challenge_warp_kernel<<<(unsigned)blocks, kFsWarpCta, 0, s>>>(d_pub, n_pub, d_containers, words, count, modulus,
+                                                                        chain ? 1 : 0, d_ab, d_hashes);
+        return cuda_ok(cudaGetLastError(), "fs_challenge_warp_kernel");
+    }
     const size_t blocks = (count + kFsThreads - 1) / kFsThreads;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     fs_challenge_kernel<<<(unsigned)blocks, kFsThreads, 0, s>>>(d_pub, n_pub, d_containers, words, count, modulus,

@@ -151,4 +151,127 @@ LSR_HD void fs_sha3_256(const FsTranscript& t, kw64 (&out)[4]) {
     out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; out[3] = a[3];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Lane-parallel form: state lane a[x + 5y] lives in execution lane l = x + 5y of a warp (lanes 25 .. 31 idle), so one
+// statement's hash advances with the latency of ~10 shuffles per round instead of ~150 dependent instructions of one
+// thread: 3x lower latency for small batches, where one thread per statement leaves the GPU empty and a proof waits
+// on its own transcript (fs_challenge_warp_kernel).  The index maps below are the whole difference to keccak_f1600
+// above; the host emulation (same maps, arrays instead of shuffles) is pinned to hashlib by the CPU suite.
+// ---------------------------------------------------------------------------------------------------------
+LSR_HD unsigned keccak_rho_rot(unsigned l) {        // rotation of a[l] in rho (the constants of keccak_f1600 above)
+    const unsigned char t[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+    return t[l];
+}
+LSR_HD unsigned keccak_pi_src(unsigned l) {         // b[l] = rotated a[keccak_pi_src(l)]  (inverse of pi)
+    const unsigned char t[25] = {0, 6, 12, 18, 24, 3, 9, 10, 16, 22, 1, 7, 13, 19, 20, 4, 5, 11, 17, 23, 2, 8, 14, 15, 21};
+    return t[l];
+}
+LSR_HD unsigned keccak_row_lane(unsigned l, unsigned dx) { return l - l % 5 + (l % 5 + dx) % 5; }   // (x + dx, y)
+LSR_HD unsigned keccak_col_lane(unsigned l, unsigned dy) { return (l + 5 * dy) % 25; }               // (x, y + dy)
+#if defined(__CUDACC__)
+// the device copy lives in the constant bank (a function-local table is rebuilt on the stack at every call)
+static __constant__ kw64 kKeccakRoundConstants[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+    0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+    0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+    0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+    0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+#endif
+LSR_HD kw64 keccak_round_constant(int round) {
+#if defined(__CUDA_ARCH__)
+    return kKeccakRoundConstants[round];
+#endif
+    const kw64 RC[24] = {
+        0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL,
+        0x000000000000808bULL, 0x0000000080000001ULL, 0x8000000080008081ULL, 0x8000000000008009ULL,
+        0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+        0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL,
+        0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
+        0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+    return RC[round];
+}
+// most significant word of (hi:lo) << (s mod 32)
+LSR_HD unsigned keccak_funnel_l(unsigned lo, unsigned hi, unsigned s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    s &= 31u;
+    return s ? (hi << s) | (lo >> (32u - s)) : hi;
+#endif
+}
+// rotation by a per-lane amount r in [0, 63]: swap the halves for r >= 32, then two funnel shifts by r mod 32
+LSR_HD kw64 keccak_rotl_var(kw64 x, unsigned r) {
+    unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+    if (r & 32u) { const unsigned t = lo; lo = hi; hi = t; }
+    const unsigned nh = keccak_funnel_l(lo, hi, r), nl = keccak_funnel_l(hi, lo, r);
+    return ((kw64)nh << 32) | nl;
+}
+
+// number of 136-byte rate blocks of the padded transcript, and lane L (0 .. 16) of block b
+LSR_HD kw64 fs_nblocks(const FsTranscript& t) { return (20 + 8 * t.total()) / 136 + 1; }
+LSR_HD kw64 fs_block_lane(const FsTranscript& t, kw64 b, int L) {
+    const long long k = (long long)(17 * b) - 3 + L;
+    const kw64 prev = t.word(k), next = t.word(k + 1);
+    kw64 lane = (prev >> 32) | (next << 32);
+    if (b == 0) {
+        if (L == 0) lane = 0x532d4144424d414cULL;                      // "LAMBDA-S"
+        if (L == 1) lane = 0x462d522d4b52414eULL;                      // "NARK-R-F"
+        if (L == 2) lane = 0x31762d53ULL | (next << 32);               // "S-v1" | lo32(word 0)
+    }
+    return lane;
+}
+
+#if !defined(__CUDA_ARCH__)
+// host emulation of the lane-parallel hash (test infrastructure for the index maps): arrays stand in for shuffles
+inline void fs_sha3_256_lanes_emulated(const FsTranscript& t, kw64 (&out)[4]) {
+    kw64 a[25] = {0};
+    const kw64 nblocks = fs_nblocks(t);
+    for (kw64 b = 0; b < nblocks; b++) {
+        for (int L = 0; L < 17; L++) a[L] ^= fs_block_lane(t, b, L);
+        if (b == nblocks - 1) a[16] ^= 0x8000000000000000ULL;
+        for (int round = 0; round < 24; round++) {
+            kw64 c[25], bb[25], tt[25];
+            for (unsigned l = 0; l < 25; l++)
+                c[l] = a[l] ^ a[keccak_col_lane(l, 1)] ^ a[keccak_col_lane(l, 2)] ^ a[keccak_col_lane(l, 3)] ^ a[keccak_col_lane(l, 4)];
+            for (unsigned l = 0; l < 25; l++)
+                tt[l] = keccak_rotl_var(a[l] ^ c[keccak_row_lane(l, 4)] ^ keccak_rotl_var(c[keccak_row_lane(l, 1)], 1), keccak_rho_rot(l));
+            for (unsigned l = 0; l < 25; l++) bb[l] = tt[keccak_pi_src(l)];
+            for (unsigned l = 0; l < 25; l++) a[l] = bb[l] ^ (~bb[keccak_row_lane(l, 1)] & bb[keccak_row_lane(l, 2)]);
+            a[0] ^= keccak_round_constant(round);
+        }
+    }
+    out[0] = a[0]; out[1] = a[1]; out[2] = a[2]; out[3] = a[3];
+}
+#endif
+
+#if defined(__CUDACC__)
+// One warp, one transcript: every lane passes the same FsTranscript; the digest is returned in all lanes.
+__device__ __forceinline__ void fs_sha3_256_warp(const FsTranscript& t, kw64 (&out)[4]) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned l = lane < 25u ? lane : 0u;           // idle lanes mirror lane 0's sources; their values are never read
+    const unsigned c1 = keccak_col_lane(l, 1), c2 = keccak_col_lane(l, 2), c3 = keccak_col_lane(l, 3), c4 = keccak_col_lane(l, 4);
+    const unsigned xm1 = keccak_row_lane(l, 4), xp1 = keccak_row_lane(l, 1), xp2 = keccak_row_lane(l, 2);
+    const unsigned rot = keccak_rho_rot(l), src = keccak_pi_src(l);
+    kw64 a = 0;
+    const kw64 nblocks = fs_nblocks(t);
+    for (kw64 b = 0; b < nblocks; b++) {
+        kw64 in = lane < 17u ? fs_block_lane(t, b, (int)lane) : 0ull;
+        if (b == nblocks - 1 && lane == 16u) in ^= 0x8000000000000000ULL;
+        a ^= in;
+#pragma unroll 1
+        for (int round = 0; round < 24; round++) {
+            const kw64 c = a ^ __shfl_sync(kFull, a, c1) ^ __shfl_sync(kFull, a, c2) ^ __shfl_sync(kFull, a, c3) ^ __shfl_sync(kFull, a, c4);
+            const kw64 d = __shfl_sync(kFull, c, xm1) ^ keccak_rotl_var(__shfl_sync(kFull, c, xp1), 1u);
+            const kw64 bb = __shfl_sync(kFull, keccak_rotl_var(a ^ d, rot), src);
+            const kw64 b1 = __shfl_sync(kFull, bb, xp1), b2 = __shfl_sync(kFull, bb, xp2);
+            a = bb ^ (~b1 & b2) ^ (lane == 0u ? keccak_round_constant(round) : 0ull);     // iota, no divergence
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = __shfl_sync(kFull, a, i);
+}
+#endif
+
 }  // namespace lsr

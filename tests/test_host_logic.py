@@ -230,6 +230,11 @@ def test_transcript_hash_source_matches_sha3_256(tmp_path):
             h = hashlib.sha3_256(b"LAMBDA-SNARK-R-FS-v1" + struct.pack("<Q", n_pub) + pub.tobytes() +
                                  struct.pack("<Q", n_words) + words.tobytes())
             assert out.tobytes() == h.digest(), (n_pub, n_words)
+            # the lane-parallel formulation of the warp-per-statement kernel (same index maps, arrays for shuffles)
+            out2 = np.zeros(4, dtype=np.uint64)
+            lib.lsr_test_fs_hash_lanes(pub.ctypes.data_as(capi.u64p), C.c_uint64(n_pub), words.ctypes.data_as(capi.u64p),
+                                       C.c_uint64(n_words), out2.ctypes.data_as(capi.u64p))
+            assert out2.tobytes() == h.digest(), ("lanes", n_pub, n_words)
 
 
 def test_copy_pool_stress(tmp_path):
