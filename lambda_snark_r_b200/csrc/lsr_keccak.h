@@ -256,10 +256,13 @@ __device__ __forceinline__ void fs_sha3_256_warp(const FsTranscript& t, kw64 (&o
     const unsigned rot = keccak_rho_rot(l), src = keccak_pi_src(l);
     kw64 a = 0;
     const kw64 nblocks = fs_nblocks(t);
+    kw64 in = lane < 17u ? fs_block_lane(t, 0, (int)lane) : 0ull;
     for (kw64 b = 0; b < nblocks; b++) {
-        kw64 in = lane < 17u ? fs_block_lane(t, b, (int)lane) : 0ull;
         if (b == nblocks - 1 && lane == 16u) in ^= 0x8000000000000000ULL;
         a ^= in;
+        // the next block's words are requested before the 24 rounds of this one: with one warp per scheduler nothing
+        // else would hide the load latency
+        if (b + 1 < nblocks) in = lane < 17u ? fs_block_lane(t, b + 1, (int)lane) : 0ull;
 #pragma unroll 1
         for (int round = 0; round < 24; round++) {
             const kw64 c = a ^ __shfl_sync(kFull, a, c1) ^ __shfl_sync(kFull, a, c2) ^ __shfl_sync(kFull, a, c3) ^ __shfl_sync(kFull, a, c4);
