@@ -119,3 +119,34 @@ def test_c_quotient_matches_the_schoolbook_python_restatement():
             assert [int(v) for v in got] == want + [0] * (m - len(want)), (q, m)
             bad = list(z); bad[3] = (bad[3] + 1) % q
             assert O.r1cs_quotient(m, cols, _triples(A), _triples(B), _triples(C), bad, q, om, Q.reference_root(q, 2 * m))[1] == 1
+
+
+def test_six_transform_identity_of_the_device_pipeline():
+    """The device pipeline never transforms C_z to the coset: Q = (C_z - N) / 2 with N = A_z * B_z mod (X^m + 1)
+    (DESIGN.md 4.7).  Checked here against the reference's own route (schoolbook product, long division by X^m - 1),
+    for satisfied witnesses; for an unsatisfied one (C_z - N) / 2 still equals what the seven-transform flow
+    ((a*b - c) * (-2)^-1 on the coset, inverse transform) produced, which is what the status flag accompanies."""
+    rng = random.Random(23)
+    for q in (P, Q.NTT_FRIENDLY_MODULUS):
+        inv2 = q // 2 + 1
+        assert (2 * inv2) % q == 1
+        for m in (2, 8, 64):
+            cols, A, B, C, z = mult_gates(m, q, rng)
+            w = Q.reference_root(q, m)
+            for witness in (z, [v if i != 3 else (v + 1) % q for i, v in enumerate(z)]):
+                ap, bp, cp = (Q.ntt_inverse(Q.mul_vec(m, M, witness, q), q, w) for M in (A, B, C))
+                prod = Q.poly_mul(ap, bp, q) + [0] * (2 * m)
+                nega = [(prod[i] - prod[i + m]) % q for i in range(m)]               # A_z * B_z mod (X^m + 1)
+                got = [((cp[i] - nega[i]) * inv2) % q for i in range(m)]
+                if witness is z:
+                    want = Q.compute_quotient_poly(m, A, B, C, z, q)
+                    assert got[:len(want)] == want and not any(got[len(want):])
+                else:
+                    # seven-transform statement: values of (A*B - C) * (-2)^-1 at psi^(2j+1), interpolated back
+                    psi = Q.reference_root(q, 2 * m)
+                    half = (q - 1) // 2
+                    assert (half * (q - 2)) % q == 1
+                    pts = [pow(psi, 2 * j + 1, q) for j in range(m)]
+                    vals = [((Q.horner(ap, x, q) * Q.horner(bp, x, q) - Q.horner(cp, x, q)) * half) % q for x in pts]
+                    # the unique polynomial of degree < m with these values on the coset is `got`
+                    assert [Q.horner(got, x, q) for x in pts] == vals
