@@ -208,6 +208,53 @@ def test_lean_export_formats_match_the_reference():
     assert lib.export_seal_pubkey_to_lean(None, buf, len(buf)) == -1
 
 
+def _gloo_prover_worker(rank, world, port, out_dir):
+    # BASELINE configs[4] on CPU: every rank forms the quotient of the same witness and commits ITS chunk range
+    # (seeds indexed by the global chunk number); the gathered containers must be the single-process result.
+    # The oracle stands in for the device; the GPU twin is test_prover_commit_phase_matches_oracle_and_is_shard_invariant.
+    import random
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle import oracle as O
+    from oracle import quotient as QO
+    from test_oracle_quotient import mult_gates
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    q, m, n, k = QO.NTT_MODULUS, 128, 16, 2
+    cols, A, B, Cm, z = mult_gates(m, q, random.Random(5))
+    quo = QO.compute_quotient_poly(m, A, B, Cm, z, q)
+    quo = quo + [0] * (m - len(quo))
+    chunks = m // n
+    lo, hi = sharding.shard_range(chunks, rank, world)
+    ctx = O.OracleLwe(Q0, n, k, 3.19, bytes(range(32)))
+    msgs = np.array(quo, dtype=np.uint64).reshape(chunks, n)
+    mine = ctx.commit_batch(msgs[lo:hi], sharding.global_seeds(0xC0FFEE, lo, hi))
+    local = torch.from_numpy(mine.view(np.int64))
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    if rank == 0:
+        np.save(Path(out_dir) / "prover_gathered.npy", sharding.gather_slices([g.numpy().view(np.uint64) for g in gathered]))
+        np.save(Path(out_dir) / "prover_msgs.npy", msgs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_prover_chunk_ranges(tmp_path):
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_gloo_prover_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "prover_gathered.npy")
+    msgs = np.load(tmp_path / "prover_msgs.npy")
+    ctx = O.OracleLwe(Q0, 16, 2, 3.19, bytes(range(32)))
+    want = ctx.commit_batch(msgs, sharding.global_seeds(0xC0FFEE, 0, msgs.shape[0]))
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 # ------------------------------------------------------------- Fiat-Shamir transcript hash
 def test_transcript_hash_source_matches_sha3_256(tmp_path):
     """csrc/lsr_keccak.h (the code fs_challenge_kernel runs, compiled here for the host) against hashlib on
