@@ -114,6 +114,10 @@ def test_null_and_invalid_arguments_need_no_gpu():
     assert lib.sample_gaussian(buf, 0, 3.2) == -1
     assert lib.sample_gaussian(buf, 16, 0.0) == -1
     assert lib.sample_gaussian(buf, 16, float("inf")) == -1
+    # extensions added for explicit-mode commitments and the Goldilocks probe: NULL arguments are refused up front
+    assert lib.lsr_lwe_commit_explicit(None, None, 4, None, None, 1, None) == -1
+    assert lib.lsr_lwe_commit_explicit_device(None, None, 4, None, None, 1, None, None) == -1
+    assert lib.lsr_goldilocks_probe_device(None, None, 4, None) == -1
 
 
 def test_missing_library_fails_loudly(tmp_path):
