@@ -123,9 +123,25 @@ void lwe_context_free(LweContext* ctx) LSR_NOEXCEPT;
 
 /* commitment.h:58-63 / commitment.cpp:138-164.  Message is padded with zeros
  * or silently truncated to ring_degree words (commitment.cpp:146-149).
- * seed == 0 draws fresh randomness (commitment.h:52 "0 = random"); any other
- * seed makes the commitment a deterministic function of (context, message,
- * seed).  NULL on NULL ctx / NULL message / failure.                        */
+ *
+ * MESSAGE RANGE.  The commitment binds every message word MODULO THE PLAINTEXT
+ * MODULUS p = lsr_lwe_plain_modulus(ctx) (204800 for the default q): the slot
+ * holds Delta * (word mod p).  A word >= p is NOT rejected by default, because
+ * the reference's callers pass field elements (44 .. 64 bits) and SEAL's
+ * BatchEncoder range check (commitment.cpp:152) exists in debug builds only;
+ * lwe_verify_opening accordingly compares with (word mod p).  Callers that
+ * need the whole word bound either commit its base-p digits
+ * (lsr_lwe_commit_digits_batch_device; lsr_prover_commit_quotient does so by
+ * itself) or switch the context to strict mode (lsr_lwe_set_strict_messages),
+ * in which a word >= p makes lwe_commit return NULL, as SEAL's debug build does.
+ *
+ * SEED.  seed == 0 draws fresh randomness (commitment.h:52 "0 = random"); any
+ * other seed makes the commitment a deterministic function of (context,
+ * message, seed): s and e depend on (context key, seed) ONLY, so two messages
+ * committed under one non-zero seed differ by exactly Delta * (m1 - m2) in the
+ * last row -- never reuse a non-zero seed for different messages (the
+ * reference ignores the argument and always randomises).
+ * NULL on NULL ctx / NULL message / failure.                                */
 LweCommitment* lwe_commit(LweContext* ctx, const uint64_t* message, size_t msg_len,
                           uint64_t seed) LSR_NOEXCEPT;
 
@@ -137,7 +153,9 @@ LweCommitment* lwe_commitment_clone(const LweCommitment* comm) LSR_NOEXCEPT;
 
 /* commitment.h:94-100 / commitment.cpp:200-232.  Opens the commitment with the
  * context's trapdoor (the reference decrypts with the SEAL secret key) and
- * compares the first msg_len decoded words with `message` in constant time.
+ * compares the first msg_len decoded words with `message` mod p (see lwe_commit,
+ * MESSAGE RANGE); the differences are OR-folded without a branch on the data,
+ * as commitment.cpp:223-226 does.
  * `opening` is ignored, as in the reference (commitment.cpp:205).
  * 1 = match, 0 = mismatch (also msg_len > ring_degree), -1 = NULL argument
  * or malformed container.                                                  */
@@ -145,8 +163,15 @@ int lwe_verify_opening(const LweContext* ctx, const LweCommitment* commitment,
                        const uint64_t* message, size_t msg_len,
                        const LweOpening* opening) LSR_NOEXCEPT;
 
-/* commitment.h:113-118 / commitment.cpp:234-276.  sum_i (coeffs[i] mod p) * C_i,
- * p = plaintext modulus (commitment.cpp:90 reduces coefficients the same way).
+/* commitment.h:113-118 / commitment.cpp:234-276.  sum_i c'_i * C_i with c'_i the
+ * centred representative of coeffs[i] mod p, p = plaintext modulus
+ * (commitment.cpp:90 reduces coefficients mod the plain modulus; the result
+ * commits to sum_i coeffs[i] * m_i mod p either way).
+ * COEFFICIENT BOUND.  With a 44-bit ring modulus the noise budget is small: the
+ * result opens correctly while sum_i |c'_i| <= lsr_lwe_lincomb_budget(ctx)
+ * (about 3 * 10^3 for n = 4096, k = 2, sigma = 3.19; inputs assumed fresh).
+ * Beyond that the call returns NULL instead of an undecodable commitment
+ * (the reference, with a 109-bit ciphertext modulus, accepts any coefficient).
  * NULL entries of `commitments` are skipped; NULL result on NULL arguments,
  * count == 0, a malformed container, or when every entry was NULL.          */
 LweCommitment* lwe_linear_combine(const LweContext* ctx, const LweCommitment** commitments,
@@ -306,16 +331,22 @@ int lsr_r1cs_quotient_batch(void* r1cs, const uint64_t* witnesses, size_t witnes
 /* Commitment phase of the prover for a circuit larger than one ring element (BASELINE configs[4]; replaces
  * compute_quotient_poly + Commitment::new of prove_r1cs, rust-api/lambda-snark/src/lib.rs:747-757, where the
  * reference silently truncates Q to ring_degree coefficients -- cpp-core/src/commitment.cpp:146-149).
- * The quotient of every witness is cut into chunks = max(1, m / ring_degree) messages of ring_degree coefficients
- * (one message of m coefficients when m < ring_degree); message (w, j) is committed with seeds[w * chunks + j]
- * exactly as lwe_commit_batch would commit it.  Only chunk indices [chunk_lo, chunk_hi) are committed -- a rank's
+ * The quotient of every witness is cut into max(1, m / ring_degree) ring elements of ring_degree coefficients
+ * (one of m coefficients when m < ring_degree), and every ring element into L = lsr_prover_quotient_planes()
+ * DIGIT PLANES: a commitment binds its words modulo p only (lwe_commit, MESSAGE RANGE), so the field elements are
+ * committed as their L = ceil(log_p(field modulus)) base-p digits (4 for Goldilocks, 3 for a 44-bit field), which
+ * together bind the whole quotient.  A unit is a (ring element j, plane l) pair, unit index u = j * L + l;
+ * lsr_prover_quotient_chunks() returns the number of units per witness (called `chunks` below); unit (w, u) is
+ * committed with seeds[w * chunks + u] exactly as lwe_commit_batch would commit the digit row
+ * (Q_j[x] / p^l) mod p.  Only unit indices [chunk_lo, chunk_hi) are committed -- a rank's
  * slice of a job sharded over GPUs; seeds is always indexed globally ([count][chunks]) so the containers do not
  * depend on the sharding.  Quotient and messages never leave the device.
  * out: [count][chunk_hi - chunk_lo][1 + k n] words; status[count]: 0 ok, 1 witness does not satisfy the
  * constraints (its containers are then commitments to a meaningless quotient and must be discarded).
  * Returns a LambdaSnarkError code.  _device: witnesses, seeds and out are DEVICE pointers on the context's
  * device (status stays on the host); the call synchronises before returning.                                  */
-size_t lsr_prover_quotient_chunks(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT;
+size_t   lsr_prover_quotient_chunks(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT;
+uint32_t lsr_prover_quotient_planes(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT;   /* 0: more than 4 would be needed */
 int lsr_prover_commit_quotient(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len,
                                size_t count, uint64_t omega, const uint64_t* seeds, size_t chunk_lo,
                                size_t chunk_hi, uint64_t* out, int* status) LSR_NOEXCEPT;
@@ -335,7 +366,17 @@ int lsr_prover_commit_quotient_device(void* r1cs, LweContext* ctx, const uint64_
  *   (chain == 0 leaves those zero).  hashes is [count][2][4] 64-bit little-endian lanes = [count][2][32] bytes.
  * lsr_poly_eval_batch: out[p][j] = sum_i coeffs[p][i] * points[p][j]^i mod modulus (modulus < 2^61 or Goldilocks).
  * lsr_prove_r1cs_batch: prove_r1cs for `count` witnesses of one circuit with m <= ring_degree constraints,
- *   interpolation over the roots of unity (the NTT path of the reference): per witness the commitment container
+ *   interpolation over the roots of unity (the NTT path of the reference).
+ *   DOMAIN RESTRICTION: H is always the m-th roots of unity, Z_H = X^m - 1, m a power of two with 2m | modulus - 1.
+ *   The reference takes that path only when should_use_ntt() holds (modulus == Goldilocks NTT_MODULUS and m a power
+ *   of two, r1cs.rs:386-389); for every other modulus it interpolates over H = {0..m-1} with Z_H = prod (X - i), and
+ *   proofs / verdicts of the two domains do not interoperate.  So: with the Goldilocks modulus this is the reference's
+ *   proof; with any other NTT-friendly modulus it is the same protocol over a different evaluation domain (prover and
+ *   verifier of THIS library agree with each other, not with the reference's baseline-domain verifier).  The same holds
+ *   for lsr_verify_r1cs_batch and lsr_r1cs_quotient*.
+ *   The single commitment of the reference's proof format (ProofR1CS::commitment_q) binds Q modulo p, like the
+ *   reference's own 20-bit BFV plaintext; lsr_prover_commit_quotient commits digit planes instead.
+ *   Per witness the commitment container
  *   ([1 + k n] words, seed seeds[w]), challenges (alpha, beta), the two transcript hashes, and evals[w][8] =
  *   {Q(alpha), Q(beta), A_z(alpha), B_z(alpha), C_z(alpha), A_z(beta), B_z(beta), C_z(beta)} -- the field order of
  *   ProofR1CS::new (lib.rs:795-809; the two openings are Q(alpha), Q(beta) again).  status[w] = 1 marks a witness
@@ -389,6 +430,23 @@ int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, siz
                                 const uint64_t* d_seeds, size_t count, uint64_t* d_out_words,
                                 void* stream) LSR_NOEXCEPT;
 
+/* Digit planes: binds whole 64-bit message words.  Every message row is committed as `planes` (1..4) commitments,
+ * unit (i, l) = i * planes + l holding the base-p digits (messages[i][x] / p^l) mod p under d_seeds[i * planes + l];
+ * d_out_words: [count * planes][1 + k*n].  lsr_lwe_message_planes(ctx, modulus) = smallest L with p^L >= modulus
+ * (0 if more than 4).  DEVICE memory, asynchronous on `stream`.                                                   */
+int lsr_lwe_commit_digits_batch_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len,
+                                       const uint64_t* d_seeds, size_t count, uint32_t planes,
+                                       uint64_t* d_out_words, void* stream) LSR_NOEXCEPT;
+uint32_t lsr_lwe_message_planes(const LweContext* ctx, uint64_t modulus) LSR_NOEXCEPT;
+
+/* Strict message range for the HOST-pointer entry points (lwe_commit, lwe_commit_batch, lwe_verify_opening*):
+ * a message word >= p makes the commit calls fail (NULL / -1) and a verification answer 0 -- SEAL's debug-build
+ * behaviour (BatchEncoder::encode throws, commitment.cpp:152,158).  Default 0 (words are reduced mod p).        */
+int lsr_lwe_set_strict_messages(LweContext* ctx, int strict) LSR_NOEXCEPT;
+
+/* Largest sum of |centred coefficients| lwe_linear_combine accepts (see there). */
+uint64_t lsr_lwe_lincomb_budget(const LweContext* ctx) LSR_NOEXCEPT;
+
 /* Explicit mode: t = A*s + e + Delta*m for CALLER-SUPPLIED s, e instead of
  * sampled ones -- the parity entry (any s, e can be put through the kernels and compared with the
  * oracle) and the way to commit under externally generated randomness.  s, e: [count][k][n]
@@ -418,9 +476,10 @@ int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
 /* Test hook: CDT magnitude #{k : cdf[k] < u[i]} evaluated on the device for caller-chosen
  * u (boundary cases the keystream never reaches).  variant 0 = linear scan of the table in
  * global memory (generic path), 1 = unrolled scan of the by-value table, 2 = warp-shuffle
- * binary search over the first 31 entries + tail scan, 3 = the fused kernel's search: the
- * compact borrow-chain search over the distinct table values when there are at most 31 of
- * them, else variant 2.  HOST memory.                                                  */
+ * binary search over the first 31 entries + tail scan, 3 = the compact carry-chain search
+ * over the distinct table values when there are at most 31 of them, else variant 2,
+ * 4 = the fused kernel's decision: 25-bit prefix search, and variant 3 for the whole warp
+ * when some lane's prefix ties with a table prefix.  HOST memory.                      */
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out,
                              int variant) LSR_NOEXCEPT;
 

@@ -4,6 +4,11 @@ Produces lambda_snark_r_b200/lib/liblambda_snark_core.so (what ctypes / a C
 harness loads) and liblambda_snark_core.a (what lambda-snark-sys would link;
 same name as the reference's static library, cpp-core/CMakeLists.txt:107).
 Objects are rebuilt only when a source or header is newer.
+
+`python -m lambda_snark_r_b200._build --profiling` builds a SECOND library,
+lib/liblambda_snark_core_prof.so, with -DLSR_PROFILING: the only build in which
+the phase-skip / kernel-selection switches of tools/ exist (LSR_FUSED_SKIP,
+LSR_NTT_COLUMN2, LSR_FS_KERNEL).  The shipped library reads no environment.
 """
 from __future__ import annotations
 
@@ -45,15 +50,15 @@ def _newest_header() -> float:
     return max(h.stat().st_mtime for h in hs)
 
 
-def _compile(src: str, force: bool, verbose: bool) -> Path:
+def _compile(src: str, force: bool, verbose: bool, objdir: Path = OBJ, extra: tuple = ()) -> Path:
     s = CSRC / src
-    o = OBJ / (s.stem + ".o")
+    o = objdir / (s.stem + ".o")
     stamp = max(s.stat().st_mtime, _newest_header(), Path(__file__).stat().st_mtime)
     if not force and o.exists() and o.stat().st_mtime >= stamp:
         return o
-    cmd = [_nvcc(), *_flags(), "-x", "cu" if s.suffix == ".cu" else "c++", "-c", str(s), "-o", str(o)]
+    cmd = [_nvcc(), *_flags(), *extra, "-x", "cu" if s.suffix == ".cu" else "c++", "-c", str(s), "-o", str(o)]
     if s.suffix != ".cu":
-        cmd = [_nvcc(), *_flags(), "-c", str(s), "-o", str(o)]
+        cmd = [_nvcc(), *_flags(), *extra, "-c", str(s), "-o", str(o)]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -82,6 +87,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return SO
 
 
+def build_profiling(force: bool = False, verbose: bool = False) -> Path:
+    """tools/ only: the library with the profiling switches compiled in (never loaded by the package itself)."""
+    objdir = PKG / "_build_prof"
+    objdir.mkdir(exist_ok=True)
+    LIB.mkdir(exist_ok=True)
+    so = LIB / "liblambda_snark_core_prof.so"
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force, verbose, objdir, ("-DLSR_PROFILING",)), SOURCES))
+    if force or not so.exists() or so.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+        cmd = [_nvcc(), "-shared", *ARCH, "-ccbin", shutil.which("g++") or "g++", "-cudart", "static",
+               "-o", str(so), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return so
+
+
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose=True)
-    print("built", p)
+    if "--profiling" in sys.argv:
+        print("built", build_profiling(force="--force" in sys.argv, verbose=True))
+    else:
+        print("built", build(force="--force" in sys.argv, verbose=True))

@@ -227,13 +227,18 @@ class R1CS:
         return self
 
     def quotient_chunks(self, ctx: "LweContext") -> int:
+        """Commitment units per witness: ring elements of the quotient x digit planes."""
         return int(_lib().lsr_prover_quotient_chunks(self._h, ctx.as_ptr()))
+
+    def quotient_planes(self, ctx: "LweContext") -> int:
+        return int(_lib().lsr_prover_quotient_planes(self._h, ctx.as_ptr()))
 
     def commit_quotient(self, ctx: "LweContext", witnesses, seeds, chunk_lo: int = 0, chunk_hi: int | None = None,
                         omega: int = 0):
         """Commitment phase of prove_r1cs (lib.rs:747-757) for quotients longer than one ring element:
-        witnesses [count][cols], seeds [count][chunks] (global chunk index) -> (containers
-        [count][chunk_hi - chunk_lo][1 + k n], status [count]).  Q stays on the device."""
+        witnesses [count][cols], seeds [count][chunks] (global unit index; a unit is one digit plane of one ring
+        element of Q, sharding.message_digits order) -> (containers [count][chunk_hi - chunk_lo][1 + k n],
+        status [count]).  Q stays on the device."""
         import ctypes as C_
         w = np.ascontiguousarray(_u64(witnesses)).reshape(-1, self.cols)
         chunks = self.quotient_chunks(ctx)
@@ -380,6 +385,25 @@ class LweContext:
     def set_commit_path(self, path: int) -> None:
         if _lib().lsr_lwe_set_commit_path(self._h, path) != 0:
             raise LambdaSnarkError("lsr_lwe_set_commit_path failed")
+
+    def set_strict_messages(self, strict: bool) -> None:
+        """Host-pointer calls reject message words >= p instead of reducing them (lsr_lwe_set_strict_messages)."""
+        if _lib().lsr_lwe_set_strict_messages(self._h, 1 if strict else 0) != 0:
+            raise LambdaSnarkError("lsr_lwe_set_strict_messages failed")
+
+    def lincomb_budget(self) -> int:
+        """Largest sum of |centred coefficients| lwe_linear_combine accepts."""
+        return int(_lib().lsr_lwe_lincomb_budget(self._h))
+
+    def message_planes(self, modulus: int) -> int:
+        """Base-p digit planes that bind a whole element of Z_modulus (0: more than 4)."""
+        return int(_lib().lsr_lwe_message_planes(self._h, modulus))
+
+    def commit_digits_batch_device(self, msgs_ptr: int, msg_len: int, seeds_ptr: int, count: int, planes: int,
+                                   out_ptr: int, stream: int = 0) -> None:
+        if _lib().lsr_lwe_commit_digits_batch_device(self._h, C.c_void_p(msgs_ptr), msg_len, C.c_void_p(seeds_ptr), count,
+                                                     planes, C.c_void_p(out_ptr), C.c_void_p(stream)) != 0:
+            raise LambdaSnarkError(f"lsr_lwe_commit_digits_batch_device failed: {last_error()}")
 
     def matrix(self) -> np.ndarray:
         out = np.zeros((self.k, self.k, self.n), dtype=np.uint64)

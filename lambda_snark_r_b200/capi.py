@@ -107,6 +107,12 @@ SIGNATURES = {
     "lsr_r1cs_quotient": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_uint64, u64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lsr_r1cs_quotient_batch": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p, C.POINTER(C.c_int)]),
     "lsr_prover_quotient_chunks": (C.c_size_t, [C.c_void_p, C.c_void_p]),
+    "lsr_prover_quotient_planes": (C.c_uint32, [C.c_void_p, C.c_void_p]),
+    "lsr_lwe_set_strict_messages": (C.c_int, [C.c_void_p, C.c_int]),
+    "lsr_lwe_lincomb_budget": (C.c_uint64, [C.c_void_p]),
+    "lsr_lwe_message_planes": (C.c_uint32, [C.c_void_p, C.c_uint64]),
+    "lsr_lwe_commit_digits_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32,
+                                                     C.c_void_p, C.c_void_p]),
     "lsr_prover_commit_quotient": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_size_t, C.c_size_t, C.c_uint64, u64p,
                                             C.c_size_t, C.c_size_t, u64p, C.POINTER(C.c_int)]),
     "lsr_prover_commit_quotient_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,

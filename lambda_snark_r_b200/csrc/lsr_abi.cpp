@@ -187,10 +187,15 @@ LambdaSnarkError lsr_r1cs_quotient(void* r1cs, const uint64_t* witness, size_t w
     LSR_CATCH(LAMBDA_SNARK_ERR_CRYPTO_FAILED)
 }
 
+uint32_t lsr_prover_quotient_planes(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT {
+    if (!r1cs || !ctx) return 0;
+    return lsr::message_planes(ctx->p, static_cast<const lsr::R1csHandle*>(r1cs)->q);
+}
+
 size_t lsr_prover_quotient_chunks(void* r1cs, const LweContext* ctx) LSR_NOEXCEPT {
     if (!r1cs || !ctx) return 0;
     const lsr::R1csHandle* h = static_cast<const lsr::R1csHandle*>(r1cs);
-    return h->rows <= ctx->n ? 1 : (size_t)h->rows / ctx->n;
+    return (h->rows <= ctx->n ? 1 : (size_t)h->rows / ctx->n) * lsr::message_planes(ctx->p, h->q);
 }
 
 static int prover_commit_impl(void* r1cs, LweContext* ctx, const uint64_t* witnesses, size_t witness_len, size_t count,
@@ -365,6 +370,27 @@ int lsr_lwe_copy_matrix(const LweContext* ctx, uint64_t* out) LSR_NOEXCEPT {
     LSR_CATCH(-1)
 }
 
+int lsr_lwe_set_strict_messages(LweContext* ctx, int strict) LSR_NOEXCEPT {
+    if (!ctx) return -1;
+    ctx->strict_messages = strict ? 1 : 0;
+    return 0;
+}
+
+uint64_t lsr_lwe_lincomb_budget(const LweContext* ctx) LSR_NOEXCEPT { return ctx ? lsr::lincomb_budget(ctx) : 0; }
+
+uint32_t lsr_lwe_message_planes(const LweContext* ctx, uint64_t modulus) LSR_NOEXCEPT {
+    return ctx ? lsr::message_planes(ctx->p, modulus) : 0;
+}
+
+// strict mode: the first min(msg_len, n) words of every message must be below p
+static bool messages_in_range(const LweContext* ctx, const uint64_t* messages, size_t msg_len, size_t count) {
+    const size_t used = msg_len < ctx->n ? msg_len : ctx->n;
+    for (size_t i = 0; i < count; i++)
+        for (size_t x = 0; x < used; x++)
+            if (messages[i * msg_len + x] >= ctx->p) return false;
+    return true;
+}
+
 int lsr_lwe_set_commit_path(LweContext* ctx, int path) LSR_NOEXCEPT {
     if (!ctx || path < 0 || path > 2) return -1;
     ctx->commit_path = path;
@@ -391,6 +417,11 @@ int lsr_lwe_set_arith(LweContext* ctx, int arith) LSR_NOEXCEPT {
 LweCommitment* lwe_commit(LweContext* ctx, const uint64_t* message, size_t msg_len, uint64_t seed) LSR_NOEXCEPT {
     LSR_TRY
     if (!ctx || !message) return nullptr;                 // commitment.cpp:144
+    if (ctx->strict_messages && !messages_in_range(ctx, message, msg_len, 1)) {
+        // BatchEncoder::encode rejects values >= plain_modulus (SEAL debug builds) -> exception -> NULL (commitment.cpp:158)
+        lsr::set_error("lwe_commit: message word >= plaintext modulus (strict mode)");
+        return nullptr;
+    }
     if (seed == 0) {                                      // commitment.h:52 "0 = random"
         uint8_t buf[8];
         do {
@@ -415,6 +446,10 @@ int lwe_commit_batch(LweContext* ctx, const uint64_t* messages, size_t msg_len, 
                      size_t count, uint64_t* out_words) LSR_NOEXCEPT {
     LSR_TRY
     if (!ctx || !seeds || !out_words || (!messages && msg_len)) return -1;
+    if (ctx->strict_messages && msg_len && !messages_in_range(ctx, messages, msg_len, count)) {
+        lsr::set_error("lwe_commit_batch: message word >= plaintext modulus (strict mode)");
+        return -1;
+    }
     return lsr::lwe_commit_host(ctx, reinterpret_cast<const u64*>(messages), msg_len,
                                 reinterpret_cast<const u64*>(seeds), count, reinterpret_cast<u64*>(out_words)) ? 0 : -1;
     LSR_CATCH(-1)
@@ -428,6 +463,18 @@ int lsr_lwe_commit_batch_device(LweContext* ctx, const uint64_t* d_messages, siz
     return lsr::lwe_commit_launch(ctx, reinterpret_cast<const u64*>(d_messages), msg_len,
                                   reinterpret_cast<const u64*>(d_seeds), count,
                                   reinterpret_cast<u64*>(d_out_words), static_cast<cudaStream_t>(stream)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
+int lsr_lwe_commit_digits_batch_device(LweContext* ctx, const uint64_t* d_messages, size_t msg_len,
+                                       const uint64_t* d_seeds, size_t count, uint32_t planes, uint64_t* d_out_words,
+                                       void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d_seeds || !d_out_words || (!d_messages && msg_len)) return -1;
+    if (planes < 1 || planes > 4 || count > (SIZE_MAX / planes)) { lsr::set_error("digit planes must be 1..4"); return -1; }
+    return lsr::lwe_commit_launch(ctx, reinterpret_cast<const u64*>(d_messages), msg_len,
+                                  reinterpret_cast<const u64*>(d_seeds), count * planes,
+                                  reinterpret_cast<u64*>(d_out_words), static_cast<cudaStream_t>(stream), planes, 0) ? 0 : -1;
     LSR_CATCH(-1)
 }
 
@@ -473,6 +520,7 @@ int lwe_verify_opening(const LweContext* ctx, const LweCommitment* commitment, c
     if (!ctx || !commitment || !message) return -1;       // commitment.cpp:207
     if (!container_ok(ctx, commitment)) return -1;        // :210-212
     if (msg_len > ctx->n) return 0;                       // :219-221
+    if (ctx->strict_messages && !messages_in_range(ctx, message, msg_len, 1)) return 0;   // no commitment to such a word exists
     int result = -1;
     if (!lsr::lwe_verify_host(ctx, reinterpret_cast<const u64*>(commitment->data),
                               reinterpret_cast<const u64*>(message), msg_len, 1, &result)) return -1;
@@ -484,8 +532,12 @@ int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words, 
                              size_t msg_len, size_t count, int* results) LSR_NOEXCEPT {
     LSR_TRY
     if (!ctx || !comm_words || !results || (!messages && msg_len)) return -1;
-    return lsr::lwe_verify_host(ctx, reinterpret_cast<const u64*>(comm_words),
-                                reinterpret_cast<const u64*>(messages), msg_len, count, results) ? 0 : -1;
+    if (!lsr::lwe_verify_host(ctx, reinterpret_cast<const u64*>(comm_words),
+                              reinterpret_cast<const u64*>(messages), msg_len, count, results)) return -1;
+    if (ctx->strict_messages && msg_len)
+        for (size_t i = 0; i < count; i++)
+            if (results[i] == 1 && !messages_in_range(ctx, messages + i * msg_len, msg_len, 1)) results[i] = 0;
+    return 0;
     LSR_CATCH(-1)
 }
 
@@ -531,7 +583,7 @@ int lsr_goldilocks_probe_device(const uint64_t* a, const uint64_t* b, size_t cou
 
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out, int variant) LSR_NOEXCEPT {
     LSR_TRY
-    if (!u || !out || count == 0 || variant < 0 || variant > 3) return -1;
+    if (!u || !out || count == 0 || variant < 0 || variant > 4) return -1;
     return lsr::cdt_probe_host(sigma, reinterpret_cast<const u64*>(u), count, out, variant) ? 0 : -1;
     LSR_CATCH(-1)
 }

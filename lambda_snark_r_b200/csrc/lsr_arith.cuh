@@ -265,6 +265,17 @@ __device__ __forceinline__ u32 mod_small(u64 m, u32 p, u64 pinv) {
     return r;
 }
 
+// floor(v / d) for any u64 v and a divisor 2 <= d < 2^63, dinv = floor((2^64-1)/d): the estimate
+// umulhi(v, dinv) is at most 1 short (v/d - v*dinv/2^64 <= v/2^64 < 1), two fix-ups for good measure.
+// Digit planes of the commitment messages: d = p^l.
+__device__ __forceinline__ u64 div_small(u64 v, u64 d, u64 dinv) {
+    u64 qh = __umul64hi(v, dinv);
+    u64 r = v - qh * d;
+    if (r >= d) { r -= d; ++qh; }
+    if (r >= d) { ++qh; }
+    return qh;
+}
+
 // modular add/sub on canonical residues
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }

@@ -9,6 +9,7 @@
 // lsr_commit_fused.cu holds the single-kernel fused path used for the
 // headline configuration.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -21,8 +22,12 @@
 namespace lsr {
 
 bool fused_commit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
-                         size_t count, u64* d_out, cudaStream_t stream);   // lsr_commit_fused.cu
+                         size_t count, u64* d_out, cudaStream_t stream, uint32_t planes, size_t unit0);   // lsr_commit_fused.cu
 bool fused_prepare(LweContext* ctx, cudaStream_t stream);                  // lsr_commit_fused.cu
+
+// commitments per pipeline slot of the host-pointer path: 444 = three fused CTAs on each of the 148 SMs, one full
+// wave per launch (28 MiB of containers at n = 4096, k = 2)
+constexpr size_t kCommitHostChunk = 444;
 
 static ChaChaKey make_key(const LweContext* c) {
     ChaChaKey k;
@@ -32,8 +37,10 @@ static ChaChaKey make_key(const LweContext* c) {
 
 // ---------------------------------------------------------------------------
 // generic K7-in-K4: one thread per (commitment, 16-coefficient chunk).
-// Randomness layout of DESIGN.md 3.3: block b = 2P + (j>>3) gives the 64-bit
-// u of coefficient j of polynomial P; block 4k bit 16P + j gives its sign.
+// Randomness layout of DESIGN.md 3.3: word j of block P is the sign draw (bit 0) and the top 31 bits of the
+// magnitude draw of coefficient j of polynomial P; the low 33 bits come from the refinement blocks
+// 0x100 | (2P + (j>>3)).  This path always forms the full 64-bit draw (the fused kernel fetches the refinement
+// only when the top bits tie with a table entry).
 // s -> S[b][P][n] as residues, e -> out payload (finalize adds the rest).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -47,23 +54,22 @@ sample_se_kernel(const ChaChaKey key, const u64* __restrict__ cdf, u32 cdf_n, u6
     const u32 tau = (u32)(idx % chunks);
     const u64 seed = seeds[b];
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
-    u32 sg[16];
-    chacha_block(key, s_lo, s_hi, tau, kDomCommit | (4u * k), sg);
     for (u32 P = 0; P < 2 * k; P++) {
         // chunk tau = the 16 coefficients tau + (n/16) j
         u64* dst = (P < k) ? S + ((b * k + P) * (size_t)n) + tau
                            : out + b * out_stride + 1 + (size_t)(P - k) * n + tau;
-        const u32 sbits = sg[P >> 1] >> ((P & 1) * 16);
+        u32 x[16];
+        chacha_block(key, s_lo, s_hi, tau, kDomCommit | P, x);
 #pragma unroll
         for (u32 h = 0; h < 2; h++) {
-            u32 x[16];
-            chacha_block(key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
+            u32 f[16];
+            chacha_block(key, s_lo, s_hi, tau, kDomCommit | kDomCommitFine | (2u * P + h), f);
 #pragma unroll
             for (u32 w = 0; w < 8; w++) {
-                const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
-                const u32 mag = cdt_magnitude_global(cdf, cdf_n, u);
                 const u32 j = 8 * h + w;
-                dst[(size_t)j * chunks] = signed_residue(mag, (sbits >> j) & 1u, q);
+                const u64 u = commit_draw(x[j], f[2 * w], f[2 * w + 1]);
+                const u32 mag = cdt_magnitude_global(cdf, cdf_n, u);
+                dst[(size_t)j * chunks] = signed_residue(mag, x[j] & 1u, q);
             }
         }
     }
@@ -109,11 +115,12 @@ matvec_kernel(const ModParams mp, const u64* __restrict__ A, u32 n, u32 k, size_
     }
 }
 
-// out[b] = [k*n*8, S[b] + e (already in out) + [i==k-1] Delta*(m mod p)]
+// out[b] = [k*n*8, S[b] + e (already in out) + [i==k-1] Delta*(digit of m)], digit = (m / p^plane) mod p for
+// unit g = unit0 + b: message row g / planes, plane g % planes (planes = 1: m mod p)
 __global__ void __launch_bounds__(256)
 finalize_kernel(const ModParams mp, u64 delta, u64 p, u32 n, u32 k, const u64* __restrict__ S,
                 const u64* __restrict__ msgs, size_t msg_len, size_t count, u64* __restrict__ out,
-                size_t out_stride) {
+                size_t out_stride, u32 planes, size_t unit0) {
     const size_t kn = (size_t)k * n;
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count * kn) return;
@@ -124,7 +131,10 @@ finalize_kernel(const ModParams mp, u64 delta, u64 p, u32 n, u32 k, const u64* _
     u64 v = addmod(S[idx], o[1 + r], mp.q);
     const size_t x = r - (size_t)(k - 1) * n;          // coefficient index if last row
     if (r >= (size_t)(k - 1) * n && x < msg_len) {     // msg_len already clamped to n
-        const u64 m = msgs[b * msg_len + x] % p;
+        const size_t unit = unit0 + b;
+        u64 word = msgs[(unit / planes) * msg_len + x];
+        for (u32 l = (u32)(unit % planes); l > 0; l--) word /= p;
+        const u64 m = word % p;
         v = addmod(v, mulmod_exact(delta, m, mp), mp.q);
     }
     o[1 + r] = v;
@@ -187,19 +197,26 @@ verify_decode_kernel(u64 q, u64 delta, u64 p, u32 n, u32 k, const u64* __restric
     if (last >= q) last = 0;                                  // flagged invalid elsewhere
     const u64 v = addmod(U[b * (size_t)n + x], last, q);
     const u64 d = ((v + delta / 2) / delta) % p;
-    const u64 df = d ^ msgs[b * msg_len + x];
-    if (df) atomicOr(diff + b, (unsigned long long)df);
+    // the commitment binds message words modulo p (lambda_snark_b200.h, lwe_commit): compare with m mod p.
+    // No branch on the outcome (commitment.cpp:223-226 folds the differences the same way).
+    const u64 df = d ^ (msgs[b * msg_len + x] % p);
+    atomicOr(diff + b, (unsigned long long)df);
 }
 
-// K5: out[x] = sum_i (c_i mod p) * t_i[x] mod q  (commitment.cpp:257-265)
+// K5: out[x] = sum_i c'_i * t_i[x] mod q, c'_i the CENTRED representative of c_i mod p (commitment.cpp:90 reduces the
+// coefficient mod the plain modulus; the centred lift keeps the noise growth at |c'| <= p/2 instead of c < p, and
+// Delta * p = -1 (mod q) makes c and c - p act identically on the message up to one unit of noise per message unit)
 __global__ void __launch_bounds__(256)
 lincomb_kernel(const ModParams mp, u64 p, size_t kn, const u64* __restrict__ payloads,
                const u64* __restrict__ coeffs, size_t count, u64* __restrict__ out) {
     const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= kn) return;
     u64 acc = 0;
-    for (size_t i = 0; i < count; i++)
-        acc = addmod(acc, mulmod_exact(coeffs[i] % p, payloads[i * kn + x], mp), mp.q);
+    for (size_t i = 0; i < count; i++) {
+        const u64 c = coeffs[i] % p;
+        const u64 cr = c <= p / 2 ? c : mp.q - (p - c);
+        acc = addmod(acc, mulmod_exact(cr, payloads[i * kn + x], mp), mp.q);
+    }
     out[x] = acc;
 }
 
@@ -304,41 +321,50 @@ void lwe_destroy(LweContext* c) {
 }
 
 // ------------------------------------------------------------------- generic
+// Scratch S is allocated and freed in stream order (cudaMallocAsync), so concurrent device-pointer calls on one
+// context -- which do not take ctx->mu, they only enqueue -- never share or resize a buffer under a running kernel.
 static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
                                   const u64* d_seeds, size_t count, u64* d_out, cudaStream_t s,
-                                  const long long* d_s = nullptr, const long long* d_e = nullptr) {
+                                  const long long* d_s = nullptr, const long long* d_e = nullptr,
+                                  uint32_t planes = 1, size_t unit0 = 0) {
     const uint32_t n = c->n, k = c->k;
     const size_t words = lwe_words(c);
-    const size_t L = std::min<size_t>(msg_len, n);
     // scratch S: chunk so it stays <= 1 GiB
     const size_t per = (size_t)k * n * sizeof(u64);
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)1 << 30) / per));
-    if (!c->scratch[0].reserve(chunk * per)) return false;
-    u64* S = static_cast<u64*>(c->scratch[0].ptr);
+    void* Sv = nullptr;
+    if (!cuda_ok(cudaMallocAsync(&Sv, chunk * per, s), "cudaMallocAsync(S)")) return false;
+    u64* S = static_cast<u64*>(Sv);
     const ChaChaKey key = make_key(c);
-    for (size_t done = 0; done < count; done += chunk) {
+    bool ok = true;
+    for (size_t done = 0; ok && done < count; done += chunk) {
         const size_t cnt = std::min(chunk, count - done);
         u64* out = d_out + done * words;
         if (d_s) {
             load_se_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->q, (size_t)k * n, d_s + done * k * n, d_e + done * k * n,
                                                                      cnt, S, out, words);
-            if (!cuda_ok(cudaGetLastError(), "load_se_kernel")) return false;
+            ok = cuda_ok(cudaGetLastError(), "load_se_kernel");
         } else {
             sample_se_kernel<<<grid_for(cnt * (n >> 4), 128), 128, 0, s>>>(key, c->d_cdf, (u32)c->cdf.size(), c->q, n, k,
                                                                           d_seeds + done, cnt, S, out, words);
-            if (!cuda_ok(cudaGetLastError(), "sample_se_kernel")) return false;
+            ok = cuda_ok(cudaGetLastError(), "sample_se_kernel");
         }
-        if (!ntt_forward_launch(c->ntt, S, cnt * k, s)) return false;
-        matvec_kernel<16><<<grid_for(cnt * n, 256), 256, 0, s>>>(c->ntt->mp, c->d_A, n, k, cnt, S);
-        if (!cuda_ok(cudaGetLastError(), "matvec_kernel")) return false;
-        if (!ntt_inverse_launch(c->ntt, S, cnt * k, s)) return false;
-        // messages are addressed with their true stride msg_len; only the first L words are used
-        finalize_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->ntt->mp, c->delta, c->p, n, k, S,
-                                                                  d_msgs + done * msg_len, msg_len, cnt, out, words);
-        if (!cuda_ok(cudaGetLastError(), "finalize_kernel")) return false;
-        (void)L;
+        ok = ok && ntt_forward_launch(c->ntt, S, cnt * k, s);
+        if (ok) {
+            matvec_kernel<16><<<grid_for(cnt * n, 256), 256, 0, s>>>(c->ntt->mp, c->d_A, n, k, cnt, S);
+            ok = cuda_ok(cudaGetLastError(), "matvec_kernel");
+        }
+        ok = ok && ntt_inverse_launch(c->ntt, S, cnt * k, s);
+        if (ok) {
+            // messages are addressed with their true stride msg_len; only the first min(msg_len, n) words are used.
+            // With digit planes the message row of a commitment follows from its unit index, so the base stays put.
+            const u64* mbase = planes > 1 ? d_msgs : d_msgs + done * msg_len;
+            finalize_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->ntt->mp, c->delta, c->p, n, k, S, mbase, msg_len, cnt,
+                                                                      out, words, planes, planes > 1 ? unit0 + done : 0);
+            ok = cuda_ok(cudaGetLastError(), "finalize_kernel");
+        }
     }
-    return true;
+    return cuda_ok(cudaFreeAsync(Sv, s), "cudaFreeAsync(S)") && ok;
 }
 
 // explicit mode: s, e supplied by the caller (device pointers, [count][k][n] two's complement)
@@ -380,12 +406,45 @@ bool lwe_commit_explicit_host(const LweContext* c, const u64* msgs, size_t msg_l
 }
 
 bool lwe_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
-                       size_t count, u64* d_out, cudaStream_t stream) {
+                       size_t count, u64* d_out, cudaStream_t stream, uint32_t planes, size_t unit0) {
     if (count == 0) return true;
+    if (planes < 1 || planes > 4) { set_error("lwe_commit: digit planes must be 1..4"); return false; }
     const bool fused_ok = fused_commit_supported(c);
     if (c->commit_path == 2 && !fused_ok) { set_error("fused commit path does not support this context"); return false; }
-    if (fused_ok && c->commit_path != 1) return fused_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream);
-    return generic_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream);
+    if (fused_ok && c->commit_path != 1)
+        return fused_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream, planes, unit0);
+    return generic_commit_launch(c, d_msgs, msg_len, d_seeds, count, d_out, stream, nullptr, nullptr, planes, unit0);
+}
+
+void plane_divisors(u64 p, u64 pdiv[4], u64 pdinv[4]) {
+    unsigned __int128 d = 1;
+    for (int l = 0; l < 4; l++) {
+        const bool fits = d < ((unsigned __int128)1 << 63);
+        pdiv[l] = fits ? (u64)d : 0;
+        pdinv[l] = fits ? ~0ull / (u64)d : 0;
+        d *= p;
+    }
+}
+
+uint32_t message_planes(u64 p, u64 modulus) {
+    unsigned __int128 d = 1;
+    for (uint32_t L = 1; L <= 4; L++) {
+        d *= p;
+        if (d >= modulus) return L;
+    }
+    return 0;
+}
+
+// Noise of a fresh commitment seen by the trapdoor: f^T s + z^T e (+ the last error term), i.e. 2k - 1 ring products of
+// sigma-Gaussians plus one sample: variance (2k - 1) n sigma^4 + sigma^2 per coefficient.  A combination with centred
+// coefficients c'_i has noise at most sum |c'_i| times the single-commitment bound, taken at 12 standard deviations;
+// a plaintext wrap-around costs one more unit each (Delta * p = -1 mod q), at most sum |c'_i| of them; the result
+// decodes while the total stays below Delta / 2.
+u64 lincomb_budget(const LweContext* c) {
+    const double s2 = c->sigma * c->sigma;
+    const double bound = 12.0 * std::sqrt((2.0 * c->k - 1.0) * c->n * s2 * s2 + s2) + 1.0;
+    const double budget = std::floor((double)(c->delta / 2) / bound);
+    return budget < 1.0 ? 1 : (u64)budget;
 }
 
 // Host path: chunks of 256 commitments rotate over three streams, each running
@@ -452,9 +511,7 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
         return lwe_commit_host_staged(c, msgs, msg_len, seeds, count, out);
     const size_t words = lwe_words(c);
     const size_t eff_len = std::max<size_t>(msg_len, 1);
-    size_t chunk_pref = 256;       // commitments per pipeline slot (16 MiB of containers at n = 4096, k = 2)
-    if (const char* e = std::getenv("LSR_COMMIT_CHUNK")) chunk_pref = std::max<size_t>(1, std::strtoull(e, nullptr, 0));
-    const size_t chunk = std::min<size_t>(count, chunk_pref);
+    const size_t chunk = std::min<size_t>(count, kCommitHostChunk);
     const bool fused = fused_commit_supported(c) && c->commit_path != 1;
     const int nbuf = (fused && count > chunk) ? 3 : 1;
     cudaStream_t streams[3] = {c->ntt->copy_streams[0], c->ntt->copy_streams[1], c->ntt->stream};
@@ -554,6 +611,20 @@ bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs
 
 bool lwe_lincomb_host(const LweContext* c, const u64* payloads, const u64* coeffs, size_t count,
                       u64* out_payload) {
+    // decodability budget (lambda_snark_b200.h, lwe_linear_combine): beyond it lwe_verify_opening of the result would fail
+    // for honest inputs, so the combination is refused instead of returned
+    {
+        const u64 budget = lincomb_budget(c);
+        u64 sum = 0;
+        for (size_t i = 0; i < count && sum <= budget; i++) {
+            const u64 cm = coeffs[i] % c->p;
+            sum += cm <= c->p / 2 ? cm : c->p - cm;
+        }
+        if (sum > budget) {
+            set_error("lwe_linear_combine: sum of |centred coefficients| exceeds the decodable budget (lsr_lwe_lincomb_budget)");
+            return false;
+        }
+    }
     std::lock_guard<std::mutex> lock(c->mu);
     if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
     const size_t kn = (size_t)c->k * c->n;

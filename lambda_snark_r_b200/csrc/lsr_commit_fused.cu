@@ -45,8 +45,23 @@ struct FusedParams {
     u64* out;                 // [count][1 + K*n]
     u32 msg_len;              // true stride of msgs
     u32 msg_used;             // min(msg_len, n)
-    u32 skip;                 // PROFILING ONLY (env LSR_FUSED_SKIP): bit i set = phase i+1 not executed; results are garbage
+    // digit planes: commitment b of the launch is unit g = unit0 + b; it commits digit g % planes
+    // (base p) of message row g / planes.  planes = 1: the message itself (mod p).
+    u32 planes;
+    u32 unit0;
+    u64 pdiv[4];              // p^l
+    u64 pdinv[4];             // floor((2^64 - 1) / p^l)
+#ifdef LSR_PROFILING
+    u32 skip;                 // tools/ build only (-DLSR_PROFILING, env LSR_FUSED_SKIP): bit i set = phase i+1 not executed
+#endif
 };
+
+// Phase switches exist only in the profiling build of tools/fused_phases.py; in the shipped library every phase runs.
+#ifdef LSR_PROFILING
+#define LSR_SKIP(fp, bits) (((fp).skip & (bits)) != 0u)
+#else
+#define LSR_SKIP(fp, bits) false
+#endif
 
 // FAST shape: n = 4096.  n/16 chunks = kNttThreads and plan<12> = 4+4+4, so the radix-16 first forward pass and
 // last inverse pass give thread tau exactly the coefficients tau + 256 j of every polynomial -- the chunk tau of the
@@ -68,14 +83,17 @@ __host__ __device__ constexpr int fused_min_blocks() {
 }
 
 // canonical row coefficient v at tile index idx -> + e (+ Delta * (m[x] mod p) on row K-1), reduced
+// pd, pdi: divisor p^plane of the commitment's digit plane and its reciprocal (pd = 0: plane 0, no division)
 template <int LOGN, int K>
 __device__ __forceinline__ u64 commit_finish(u32 idx, u64 v, int ev, const u64* __restrict__ msg, u64 q, u64 delta,
-                                             u64 p, u64 pinv, u32 msg_used) {
+                                             u64 p, u64 pinv, u32 msg_used, u64 pd, u64 pdi) {
     v += ev < 0 ? q - (u64)(-ev) : (u64)ev;                                    // < 2q
     const u32 x = idx - ((u32)(K - 1) << LOGN);                                // wraps for earlier rows
     if ((K == 1 || idx >= ((u32)(K > 1 ? K - 1 : 1) << LOGN)) && x < msg_used) {
+        u64 word = __ldcs(msg + x);
+        if (pd) word = div_small(word, pd, pdi);                               // uniform over the CTA
         // messages are field elements in practice (>= p more often than not): Barrett, not a 64-bit division
-        const u64 m = p < (1ull << 21) ? (u64)mod_small(__ldcs(msg + x), (u32)p, pinv) : __ldcs(msg + x) % p;
+        const u64 m = p < (1ull << 21) ? (u64)mod_small(word, (u32)p, pinv) : word % p;
         v = csub(v + delta * m, q);                                            // delta*m <= q-1
     }
     return csub(v, q);
@@ -90,8 +108,9 @@ struct CommitEpilogue {
     const u64* msg;
     u64 q, delta, p, pinv;
     u32 msg_used;
+    u64 pd, pdi;
     __device__ __forceinline__ u64 operator()(u32 idx, u64 v) const {
-        return commit_finish<LOGN, K>(idx, v, (int)E[idx], msg, q, delta, p, pinv, msg_used);
+        return commit_finish<LOGN, K>(idx, v, (int)E[idx], msg, q, delta, p, pinv, msg_used, pd, pdi);
     }
 };
 
@@ -104,33 +123,59 @@ struct CdtLanes {
     const CdtParam& cdt;
     u64 lane_entry;
     u32 lane_cum;
+    u32 lane_fast;                // ~fast[lane] (compact tables only)
     __device__ __forceinline__ u32 operator()(u64 u) const {
         if constexpr (NCH8 == 0) return cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, u);
         else return cdt_magnitude_shfl<NCH8>(cdt, lane_entry, u);
     }
 };
 
+__device__ __forceinline__ u32 pack_sample(u32 mag, u32 w, u32 j) {
+    const int sv = (w & 1u) ? -(int)mag : (int)mag;                               // -0 == 0: no test of mag needed
+    return ((u32)sv & 0xffu) << (8u * (j & 3u));
+}
+
 // The 16 samples of chunk tau of polynomial P as signed bytes packed into four words (lane j in byte j & 3 of word
-// j >> 2).  Sampling into 4 registers instead of 16 doubles keeps the register pressure low enough for the compiler
-// to interleave the eight shuffle searches of a ChaCha block.
+// j >> 2): one ChaCha block, word j = sign draw + top 31 bits of the magnitude draw of lane j.
+// Compact tables: cdt_fast_probe decides every sample from the top 25 bits; only when one of the 512 draws of the warp
+// ties with a table prefix (probability ~ 4e-4 per call at sigma = 3.19) the refinement blocks are generated and the
+// whole chunk is redone with the full 64-bit search -- the branch is warp-uniform (__any_sync) and what it reveals
+// is that SOME draw of the warp shared 25 leading bits with a table entry, not which nor its value.
+// Sampling into 4 registers instead of 16 doubles keeps the register pressure low enough for the compiler to interleave
+// the searches of a block.
 template <int NCH8>
-__device__ __forceinline__ void sample_chunk_packed(const ChaChaKey& key, u32 s_lo, u32 s_hi, u32 tau, u32 P, u32 sbits,
+__device__ __forceinline__ void sample_chunk_packed(const ChaChaKey& key, u32 s_lo, u32 s_hi, u32 tau, u32 P,
                                                     const CdtLanes<NCH8>& cdtl, u32 (&pk)[4]) {
-    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
-#pragma unroll 1
-    for (u32 h = 0; h < 2; h++) {                 // one copy of the block + searches in the code, run twice
-        u32 x[16];
-        chacha_block(key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
-        const u32 sb = sbits >> (8u * h);
-        u32 a = 0u, b = 0u;
+    u32 x[16];
+    chacha_block(key, s_lo, s_hi, tau, kDomCommit | P, x);
+    bool redo = NCH8 != 0;
+    if constexpr (NCH8 == 0) {
+        const u32 mid_e = ~cdtl.cdt.fast[15];
+        u32 tie = 0u;
+        pk[0] = pk[1] = pk[2] = pk[3] = 0u;
 #pragma unroll
-        for (u32 w = 0; w < 8; w++) {
-            const u32 mag = cdtl((u64)x[2 * w] | ((u64)x[2 * w + 1] << 32));
-            const int sv = ((sb >> w) & 1u) ? -(int)mag : (int)mag;           // -0 == 0: no test of mag needed
-            const u32 byte = ((u32)sv & 0xffu) << (8u * (w & 3u));
-            if (w < 4) a |= byte; else b |= byte;
+        for (u32 j = 0; j < 16; j++) {
+            const u32 e = cdt_fast_probe(mid_e, cdtl.lane_fast, x[j]);
+            tie = max(tie, (e ^ x[j]) | 0x7fu);
+            pk[j >> 2] |= pack_sample((e & 0x7fu) ^ 0x7fu, x[j], j);
         }
-        if (h == 0) { pk[0] = a; pk[1] = b; } else { pk[2] = a; pk[3] = b; }
+        redo = __any_sync(0xffffffffu, tie == 0xffffffffu) != 0;
+    }
+    if (redo) {
+        pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+#pragma unroll 1
+        for (u32 h = 0; h < 2; h++) {                 // one copy of the block + searches in the code, run twice
+            u32 f[16];
+            chacha_block(key, s_lo, s_hi, tau, kDomCommit | kDomCommitFine | (2u * P + h), f);
+            u32 a = 0u, b = 0u;
+#pragma unroll
+            for (u32 w = 0; w < 8; w++) {
+                const u32 xw = h ? x[8 + w] : x[w];
+                const u32 byte = pack_sample(cdtl(commit_draw(xw, f[2 * w], f[2 * w + 1])), xw, w);
+                if (w < 4) a |= byte; else b |= byte;
+            }
+            if (h == 0) { pk[0] = a; pk[1] = b; } else { pk[2] = a; pk[3] = b; }
+        }
     }
 }
 __device__ __forceinline__ int unpack_s8(const u32 (&pk)[4], u32 j) {
@@ -147,16 +192,13 @@ struct CommitEpilogueFast {
     const CdtLanes<NCH8>& cdtl;
     const u64* msg;
     u32 s_lo, s_hi;
-    u32 esg[2];                   // sign words of the e polynomials: block 4K words (K >> 1), (K >> 1) + 1
-    bool no_e;                    // profiling only
+    u64 pd, pdi;
     __device__ __forceinline__ Pre pre(u32 W) const {
         constexpr u32 LG = LOGN - 4;
         const u32 row = W >> LG, tau = W & ((1u << LG) - 1u);
-        const u32 P = (u32)K + row;
-        const u32 sbits = esg[(P >> 1) - ((u32)K >> 1)] >> ((P & 1u) * 16u);
         Pre r;
-        if (no_e) { r.pk[0] = r.pk[1] = r.pk[2] = r.pk[3] = 0u; }
-        else sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, sbits, cdtl, r.pk);
+        if (LSR_SKIP(fp, 33u)) { r.pk[0] = r.pk[1] = r.pk[2] = r.pk[3] = 0u; }
+        else sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, (u32)K + row, cdtl, r.pk);
         return r;
     }
     __device__ __forceinline__ void item(u64* __restrict__ g, u32, u32 base, const u64 (&v)[16], const Pre& pre) const {
@@ -165,7 +207,7 @@ struct CommitEpilogueFast {
 #pragma unroll
         for (u32 j = 0; j < 16; j++) {
             const u32 idx = base + (j << LG);
-            __stcs(g + idx, commit_finish<LOGN, K>(idx, v[j], unpack_s8(pre.pk, j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used));
+            __stcs(g + idx, commit_finish<LOGN, K>(idx, v[j], unpack_s8(pre.pk, j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
         }
     }
 };
@@ -176,7 +218,6 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     constexpr u32 n = 1u << LOGN;
     constexpr bool FAST = fused_fast<LOGN, K>();
     static_assert((n >> 4) % 32 == 0, "whole warps must take part in the shuffle search");
-    static_assert(K <= 4, "sign words 0..3 only");
     extern __shared__ __align__(16) u64 sm[];
     u64* S = sm;                                                     // [K][n], swizzled (FAST: padded)
     const ModParams& mp = fp.mp;
@@ -185,12 +226,18 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     const u32 s_lo = (u32)seed, s_hi = (u32)(seed >> 32);
     const u64 lane_entry = NCH8 == 0 ? cdt.dval[threadIdx.x & 31u]
                                      : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
-    const CdtLanes<NCH8> cdtl{cdt, lane_entry, cdt.dcum[threadIdx.x & 31u]};
+    const CdtLanes<NCH8> cdtl{cdt, lane_entry, cdt.dcum[threadIdx.x & 31u], ~cdt.fast[threadIdx.x & 31u]};
 
+    // digit planes: unit g = unit0 + b commits digit (g % planes) of message row g / planes
+    const size_t unit = (size_t)fp.unit0 + b;
+    const size_t mrow = fp.planes > 1 ? unit / fp.planes : unit;
+    const u32 plane = fp.planes > 1 ? (u32)(unit % fp.planes) : 0u;
+    const u64 pd = plane ? fp.pdiv[plane & 3u] : 0ull, pdi = plane ? fp.pdinv[plane & 3u] : 0ull;
+    const u64* const msg_row = fp.msgs + mrow * (size_t)fp.msg_len;
     // the message is consumed by the last pass only: pull it towards L2 now (one 128-byte line per thread)
     // so that the epilogue's loads do not wait on HBM
     {
-        const u64* m = fp.msgs + b * (size_t)fp.msg_len;
+        const u64* m = msg_row;
         for (u32 x = threadIdx.x * 16u; x < fp.msg_used; x += kNttThreads * 16u)
             asm volatile("prefetch.global.L2 [%0];" :: "l"(m + x));
     }
@@ -202,38 +249,27 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         // pass (stages 0-3, grid-uniform twiddles from the kernel parameters) runs on it, and only its output
         // goes to shared memory.
         const u32 tau = threadIdx.x;
-        u32 esg[2] = {0u, 0u};
-        {
-            u32 sg[16];
-            if (!(fp.skip & 1u)) chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
-            else { for (int i = 0; i < 16; i++) sg[i] = 0; }
-            esg[0] = sg[K >> 1];
-            esg[1] = sg[(K >> 1) + 1 < 4 ? (K >> 1) + 1 : 3];
 #pragma unroll 1
-            for (u32 P = 0; P < (u32)K; P++) {
-                const u32 wsel = P >> 1;
-                const u32 sw = wsel == 0 ? sg[0] : sg[1];
-                const u32 sbits = sw >> ((P & 1) * 16);
-                u32 pk[4] = {0u, 0u, 0u, 0u};
-                if (!(fp.skip & 1u)) sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, sbits, cdtl, pk);
-                u64 v[16];
+        for (u32 P = 0; P < (u32)K; P++) {
+            u32 pk[4] = {0u, 0u, 0u, 0u};
+            if (!LSR_SKIP(fp, 1u)) sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, cdtl, pk);
+            u64 v[16];
 #pragma unroll
-                for (u32 j = 0; j < 16; j++) {
-                    const int sv = unpack_s8(pk, j);
-                    v[j] = POL == POL_F64 ? as_u((double)sv) : (sv < 0 ? mp.q - (u64)(-sv) : (u64)sv);
-                }
-                if (!(fp.skip & 2u)) fwd_network<4, POL, false, true>(v, fp.tbl.fwd, 1u, mp, 0u, fp.tbl.head_fwd);
-                const u32 pb = padx((P << LOGN) + tau);
-#pragma unroll
-                for (u32 j = 0; j < 16; j++) S[pb + j * 272u] = v[j];          // padded stride of 256 coefficients
+            for (u32 j = 0; j < 16; j++) {
+                const int sv = unpack_s8(pk, j);
+                v[j] = POL == POL_F64 ? as_u((double)sv) : (sv < 0 ? mp.q - (u64)(-sv) : (u64)sv);
             }
+            if (!LSR_SKIP(fp, 2u)) fwd_network<4, POL, false, true>(v, fp.tbl.fwd, 1u, mp, 0u, fp.tbl.head_fwd);
+            const u32 pb = padx((P << LOGN) + tau);
+#pragma unroll
+            for (u32 j = 0; j < 16; j++) S[pb + j * 272u] = v[j];              // padded stride of 256 coefficients
         }
         __syncthreads();
         // ---- phase 2b: remaining forward passes (POL_F64: evaluations stay unreduced, the mat-vec product reduces)
-        if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, POL, true, 1>(S, fp.tbl, mp, (u32)K * n, 0u);
+        if (!LSR_SKIP(fp, 2u)) tile_forward<LOGN, LOGN, POL, true, 1>(S, fp.tbl, mp, (u32)K * n, 0u);
 
         // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
-        for (u32 x = threadIdx.x; x < ((fp.skip & 4u) ? 0u : n); x += kNttThreads) {
+        for (u32 x = threadIdx.x; x < (LSR_SKIP(fp, 4u) ? 0u : n); x += kNttThreads) {
             u64 sv[K];
 #pragma unroll
             for (u32 j = 0; j < (u32)K; j++) sv[j] = S[padx((j << LOGN) + x)];
@@ -262,9 +298,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
 
         // ---- phase 4+5: inverse transform of the K rows; its last pass (thread tau again owns tau + 256 j) samples
         // e in registers, adds it (and Delta*m on the last row) and stores the container straight to HBM
-        if (!(fp.skip & 8u)) {
-            const CommitEpilogueFast<LOGN, K, NCH8> epi{fp, cdtl, fp.msgs + b * (size_t)fp.msg_len, s_lo, s_hi,
-                                                        {esg[0], esg[1]}, (fp.skip & 33u) != 0};
+        if (!LSR_SKIP(fp, 8u)) {
+            const CommitEpilogueFast<LOGN, K, NCH8> epi{fp, cdtl, msg_row, s_lo, s_hi, pd, pdi};
             tile_inverse_to_global<LOGN, LOGN, POL, CommitEpilogueFast<LOGN, K, NCH8>, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
         }
         return;
@@ -274,31 +309,19 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     signed char* E = reinterpret_cast<signed char*>(sm + (size_t)K * n);   // [K][n]
     constexpr u32 CH = n >> 4;                                              // chunks; chunk tau = coefficients tau + CH j
     // ---- phase 1: randomness (DESIGN.md 3.3 layout, same as sample_se_kernel)
-    for (u32 tau = threadIdx.x; tau < ((fp.skip & 1u) ? 0u : CH); tau += kNttThreads) {
-        u32 sg[16];
-        chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (4u * K), sg);
+    for (u32 tau = threadIdx.x; tau < (LSR_SKIP(fp, 1u) ? 0u : CH); tau += kNttThreads) {
 #pragma unroll 1
         for (u32 P = 0; P < 2 * K; P++) {
-            const u32 wsel = P >> 1;
-            const u32 sw = wsel == 0 ? sg[0] : (wsel == 1 ? sg[1] : (wsel == 2 ? sg[2] : sg[3]));
-            const u32 sbits = sw >> ((P & 1) * 16);
+            u32 pk[4];
+            sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, P, cdtl, pk);
 #pragma unroll
-            for (u32 h = 0; h < 2; h++) {
-                u32 x[16];
-                chacha_block(fp.key, s_lo, s_hi, tau, kDomCommit | (2u * P + h), x);
-#pragma unroll
-                for (u32 w = 0; w < 8; w++) {
-                    const u64 u = (u64)x[2 * w] | ((u64)x[2 * w + 1] << 32);
-                    const u32 mag = cdtl(u);
-                    const u32 j = 8 * h + w;
-                    const u32 sign = (sbits >> j) & 1u;
-                    const int sv = sign ? -(int)mag : (int)mag;                // -0 == 0: no test of mag needed
-                    if (P < K) {
-                        S[swz((P << LOGN) + tau + CH * j)] =
-                            POL == POL_F64 ? as_u((double)sv) : signed_residue(mag, sign, mp.q);
-                    } else {
-                        E[((P - K) << LOGN) + tau + CH * j] = (signed char)sv;
-                    }
+            for (u32 j = 0; j < 16; j++) {
+                const int sv = unpack_s8(pk, j);
+                if (P < K) {
+                    S[swz((P << LOGN) + tau + CH * j)] =
+                        POL == POL_F64 ? as_u((double)sv) : (sv < 0 ? mp.q - (u64)(-sv) : (u64)sv);
+                } else {
+                    E[((P - K) << LOGN) + tau + CH * j] = (signed char)sv;
                 }
             }
         }
@@ -307,10 +330,10 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
 
     // ---- phase 2: s-hat = NTT(s), all K polynomials as one multi-polynomial tile
     // (POL_F64: evaluations stay unreduced, |s-hat| < (1 + 0.75 logn) q; the mat-vec product reduces)
-    if (!(fp.skip & 2u)) tile_forward<LOGN, LOGN, POL>(S, fp.tbl, mp, (u32)K * n, 0u);
+    if (!LSR_SKIP(fp, 2u)) tile_forward<LOGN, LOGN, POL>(S, fp.tbl, mp, (u32)K * n, 0u);
 
     // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
-    for (u32 x = threadIdx.x; x < ((fp.skip & 4u) ? 0u : n); x += kNttThreads) {
+    for (u32 x = threadIdx.x; x < (LSR_SKIP(fp, 4u) ? 0u : n); x += kNttThreads) {
         u64 sv[K];
 #pragma unroll
         for (u32 j = 0; j < (u32)K; j++) sv[j] = S[swz((j << LOGN) + x)];
@@ -340,8 +363,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     // ---- phase 4+5: rows of A*s back to coefficients; the last inverse pass (coalesced
     // thread -> coefficient map) adds e (and Delta*m on the last row) in registers and
     // stores the LweCommitment container straight to HBM
-    if (!(fp.skip & 8u)) {
-        const CommitEpilogue<LOGN, K> epi{E, fp.msgs + b * (size_t)fp.msg_len, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used};
+    if (!LSR_SKIP(fp, 8u)) {
+        const CommitEpilogue<LOGN, K> epi{E, msg_row, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi};
         tile_inverse_to_global<LOGN, LOGN, POL>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
     }
 }
@@ -369,6 +392,7 @@ static bool build_cdt_param(const LweContext* c, CdtParam& out) {
         ++distinct;
     }
     for (size_t i = distinct; i < 32; i++) out.dcum[i] = (u32)used;
+    for (int i = 0; i < 32; i++) out.fast[i] = ((u32)(out.dval[i] >> 39) << 7) | out.dcum[i];   // dcum <= 64 < 128
     return true;
 }
 
@@ -379,7 +403,7 @@ template <int NCH8>
 __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64* __restrict__ cdf_full, u32 cdf_n,
                                  const u64* __restrict__ u, size_t count, u32* __restrict__ out, int variant) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // count is padded to a multiple of 32
-    const bool compact = variant == 3 && cdt.compact != 0;
+    const bool compact = variant >= 3 && cdt.compact != 0;
     const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
                                    : cdt.cdf[(threadIdx.x & 31u) < 31u ? (threadIdx.x & 31u) : (u32)(kCdtInline - 1)];
     const u32 lane_cum = cdt.dcum[threadIdx.x & 31u];
@@ -387,6 +411,14 @@ __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64
     u32 r;
     if (variant == 0) r = cdt_magnitude_global(cdf_full, cdf_n, x);
     else if (variant == 1) r = cdt_magnitude<NCH8>(cdt, x);
+    else if (compact && variant == 4) {
+        // the commitment sampler's decision: 25-bit prefix first, full draw only when some lane of the warp ties
+        const u32 w = (u32)(x >> 32);                                 // bits 31..1 = top 31 bits of the draw
+        const u32 e = cdt_fast_probe(~cdt.fast[15], ~cdt.fast[threadIdx.x & 31u], w);
+        r = (e & 0x7fu) ^ 0x7fu;
+        if (__any_sync(0xffffffffu, ((e ^ w) | 0x7fu) == 0xffffffffu))
+            r = cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, x);
+    }
     else if (compact) r = cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, x);
     else r = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, x);
     if (i < count) out[i] = r;
@@ -490,8 +522,9 @@ static bool launch_fused(const FusedParams& fp, const CdtParam& cdt, size_t coun
 }
 
 bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
-                         size_t count, u64* d_out, cudaStream_t s) {
+                         size_t count, u64* d_out, cudaStream_t s, uint32_t planes, size_t unit0) {
     if (count == 0) return true;
+    if (planes < 1 || planes > 4 || unit0 > 0xffffffffull) { set_error("fused path: bad digit planes"); return false; }
     if (count > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     if (msg_len > 0xffffffffull) { set_error("msg_len too large"); return false; }
     CdtParam cdt;
@@ -512,8 +545,13 @@ bool fused_commit_launch(const LweContext* c, const u64* d_msgs, size_t msg_len,
     fp.out = d_out;
     fp.msg_len = (u32)msg_len;
     fp.msg_used = (u32)std::min<size_t>(msg_len, c->n);
+    fp.planes = planes;
+    fp.unit0 = (u32)unit0;
+    plane_divisors(c->p, fp.pdiv, fp.pdinv);
+#ifdef LSR_PROFILING
     const char* skip = std::getenv("LSR_FUSED_SKIP");
     fp.skip = skip ? (u32)std::strtoul(skip, nullptr, 0) : 0u;
+#endif
     switch (c->logn * 16 + c->k) {
         case 12 * 16 + 1: return launch_fused<12, 1>(fp, cdt, count, s, f64);
         case 12 * 16 + 2: return launch_fused<12, 2>(fp, cdt, count, s, f64);

@@ -23,6 +23,7 @@ constexpr int kChaChaRounds = 8;
 constexpr u32 kDomMatrix = 0x01000000u;
 constexpr u32 kDomTrap   = 0x02000000u;
 constexpr u32 kDomCommit = 0x03000000u;
+constexpr u32 kDomCommitFine = 0x100u;    // refinement blocks of the commitment randomness
 constexpr u32 kDomSample = 0x05000000u;
 
 // Modulus constants.  "lazy" policies: butterflies carry unreduced values and

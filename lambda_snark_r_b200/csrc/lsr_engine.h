@@ -81,6 +81,7 @@ struct LweContext {
     lsr::u64* d_zh = nullptr;         // [k-1][n]
     lsr::u64* d_cdf = nullptr;        // [cdf.size()]
     int commit_path = 0;              // 0 auto, 1 generic, 2 fused
+    int strict_messages = 0;          // 1: host-pointer entry points reject message words >= p (lsr_lwe_set_strict_messages)
     mutable std::mutex mu;
     mutable lsr::DeviceScratch scratch[10];
     mutable lsr::PinnedScratch staging[6];   // pageable callers: 3 slots x (messages + seeds | containers)
@@ -92,9 +93,17 @@ LweContext* lwe_create(u64 modulus_req, uint32_t n, uint32_t k, double sigma, co
 void lwe_destroy(LweContext* ctx);
 size_t lwe_words(const LweContext* ctx);
 
-// device-pointer commit: msgs [count][msg_len], seeds [count], out [count][1+k*n]
+// device-pointer commit: msgs [count][msg_len], seeds [count], out [count][1+k*n].
+// Digit planes: with planes = L > 1 commitment b is unit g = unit0 + b and commits the base-p digit
+// g % L of message row g / L (msgs then holds ceil((unit0 + count) / L) rows); planes = 1 commits msgs[b] mod p.
 bool lwe_commit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
-                       size_t count, u64* d_out, cudaStream_t stream);
+                       size_t count, u64* d_out, cudaStream_t stream, uint32_t planes = 1, size_t unit0 = 0);
+// p^l and floor((2^64-1) / p^l) for l = 0..3 (entries whose power overflows 2^63 are 0: such a digit is always 0)
+void plane_divisors(u64 p, u64 pdiv[4], u64 pdinv[4]);
+// smallest L with p^L >= modulus: digits that bind a whole field element (0 if more than 4 would be needed)
+uint32_t message_planes(u64 p, u64 modulus);
+// sum of |centred coefficient| a linear combination of fresh commitments may carry and still decode
+u64 lincomb_budget(const LweContext* ctx);
 bool lwe_commit_host(const LweContext* ctx, const u64* msgs, size_t msg_len, const u64* seeds,
                      size_t count, u64* out);
 // results[i] in {1,0,-1}

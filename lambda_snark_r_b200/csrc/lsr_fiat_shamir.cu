@@ -82,12 +82,13 @@ fs_challenge_warp_kernel(const u64* __restrict__ pub, size_t n_pub, const u64* _
     }
 }
 
-// out[p][j] = sum_i coeffs[p][i] * x^i, x = points[(p % point_rows)][j];  grid = (npts, polys)
+// out[p][j] = sum_i coeffs[p][i] * x^i, x = points[(p % point_rows)][j];  grid = (npts, polys of this launch);
+// p0 = index of the launch's first polynomial (batches above the 65 535 limit of gridDim.y go in several launches)
 __global__ void __launch_bounds__(kEvalThreads)
 poly_eval_kernel(const ModParams mp, const u64* __restrict__ coeffs, size_t len, const u64* __restrict__ points,
-                 size_t npts, size_t point_rows, u64* __restrict__ out) {
+                 size_t npts, size_t point_rows, u64* __restrict__ out, size_t p0) {
     __shared__ u64 part[kEvalThreads];
-    const size_t p = blockIdx.y, j = blockIdx.x;
+    const size_t p = p0 + blockIdx.y, j = blockIdx.x;
     const u64 x = reduce64(points[(p % point_rows) * npts + j], mp);
     const u64* __restrict__ c = coeffs + p * len;
     const size_t per = (len + kEvalThreads - 1) / kEvalThreads;
@@ -117,7 +118,11 @@ bool fs_challenge_launch(const u64* d_pub, size_t n_pub, const u64* d_containers
                          u64 modulus, bool chain, u64* d_ab, u64* d_hashes, cudaStream_t s) {
     if (count == 0) return true;
     if (modulus == 0) { set_error("fs_challenge: modulus 0"); return false; }
-    static const int force = [] { const char* e = std::getenv("LSR_FS_KERNEL"); return e ? std::atoi(e) : 0; }();   // 1 thread, 2 warp
+#ifdef LSR_PROFILING    // tools/ build only: 1 = thread per statement, 2 = warp per statement
+    static const int force = [] { const char* e = std::getenv("LSR_FS_KERNEL"); return e ? std::atoi(e) : 0; }();
+#else
+    constexpr int force = 0;
+#endif
     const bool warp = force == 2 || (force != 1 && count < kFsWarpMaxCount);
     if (warp) {
         const size_t blocks = (count + kFsWarpCta / 32 - 1) / (kFsWarpCta / 32);
@@ -138,11 +143,15 @@ bool poly_eval_launch(u64 modulus, const u64* d_coeffs, size_t len, size_t polys
     if (polys == 0 || npts == 0) return true;
     if (modulus < 2 || (modulus != kGoldilocks && (modulus >> 61))) { set_error("poly_eval: unsupported modulus"); return false; }
     if (len == 0 || point_rows == 0) { set_error("poly_eval: empty polynomial"); return false; }
-    if (polys > 65535 || npts > 0x7fffffffull) { set_error("poly_eval: batch too large"); return false; }
+    if (npts > 0x7fffffffull) { set_error("poly_eval: too many points"); return false; }
     const ModParams mp = host::make_mod_params(modulus, 1);
-    poly_eval_kernel<<<dim3((unsigned)npts, (unsigned)polys), kEvalThreads, 0, s>>>(mp, d_coeffs, len, d_points, npts,
-                                                                                     point_rows, d_out);
-    return cuda_ok(cudaGetLastError(), "poly_eval_kernel");
+    for (size_t p0 = 0; p0 < polys; p0 += 65535) {
+        const size_t cnt = std::min<size_t>(65535, polys - p0);
+        poly_eval_kernel<<<dim3((unsigned)npts, (unsigned)cnt), kEvalThreads, 0, s>>>(mp, d_coeffs, len, d_points, npts,
+                                                                                     point_rows, d_out, p0);
+        if (!cuda_ok(cudaGetLastError(), "poly_eval_kernel")) return false;
+    }
+    return true;
 }
 
 // host-pointer forms (tests, small batches): stage through temporary device buffers on the chosen device

@@ -140,8 +140,12 @@ static bool launch_column2(const NttContext* c, u64* d, size_t batch, cudaStream
 }
 
 static bool column2_enabled() {
+#ifdef LSR_PROFILING    // tools/ build only: LSR_NTT_COLUMN2=0 falls back to chained single-column passes
     static const bool on = [] { const char* e = std::getenv("LSR_NTT_COLUMN2"); return !(e && e[0] == '0'); }();
     return on;
+#else
+    return true;
+#endif
 }
 
 // n <= 2^13: one kernel, the polynomial never leaves shared memory.

@@ -380,7 +380,6 @@ int r1cs_quotient_batch(R1csHandle* h, const u64* witnesses, size_t count, u64 o
 // page-locked caller buffers the call is bound by the slower PCIe direction instead of the sum of both copies and the
 // compute.  Groups hold at least ~8 MB of witness words so that the copies run at full link rate.
 static std::pair<size_t, size_t> pipeline_groups(const R1csHandle* h, size_t count) {
-    if (std::getenv("LSR_PROVER_PIPELINE") && std::getenv("LSR_PROVER_PIPELINE")[0] == '0') return {count, count ? 1 : 0};
     const size_t wbytes = (size_t)h->cols * 8;
     const size_t G = std::max<size_t>(1, std::min<size_t>(count, ((size_t)8 << 20) / std::max<size_t>(wbytes, 1)));
     return {G, G ? (count + G - 1) / G : 0};
@@ -398,14 +397,15 @@ static bool pipeline_init(QuotientState* st) {
 }
 
 static int prover_commit_pipelined(R1csHandle* h, const LweContext* lwe, const u64* witnesses, size_t count, u64 omega,
-                                   const u64* seeds, size_t chunk_lo, size_t chunk_hi, u64* out, int* status) {
+                                   const u64* seeds, size_t chunk_lo, size_t chunk_hi, uint32_t planes, u64* out, int* status) {
     QuotientState* st = nullptr;
     const int rc = quotient_prepare(h, omega, &st);
     if (rc != 0) return rc;
     if (st->device != lwe->device) { set_error("prover_commit_quotient: R1CS and LWE context live on different devices"); return 2; }
     if (!pipeline_init(st)) return 4;
     const uint32_t m = h->rows, cols = h->cols, n = lwe->n;
-    const size_t chunks = (size_t)m / n, mine = chunk_hi - chunk_lo, words = lwe_words(lwe);
+    // units = (ring-element chunk, digit plane) pairs; [chunk_lo, chunk_hi) ranges over units
+    const size_t chunks = (size_t)m / n * planes, mine = chunk_hi - chunk_lo, words = lwe_words(lwe);
     const auto [G, NG] = pipeline_groups(h, count);
     bool ok = st->z.reserve(2 * G * cols * 8) && st->e.reserve((size_t)3 * G * m * 8) && st->qbuf.reserve(G * (size_t)m * 8) &&
               st->flags.reserve(count * 4) && st->h_flags.reserve(count * 4) && st->seeds.reserve(2 * G * mine * 8) &&
@@ -424,18 +424,19 @@ static int prover_commit_pipelined(R1csHandle* h, const LweContext* lwe, const u
         // copy-in: the buffers of group g - 2 must have been consumed
         if (g >= 2) ok = cuda_ok(cudaStreamWaitEvent(sin, st->ev_zfree[b], 0), "wait");
         ok = ok && cuda_ok(cudaMemcpyAsync(dz, witnesses + w0 * cols, gw * cols * 8, cudaMemcpyHostToDevice, sin), "H2D witness");
-        for (size_t w = 0; ok && w < gw; w++)
-            ok = cuda_ok(cudaMemcpyAsync(dseed + w * mine, seeds + (w0 + w) * chunks + chunk_lo, mine * 8, cudaMemcpyHostToDevice, sin), "H2D seeds");
+        // seeds of the group: rows of `chunks` words, of which [chunk_lo, chunk_hi) are this call's -- one strided copy
+        ok = ok && cuda_ok(cudaMemcpy2DAsync(dseed, mine * 8, seeds + w0 * chunks + chunk_lo, chunks * 8, mine * 8, gw,
+                                             cudaMemcpyHostToDevice, sin), "H2D seeds");
         ok = ok && cuda_ok(cudaEventRecord(st->ev_in[b], sin), "record");
         // compute: quotient of the group, then its commitments into container buffer b (free once group g - 2 is out)
         ok = ok && cuda_ok(cudaStreamWaitEvent(scomp, st->ev_in[b], 0), "wait");
         if (ok && g >= 2) ok = cuda_ok(cudaStreamWaitEvent(scomp, st->ev_out[b], 0), "wait");
         ok = ok && quotient_compute(h, st, dz, gw, dE, dQ, dF + w0, false, scomp);
         if (ok && mine == chunks) {
-            ok = lwe_commit_launch(lwe, dQ, n, dseed, gw * chunks, dcont, scomp);
+            ok = lwe_commit_launch(lwe, dQ, n, dseed, gw * chunks, dcont, scomp, planes, 0);
         } else for (size_t w = 0; ok && w < gw; w++) {
-            ok = lwe_commit_launch(lwe, dQ + w * (size_t)m + chunk_lo * (size_t)n, n, dseed + w * mine, mine,
-                                   dcont + w * mine * words, scomp);
+            ok = lwe_commit_launch(lwe, dQ + w * (size_t)m, n, dseed + w * mine, mine, dcont + w * mine * words, scomp,
+                                   planes, chunk_lo);
         }
         // the seeds live in the same double buffer as the witnesses: both are free after the commitments
         ok = ok && cuda_ok(cudaEventRecord(st->ev_zfree[b], scomp), "record") &&
@@ -466,12 +467,16 @@ int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witn
                            int* status) {
     std::lock_guard<std::mutex> lock(h->mu);
     const uint32_t m = h->rows, n = lwe->n;
-    const size_t chunks = m <= n ? 1 : (size_t)m / n;
+    // Digit planes: a commitment binds its message words modulo p, so every ring-element chunk of Q is
+    // committed as L = ceil(log_p(field modulus)) commitments to its base-p digits; together they bind the whole quotient.
+    const uint32_t planes = message_planes(lwe->p, h->q);
+    if (planes == 0) { set_error("prover_commit_quotient: more than 4 digit planes needed (plaintext modulus too small)"); return 2; }
+    const size_t chunks = (m <= n ? 1 : (size_t)m / n) * planes;       // units: (chunk, plane) pairs
     if (chunk_lo > chunk_hi || chunk_hi > chunks) { set_error("prover_commit_quotient: bad chunk range"); return 2; }
     QuotientState* st = nullptr;
     const size_t mine = chunk_hi - chunk_lo;
     if (!io_on_device && mine > 0 && lwe->n <= m && pipeline_groups(h, count).second >= 2)
-        return prover_commit_pipelined(h, lwe, witnesses, count, omega, seeds, chunk_lo, chunk_hi, out, status);
+        return prover_commit_pipelined(h, lwe, witnesses, count, omega, seeds, chunk_lo, chunk_hi, planes, out, status);
     const int rc = quotient_device(h, witnesses, io_on_device, count, omega, status, &st);
     if (rc != 0) return rc;
     if (count == 0 || mine == 0) return 0;
@@ -492,12 +497,13 @@ int prover_commit_quotient(R1csHandle* h, const LweContext* lwe, const u64* witn
         // the whole quotient of every witness: Q [count][m] is [count * chunks][msg_len] -- one launch
         ok = cuda_ok(cudaMemcpyAsync(d_seeds, seeds, count * chunks * 8,
                                      io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds") &&
-             lwe_commit_launch(lwe, dQ, msg_len, d_seeds, count * chunks, d_out, s);
-    } else for (size_t w = 0; ok && w < count; w++) {
-        ok = cuda_ok(cudaMemcpyAsync(d_seeds + w * mine, seeds + w * chunks + chunk_lo, mine * 8,
-                                     io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds") &&
-             lwe_commit_launch(lwe, dQ + w * (size_t)m + chunk_lo * (size_t)n, msg_len, d_seeds + w * mine, mine,
-                               d_out + w * mine * words, s);
+             lwe_commit_launch(lwe, dQ, msg_len, d_seeds, count * chunks, d_out, s, planes, 0);
+    } else {
+        ok = cuda_ok(cudaMemcpy2DAsync(d_seeds, mine * 8, seeds + chunk_lo, chunks * 8, mine * 8, count,
+                                       io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "H2D seeds");
+        for (size_t w = 0; ok && w < count; w++)
+            ok = lwe_commit_launch(lwe, dQ + w * (size_t)m, msg_len, d_seeds + w * mine, mine, d_out + w * mine * words, s,
+                                   planes, chunk_lo);
     }
     if (ok && !io_on_device)
         ok = cuda_ok(cudaMemcpyAsync(out, d_out, count * mine * words * 8, cudaMemcpyDeviceToHost, s), "D2H containers");

@@ -61,7 +61,14 @@ struct CdtParam {
     u32 pad2;
     u64 dval[32];              // unused = 2^64-1; dval[31] is always 2^64-1
     u32 dcum[32];              // dcum[i] = number of table entries < dval[i] (= entries counted by dval[0..i-1])
+    u32 fast[32];              // (dval[i] >> 39) << 7 | dcum[i]: 25-bit prefix + count in one word (cdt_fast_probe)
 };
+
+// Magnitude draw of a commitment sample: top 31 bits from the sample's own keystream word w
+// (whose bit 0 is the sign draw), low 33 bits from the refinement block (bit 0 of f0, all of f1).
+__host__ __device__ __forceinline__ u64 commit_draw(u32 w, u32 f0, u32 f1) {
+    return ((u64)(w >> 1) << 33) | ((u64)(f0 & 1u) << 32) | (u64)f1;
+}
 
 // magnitude = #{k : cdf[k] < u}; NCH8 = ceil(count / 8)
 template <int NCH8>
@@ -144,6 +151,29 @@ __device__ __forceinline__ u32 cdt_magnitude_compact(u64 mid, u64 lane_val, u32 
             : "+r"(p) : "r"(v_lo), "r"(v_hi), "r"(u_lo), "r"(u_hi));
     }
     return __shfl_sync(0xffffffffu, lane_cum, p);                             // p = #{i < 31 : dval[i] < u}
+}
+
+// Fast form of the compact search for the commitment sampler: the top 25 bits of the draw (= w >> 7) against
+// the 25-bit prefixes of the distinct table values, prefix and entry count packed in ONE word per lane
+// (lane_e = ~fast[lane], complemented for the carry trick), so a step is one shuffle, one add.cc and one addc.
+// [fast[i] < (w & ~0x7f)]  <=>  prefix[i] < w >> 7  (the count occupies the low 7 bits, which are cleared in the
+// key).  Returns e = ~fast[p] with p = #{i : prefix[i] < w >> 7}:
+//   magnitude = (e & 0x7f) ^ 0x7f      -- valid iff no table prefix equals w >> 7;
+//   tie       = ((e ^ w) | 0x7f) == 0xffffffff   (prefix[p] == w >> 7: the low bits of the draw decide; the
+//               caller then forms the full 64-bit draw and runs cdt_magnitude_compact).
+// The sentinel lanes (value 2^64-1, prefix 0x1ffffff) make the all-ones prefix a tie, which is correct if
+// conservative.  Probability of a tie: (#distinct prefixes) * 2^-25 per sample.  All 32 lanes must call.
+__device__ __forceinline__ u32 cdt_fast_probe(u32 mid_e, u32 lane_e, u32 w) {
+    const u32 key = w & ~0x7fu;
+    u32 p;
+    asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, 0, 0;\n\t}" : "=r"(p) : "r"(mid_e), "r"(key));
+#pragma unroll
+    for (int i = 1; i < 5; i++) {
+        const u32 probe = p * (1u << (5 - i)) + ((1u << (4 - i)) - 1u);
+        const u32 v = __shfl_sync(0xffffffffu, lane_e, probe);
+        asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, %0;\n\t}" : "+r"(p) : "r"(v), "r"(key));
+    }
+    return __shfl_sync(0xffffffffu, lane_e, p);
 }
 
 // table in global memory, any size

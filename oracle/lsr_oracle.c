@@ -587,27 +587,33 @@ const uint64_t *lsro_lwe_trapdoor(const lsro_lwe *c) { return c->zh; }
 /*
  * Commitment randomness layout.  Coefficient c of
  * polynomial P (P<k: s_P, P>=k: e_{P-k}) lives in chunk tau = c mod (n/16), lane j = c div (n/16)
- * (a chunk is the 16 coefficients tau + (n/16) j that one thread of the radix-16 first / last NTT pass owns):
- *   u1   = 64-bit word (j&7) of block b = 2P + (j>>3)
- *   sign = bit (16P + j) of block b = 4k
- * block(b) = ChaCha(key, w12=seed_lo, w13=seed_hi, w14=tau, w15=DOM_COMMIT|b).
+ * (a chunk is the 16 coefficients tau + (n/16) j that one thread of the radix-16 first / last NTT pass owns).
+ * One ChaCha block per (P, tau) carries all 16 samples of the chunk: with w = word j of
+ *   block(P)            = ChaCha(key, w12=seed_lo, w13=seed_hi, w14=tau, w15=DOM_COMMIT|P)
+ * the two draws of utils.cpp:95-121 (sample_single) are
+ *   u2 (sign draw)      = w            (only bit 0 is looked at, utils.cpp:113)
+ *   u1 (magnitude draw) = (w >> 1) * 2^33 + lo33,
+ *   lo33                = 33 bits of the REFINEMENT block 0x100 | (2P + (j>>3)): bit 0 of word 2(j&7) as
+ *                         bit 32, word 2(j&7)+1 as bits 31..0.
+ * u1 is a uniform 64-bit word independent of u2.  Its top 31 bits decide the sample unless they equal the
+ * top 31 bits of a table entry (probability < 2^-26 per sample), so an implementation may fetch the refinement
+ * block only then; this restatement always forms the full u1.
  */
 static void sample_chunk(const lsro_lwe *c, uint64_t seed, uint32_t tau, int64_t *out /*[2k][16]*/) {
     const uint32_t k = c->k;
-    uint32_t sgn[16];
-    lsro_chacha_block(c->key, (uint32_t)seed, (uint32_t)(seed >> 32), tau, DOM_COMMIT | (4 * k), sgn);
     for (uint32_t P = 0; P < 2 * k; P++) {
-        for (uint32_t h = 0; h < 2; h++) {
-            uint32_t blk[16];
+        uint32_t blk[16], fine[2][16];
+        lsro_chacha_block(c->key, (uint32_t)seed, (uint32_t)(seed >> 32), tau, DOM_COMMIT | P, blk);
+        for (uint32_t h = 0; h < 2; h++)
             lsro_chacha_block(c->key, (uint32_t)seed, (uint32_t)(seed >> 32), tau,
-                              DOM_COMMIT | (2 * P + h), blk);
-            for (uint32_t w = 0; w < 8; w++) {
-                uint32_t j = 8 * h + w;
-                uint64_t u1 = (uint64_t)blk[2 * w] | ((uint64_t)blk[2 * w + 1] << 32);
-                uint32_t bit = 16 * P + j;
-                uint64_t u2 = (sgn[bit >> 5] >> (bit & 31)) & 1u;
-                out[P * 16 + j] = lsro_cdt_sample(c->cdf, c->cdf_n, u1, u2);
-            }
+                              DOM_COMMIT | 0x100u | (2 * P + h), fine[h]);
+        for (uint32_t j = 0; j < 16; j++) {
+            const uint32_t w = blk[j];
+            const uint32_t *f = fine[j >> 3];
+            const uint64_t lo33 = ((uint64_t)(f[2 * (j & 7)] & 1u) << 32) | (uint64_t)f[2 * (j & 7) + 1];
+            const uint64_t u1 = ((uint64_t)(w >> 1) << 33) | lo33;
+            const uint64_t u2 = (uint64_t)w;
+            out[P * 16 + j] = lsro_cdt_sample(c->cdf, c->cdf_n, u1, u2);
         }
     }
 }
@@ -761,7 +767,7 @@ int lsro_lwe_verify(const lsro_lwe *c, const uint64_t *w, size_t len,
         uint64_t v = u[x] + last[x];
         if (v >= q) v -= q;
         uint64_t d = ((v + c->delta / 2) / c->delta) % c->p;
-        diff |= d ^ msg[x];                        /* :223-226 */
+        diff |= d ^ (msg[x] % c->p);               /* :223-226; words are bound mod p */
     }
     free(u); free(tmp);
     return diff == 0 ? 1 : 0;
@@ -777,7 +783,8 @@ int lsro_lwe_linear_combine(const lsro_lwe *c, const uint64_t *const *comms,
     for (size_t i = 0; i < count; i++) {
         if (!comms[i]) continue;                   /* :248-250 */
         if (!container_ok(c, comms[i], comm_lens[i])) return -1;   /* :253-255 */
-        const uint64_t cf = coeffs[i] % c->p;      /* :90 coeff %= plain_modulus */
+        uint64_t cf = coeffs[i] % c->p;            /* :90 coeff %= plain_modulus */
+        if (cf > c->p / 2) cf = c->q - (c->p - cf); /* centred representative */
         for (size_t x = 0; x < kn; x++) {
             uint64_t v = out[1 + x] + lsro_mulmod(cf, comms[i][1 + x], c->q);
             if (v >= c->q) v -= c->q;

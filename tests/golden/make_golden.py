@@ -60,6 +60,18 @@ def ntt_kat():
              "fwd_1to8": [4906668228709, 13352284639367, 1243151528753, 7252051638976],
              "fwd_1to8_last": 17473155690403, "fwd_ones": [10796465977081, 15311896912402, 8589703109061]},
         ],
+        # Constants asserted by SEAL's OWN unit tests (Microsoft SEAL 4.1, native/tests/seal/util/ntt.cpp:
+        # NTTTablesTest.NTTPrimitiveRootsTest and NTTTablesTest.NegacyclicNTTTest), restated here from that file -- SEAL
+        # is the library cpp-core/src/ntt.cpp:46,84 calls and is not vendored under /root/reference.  They were NOT
+        # produced by this repo's code: the oracle and the device are checked against them.  They pin the choice of
+        # the minimal primitive 2n-th root, the bit-reversed table order and the output order of the forward transform.
+        "seal_unit_tests": {
+            "source": "SEAL 4.1 native/tests/seal/util/ntt.cpp (NTTPrimitiveRootsTest, NegacyclicNTTTest)",
+            "q": 0xffffffffffc0001,
+            "root_powers": {"2": [1, 288794978602139552],
+                            "4": [1, 288794978602139552, 178930308976060547, 748001537669050592]},
+            "forward_n2": [{"in": [0, 0], "out": [0, 0]}, {"in": [1, 0], "out": [1, 1]},
+                           {"in": [1, 1], "out": [288794978602139553, 864126526004445282]}]},
         "roots_of_unity_rs": {      # rust-api/lambda-snark/src/r1cs.rs:534-547, omega_m = 3^((q-1)/m)
             "q": Q0, "generator": 3, "m": [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]},
     }

@@ -123,3 +123,27 @@ def test_null_and_invalid_arguments_need_no_gpu():
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(FileNotFoundError):
         capi.load(tmp_path / "liblambda_snark_core.so")
+
+
+def test_static_archive_resolves_with_the_cargo_link_line(tmp_path):
+    """A12 (rust-api/lambda-snark-sys/build.rs:106-124,180 as patched in INTEGRATION.md section 2): the static archive,
+    cudart_static, dl, rt, pthread, stdc++ resolve every symbol of a C consumer.  Linking needs no GPU; the binary is
+    run by tests/test_gpu_cabi_c.py."""
+    import subprocess
+    exe = tmp_path / "test_cabi_static"
+    lib_dir = capi.LIB_PATH.parent
+    cmd = ["gcc", "-std=c11", "-O1", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cabi" / "test_cabi.c"),
+           "-L", str(lib_dir), "-l:liblambda_snark_core.a", "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt",
+           "-lpthread", "-lstdc++", "-lm", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ldd = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "lambda_snark_core" not in ldd and "libcudart" not in ldd, ldd
+
+
+def test_no_profiling_switch_ships_in_the_library():
+    """The phase-skip / kernel-selection switches of tools/ exist only in the -DLSR_PROFILING build: the shipped
+    library reads no LSR_* environment variable."""
+    blob = capi.LIB_PATH.read_bytes() + (capi.LIB_PATH.parent / "liblambda_snark_core.a").read_bytes()
+    for name in (b"LSR_FUSED_SKIP", b"LSR_COMMIT_CHUNK", b"LSR_PROVER_PIPELINE", b"LSR_NTT_COLUMN2", b"LSR_FS_KERNEL"):
+        assert name not in blob, name

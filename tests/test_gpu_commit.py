@@ -339,6 +339,78 @@ def test_verify_and_lincomb_match_oracle(gpu, rng):
     ctx.close()
 
 
+def test_words_at_or_above_p_strict_mode_and_lincomb_budget(gpu, rng):
+    """lambda_snark_b200.h, lwe_commit MESSAGE RANGE / lwe_linear_combine COEFFICIENT BOUND: message words are bound
+    modulo p and the library's own commitments to words >= p open; strict mode rejects such words the way SEAL's
+    debug-build BatchEncoder does; combinations beyond the decodable budget are refused, at the budget they open."""
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    lib = capi.load()
+    p = ctx.p
+    msgs = rng.integers(0, 2**64, size=(3, 40), dtype=np.uint64)
+    msgs[0, :4] = [p, p + 5, 2**64 - 1, p - 1]
+    seeds = np.array([5, 6, 7], dtype=np.uint64)
+    cms = ctx.commit_batch(msgs, seeds)
+    assert np.array_equal(cms, orc.commit_batch(msgs, seeds))
+    assert ctx.verify_batch(cms, msgs).tolist() == [1, 1, 1] == [orc.verify(cms[i], msgs[i]) for i in range(3)]
+    assert ctx.verify_batch(cms, msgs % np.uint64(p)).tolist() == [1, 1, 1]
+    bad = msgs.copy(); bad[:, 3] ^= 1                                 # p is even: the residue changes
+    assert ctx.verify_batch(cms, bad).tolist() == [0, 0, 0] == [orc.verify(cms[i], bad[i]) for i in range(3)]
+    ctx.set_strict_messages(True)
+    with pytest.raises(api.LambdaSnarkError):
+        ctx.commit_batch(msgs, seeds)
+    assert not lib.lwe_commit(ctx.as_ptr(), msgs[0].ctypes.data_as(capi.u64p), 40, 9)
+    assert ctx.verify_batch(cms, msgs).tolist() == [0, 0, 0]
+    small = msgs % np.uint64(p)
+    assert np.array_equal(ctx.commit_batch(small, seeds), cms) and ctx.verify_batch(cms, small).tolist() == [1, 1, 1]
+    ctx.set_strict_messages(False)
+    # linear combinations
+    budget = ctx.lincomb_budget()
+    assert 1000 < budget < 10000
+    cs = [api.Commitment.new(ctx, small[i], int(seeds[i])) for i in range(3)]
+    with pytest.raises(api.LambdaSnarkError):                        # a full-range coefficient cannot be decoded at 44 bits
+        api.Commitment.linear_combine(ctx, cs, [p // 2, 17, 5])
+    with pytest.raises(api.LambdaSnarkError):
+        api.Commitment.linear_combine(ctx, cs, [budget - 9, p - 7, 3])
+    coeffs = [budget - 10, p - 7, 3]                                  # centred: budget - 10, -7, 3
+    comb = api.Commitment.linear_combine(ctx, cs, coeffs)
+    assert np.array_equal(comb.as_bytes(), orc.linear_combine([c.as_bytes() for c in cs], coeffs))
+    expected = sum(int(c) * small[i].astype(object) for i, c in enumerate(coeffs)) % p
+    assert api.verify_commitment(ctx, comb, expected.astype(np.uint64)) == 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("msg_len,modulus", [(4096, 2**64 - 2**32 + 1), (33, Q0), (4096, 1000)])
+def test_digit_planes_bind_whole_words(gpu, rng, msg_len, modulus):
+    """lsr_lwe_commit_digits_batch_device: every message row as `planes` commitments to its base-p digits, equal to the
+    oracle's commitments to sharding.message_digits on both commitment paths; the digits recompose the words."""
+    import torch
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    p = ctx.p
+    planes = ctx.message_planes(modulus)
+    assert planes == sharding.message_planes(p, modulus) == {2**64 - 2**32 + 1: 4, Q0: 3, 1000: 1}[modulus]
+    count = 3
+    msgs = rng.integers(0, modulus, size=(count, msg_len), dtype=np.uint64)
+    msgs[0, :4] = [0, min(p - 1, modulus - 1), min(p, modulus - 1), modulus - 1]
+    seeds = np.arange(1, count * planes + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    digits = sharding.message_digits(msgs, p, planes)
+    assert digits.shape == (count * planes, msg_len) and int(digits.max()) < p
+    assert np.array_equal(sum(digits[l::planes].astype(object) * p ** l for l in range(planes)), msgs.astype(object))
+    want = orc.commit_batch(digits, seeds)
+    dm, ds = torch.from_numpy(msgs.view(np.int64)).cuda(), torch.from_numpy(seeds.view(np.int64)).cuda()
+    for path in (1, 2):
+        ctx.set_commit_path(path)
+        out = torch.zeros((count * planes, ctx.words), dtype=torch.int64, device="cuda")
+        ctx.commit_digits_batch_device(dm.data_ptr(), msg_len, ds.data_ptr(), count, planes, out.data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), want), path
+    ctx.set_commit_path(0)
+    assert ctx.verify_batch(want, digits).tolist() == [1] * (count * planes)
+    ctx.close()
+
+
 def test_homomorphism_at_scale(gpu, rng):
     """Size-independent property at a BASELINE batch size: verify(sum c_i C_i) == sum c_i m_i (mod p)."""
     ctx = mk()
@@ -436,14 +508,39 @@ def test_cdt_search_variants_on_boundaries(gpu, rng):
             us += [(int(v) + d) % 2**64 for d in (-2, -1, 0, 1, 2)]
         us += [int(x) for x in rng.integers(0, 2**64, 500, dtype=np.uint64)]
         us += [int(x) | 0xFFFFFFFF00000000 for x in rng.integers(0, 2**32, 500, dtype=np.uint64)]   # tail region
+        # variant 4 (the commitment sampler: 25-bit prefix search, full draw only when a lane of the warp ties with a
+        # table prefix) decides per WARP: pad to a multiple of 32, then add warps that contain no tie at all -- random
+        # draws, and draws whose 25-bit prefix is one off a table prefix on either side -- so that the prefix-only
+        # decision is what gets compared there
+        us += [0] * (-len(us) % 32)
+        prefixes = {int(v) >> 39 for v in cdf}
+        near = [((p + d) << 39) | int(x) for p in sorted(prefixes) for d in (-1, 1)
+                for x in rng.integers(0, 2**39, 4, dtype=np.uint64) if 0 <= p + d < 2**25 and (p + d) not in prefixes]
+        free = [int(x) for x in rng.integers(0, 2**64, 4096, dtype=np.uint64) if (int(x) >> 39) not in prefixes]
+        tie_free = near + free
+        us += tie_free[: len(tie_free) - len(tie_free) % 32]
         u = np.array(us, dtype=np.uint64)
         want = np.array([abs(O.cdt_sample(cdf, int(x), 0)) for x in u], dtype=np.uint32)
-        for variant in (0, 1, 2, 3):
+        for variant in (0, 1, 2, 3, 4):
             out = np.zeros(u.size, dtype=np.uint32)
             rc = lib.lsr_cdt_magnitude_device(sigma, u.ctypes.data_as(capi.u64p), u.size,
                                               out.ctypes.data_as(C.POINTER(C.c_uint32)), variant)
             assert rc == 0, (sigma, variant)
             assert np.array_equal(out, want), (sigma, variant, np.nonzero(out != want)[0][:5])
+
+
+def test_large_batch_matches_oracle_and_exercises_the_refinement_path(gpu, rng):
+    """4 096 fused commitments (6.7e7 samples: a dozen or so prefix ties, i.e. the rarely taken refinement branch of
+    the sampler runs) against the oracle's OpenMP port, word for word."""
+    ctx = mk()
+    orc = O.OracleLwe(Q0, 4096, 2, 3.19, SEED32)
+    count = 4096
+    msgs = rng.integers(0, 2**64, size=(count, 4096), dtype=np.uint64)
+    seeds = sharding.global_seeds(0xBADC0DE, 0, count)
+    got = ctx.commit_batch(msgs, seeds)
+    want = orc.commit_batch(msgs, seeds, threads=O.max_threads())
+    assert np.array_equal(got, want)
+    ctx.close()
 
 
 def test_page_locked_host_buffers(gpu, rng):

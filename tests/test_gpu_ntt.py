@@ -71,6 +71,28 @@ def test_survey_kats_on_device(gpu):
         ctx.close()
 
 
+def test_seal_unit_test_constants_on_device(gpu):
+    """SEAL's own unit-test vectors (native/tests/seal/util/ntt.cpp NTTPrimitiveRootsTest / NegacyclicNTTTest, restated in
+    tests/golden/ntt_kat.json) through ntt_context_create / ntt_forward / ntt_inverse -- what cpp-core/src/ntt.cpp:46,84,99
+    would return with SEAL behind it.  q = 0xffffffffffc0001 is a 60-bit modulus: the guarded u64 butterflies."""
+    g = json.loads((GOLD / "ntt_kat.json").read_text())["seal_unit_tests"]
+    q = g["q"]
+    for n, powers in g["root_powers"].items():
+        ctx = api.NttContext(q, int(n))
+        assert ctx.root == (powers[2] if int(n) == 4 else powers[1])
+        # forward(X^j)[i] = psi^((2 brv(i) + 1) j): with j = 1 the outputs are the odd powers, and output 0 is psi itself
+        x = np.zeros(int(n), dtype=np.uint64); x[1] = 1
+        y = ctx.forward(x)
+        assert int(y[0]) == ctx.root and int(y[1]) == q - ctx.root
+        ctx.close()
+    ctx = api.NttContext(q, 2)
+    for v in g["forward_n2"]:
+        y = ctx.forward(np.array(v["in"], dtype=np.uint64))
+        assert [int(t) for t in y] == v["out"]
+        assert [int(t) for t in ctx.inverse(y)] == v["in"]
+    ctx.close()
+
+
 # ------------------------------------------------------------ parity sweeps
 SWEEP = [(12289, 256), (257, 2), (Q0, 2), (Q0, 4), (Q0, 8), (Q0, 16), (Q0, 32), (Q0, 64), (Q0, 128), (Q0, 512),
          (Q0, 1024), (Q0, 2048), (Q0, 4096), (Q1, 8192), (Q1, 16384), (Q1, 32768), (Q1, 65536), (Q1, 131072),

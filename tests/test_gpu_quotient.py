@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import Q0, Q1, Q45, Q50, Q60
-from lambda_snark_r_b200 import api, capi
+from lambda_snark_r_b200 import api, capi, sharding
 from oracle import quotient as QO
 from test_oracle_quotient import mult_gates
 
@@ -218,8 +218,8 @@ def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
     cols, A, B, C, z = np_mult_gates(m, q, 70 + logm)
     r = api.R1CS.from_arrays(m, cols, A, B, C, q)
     ctx = api.LweContext(api.Params(n=n, k=k, q=Q0, sigma=3.19), seed32=seed32)
-    chunks = r.quotient_chunks(ctx)
-    assert chunks == max(1, m // n)
+    chunks, planes = r.quotient_chunks(ctx), r.quotient_planes(ctx)
+    assert planes == sharding.message_planes(ctx.p, q) == 4 and chunks == max(1, m // n) * planes
     seeds = np.arange(1, 2 * chunks + 1, dtype=np.uint64).reshape(2, chunks) * np.uint64(0x9E3779B97F4A7C15)
     bad = z.copy(); bad[3] = (int(bad[3]) + 1) % q
     got, status = r.commit_quotient(ctx, np.stack([z, bad]), seeds)
@@ -228,10 +228,14 @@ def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
                                  api.reference_root_of_unity(q, 2 * m))
     assert st == 0
     orc = O.OracleLwe(Q0, n, k, 3.19, seed32)
-    msgs = want_q.reshape(chunks, -1)                   # [chunks][min(m, n)]
+    # units = (ring element, digit plane): the base-p digits of the quotient coefficients, which together bind them
+    msgs = sharding.message_digits(want_q.reshape(chunks // planes, -1), ctx.p, planes)     # [chunks][min(m, n)]
+    assert int(msgs.max()) < ctx.p
+    recomposed = sum(msgs[l::planes].astype(object) * ctx.p ** l for l in range(planes))
+    assert np.array_equal(recomposed, want_q.reshape(chunks // planes, -1).astype(object))
     assert np.array_equal(got[0], orc.commit_batch(msgs, seeds[0]))
-    # the context opens what the prover committed (slots hold the quotient coefficients mod the plaintext modulus)
-    assert ctx.verify_batch(got[0], msgs % np.uint64(ctx.p)).tolist() == [1] * chunks
+    # the context opens what the prover committed
+    assert ctx.verify_batch(got[0], msgs).tolist() == [1] * chunks
     if chunks >= 4:
         lo, _ = r.commit_quotient(ctx, z[None, :], seeds[:1], 0, chunks // 4)
         hi, _ = r.commit_quotient(ctx, z[None, :], seeds[:1], chunks // 4, chunks)
@@ -245,9 +249,8 @@ def test_prover_commit_phase_matches_oracle_and_is_shard_invariant(gpu, logm):
 def test_prover_commit_pipeline_equals_the_serial_path(gpu, logm, count):
     """Host-io pipeline of lsr_prover_commit_quotient (groups of witnesses over copy-in / compute / copy-out streams, two
     buffers each): five groups of one witness (2^18) and groups of 5, 5, 2 witnesses (2^16), an unsatisfied witness in
-    the middle, whole quotients and a chunk slice -- bit-identical to the one-shot path (LSR_PROVER_PIPELINE=0) and
-    repeatable on the same handle."""
-    import os
+    the middle, whole quotients and a chunk slice -- bit-identical to the one-shot path (one call per witness: a single
+    group is never pipelined) and repeatable on the same handle."""
     q, m, n, k = P, 1 << logm, 4096, 2
     cols, A, B, C, z = np_mult_gates(m, q, 99)
     r = api.R1CS.from_arrays(m, cols, A, B, C, q)
@@ -261,12 +264,9 @@ def test_prover_commit_pipeline_equals_the_serial_path(gpu, logm, count):
         zs[w, 3::3] = np.array([(int(x) * int(y)) % q for x, y in zip(a.tolist(), zs[w, 2::3].tolist())], dtype=np.uint64)
     zs[2, 3] = (int(zs[2, 3]) + 1) % q                  # witness 2 violates constraint 0
     seeds = (np.arange(1, count * chunks + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(count, chunks)
-    os.environ["LSR_PROVER_PIPELINE"] = "0"
-    try:
-        want, st_want = r.commit_quotient(ctx, zs, seeds)
-        want_slice, _ = r.commit_quotient(ctx, zs, seeds, 3, chunks - 5)         # 2^16: chunks = 16
-    finally:
-        del os.environ["LSR_PROVER_PIPELINE"]
+    one = [r.commit_quotient(ctx, zs[w:w + 1], seeds[w:w + 1]) for w in range(count)]
+    want, st_want = np.concatenate([c for c, _ in one]), np.concatenate([s for _, s in one])
+    want_slice = np.concatenate([r.commit_quotient(ctx, zs[w:w + 1], seeds[w:w + 1], 3, chunks - 5)[0] for w in range(count)])
     assert st_want.tolist() == [0, 0, 1] + [0] * (count - 3)
     for _ in range(2):
         got, st = r.commit_quotient(ctx, zs, seeds)

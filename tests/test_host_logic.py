@@ -227,10 +227,12 @@ def _gloo_prover_worker(rank, world, port, out_dir):
     cols, A, B, Cm, z = mult_gates(m, q, random.Random(5))
     quo = QO.compute_quotient_poly(m, A, B, Cm, z, q)
     quo = quo + [0] * (m - len(quo))
-    chunks = m // n
-    lo, hi = sharding.shard_range(chunks, rank, world)
     ctx = O.OracleLwe(Q0, n, k, 3.19, bytes(range(32)))
-    msgs = np.array(quo, dtype=np.uint64).reshape(chunks, n)
+    # units = (ring element, base-p digit plane) pairs, the order lsr_prover_commit_quotient commits them in
+    planes = sharding.message_planes(ctx.p, q)
+    chunks = m // n * planes
+    lo, hi = sharding.shard_range(chunks, rank, world)
+    msgs = sharding.message_digits(np.array(quo, dtype=np.uint64).reshape(m // n, n), ctx.p, planes)
     mine = ctx.commit_batch(msgs[lo:hi], sharding.global_seeds(0xC0FFEE, lo, hi))
     local = torch.from_numpy(mine.view(np.int64))
     gathered = [torch.empty_like(local) for _ in range(world)]

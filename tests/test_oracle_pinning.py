@@ -105,6 +105,22 @@ def test_ntt_kats():
         assert [str(int(v)) for v in ctx.forward(x)] == f["forward"]
 
 
+def test_seal_unit_test_constants():
+    """The constants SEAL's own unit tests assert (native/tests/seal/util/ntt.cpp, restated in ntt_kat.json): root-power
+    tables for n = 2, 4 and the n = 2 forward transforms at q = 0xffffffffffc0001.  cpp-core/src/ntt.cpp:46,84 is SEAL."""
+    g = json.loads((GOLD / "ntt_kat.json").read_text())["seal_unit_tests"]
+    q = g["q"]
+    for n, powers in g["root_powers"].items():
+        ctx = O.OracleNtt(q, int(n))
+        assert ctx.psi == powers[2 if int(n) == 4 else 1]            # root_powers[brv(1)] = psi for n = 2; [2] = psi^1 for n = 4
+        assert [int(v) for v in ctx.table(0)] == powers
+        if int(n) == 2:                                               # the same SEAL test: inv_root_powers(1) inverts root_powers(1)
+            assert (int(ctx.table(2)[1]) * powers[1]) % q == 1
+    ctx = O.OracleNtt(q, 2)
+    for v in g["forward_n2"]:
+        assert [int(x) for x in ctx.forward(np.array(v["in"], dtype=np.uint64))] == v["out"]
+
+
 @pytest.mark.parametrize("q,n", [(12289, 256), (Q0, 64), (Q0, 512), (Q60, 128), (Q31, 32), (257, 2), (Q0, 2)])
 def test_forward_is_closed_form(q, n, rng):
     ctx = O.OracleNtt(q, n)

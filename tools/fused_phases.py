@@ -1,10 +1,14 @@
 """Phase cost breakdown of the fused commitment kernel: time it with individual phases
-switched off (LSR_FUSED_SKIP bit mask; results are garbage, timing only)."""
+switched off (LSR_FUSED_SKIP bit mask; results are garbage, timing only).  The switch exists only in the
+profiling build of the library (python -m lambda_snark_r_b200._build --profiling), loaded here in place
+of the shipped one."""
 import os, sys
 from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+from lambda_snark_r_b200 import _build, capi
+capi._lib = capi.load(_build.build_profiling())     # before api binds: every wrapper goes through capi.load()
 from lambda_snark_r_b200 import api
 Q, N, B = 17592169062401, 4096, 16384
 api.set_device(0)
