@@ -54,6 +54,7 @@ FP64_PER_MODMUL = 6
 FP64_NTT_FWD = BUTTERFLIES_NTT * FP64_PER_BUTTERFLY
 FP64_NTT_INV = FP64_NTT_FWD + (N_RING // 2) * FP64_PER_MODMUL     # n^-1 folded into the last stage
 FP64_COMMIT = K_RANK * (FP64_NTT_FWD + FP64_NTT_INV) + K_RANK * K_RANK * N_RING * (FP64_PER_MODMUL + 1)
+PARITY_N, PARITY_NTT_ROWS = 32, 4
 
 
 def peaks():
@@ -314,6 +315,25 @@ def run_gpu(args):
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
+    # ---- parity of what the timed region produced (outside it): `out` is the last timed step's output; rank 0 puts
+    # PARITY_N randomly chosen containers of it next to the CPU oracle's commitments to the same (message, seed)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import oracle as O
+        prng = np.random.Generator(np.random.PCG64(int(time.time_ns()) & 0xffffffff))
+        pick = np.sort(prng.choice(B, size=min(PARITY_N, B), replace=False))
+        pt = torch.from_numpy(pick).to(dev)
+        got = out.index_select(0, pt).cpu().numpy().view(np.uint64)
+        pm = msgs.index_select(0, pt).cpu().numpy().view(np.uint64)
+        ps = seeds.index_select(0, pt).cpu().numpy().view(np.uint64)
+        want = O.OracleLwe(Q_MOD, N_RING, K_RANK, SIGMA, CTX_SEED).commit_batch(pm, ps, threads=host_threads())
+        same = int((got == want).all(axis=1).sum())
+        parity = {"containers_compared": int(pick.size), "containers_identical": same,
+                  "what": "random containers of the last timed step vs oracle/lsr_oracle.c (bit for bit)"}
+        if same != pick.size:
+            raise SystemExit(f"bench.py: PARITY FAILURE: {pick.size - same} of {pick.size} containers of the timed step "
+                             f"differ from the oracle")
+
     # ---- NTT sweep point at the same n (BASELINE configs[2])
     NB = args.ntt_batch
     data = torch.randint(0, Q_MOD, (NB, N_RING), device=dev, dtype=torch.int64, generator=g)
@@ -322,6 +342,27 @@ def run_gpu(args):
     ms_inv = timed(lambda: ntt.inverse_device(data.data_ptr(), NB, stream), args.warmup, args.steps) / args.steps
     ms_mul = timed(lambda: ntt.mul_pointwise_device(data2.data_ptr(), data.data_ptr(), data2.data_ptr(), NB * N_RING, stream),
                    args.warmup, args.steps) / args.steps
+    if parity is not None:
+        # one more full-batch launch of each timed NTT call; PARITY_NTT_ROWS rows of it against the oracle
+        from oracle import oracle as O
+        rows = torch.from_numpy(np.sort(prng.choice(NB, size=min(PARITY_NTT_ROWS, NB), replace=False))).to(dev)
+        orc_ntt = O.OracleNtt(Q_MOD, N_RING)
+        before = data.index_select(0, rows).cpu().numpy().view(np.uint64)
+        ntt.forward_device(data.data_ptr(), NB, stream); torch.cuda.synchronize()
+        fwd = data.index_select(0, rows).cpu().numpy().view(np.uint64)
+        ntt.inverse_device(data.data_ptr(), NB, stream); torch.cuda.synchronize()
+        back = data.index_select(0, rows).cpu().numpy().view(np.uint64)
+        b2 = data2.index_select(0, rows).cpu().numpy().view(np.uint64)
+        ntt.mul_pointwise_device(data2.data_ptr(), data.data_ptr(), data2.data_ptr(), NB * N_RING, stream); torch.cuda.synchronize()
+        prod = data2.index_select(0, rows).cpu().numpy().view(np.uint64)
+        ok_rows = int(sum(bool(np.array_equal(f, orc_ntt.forward(x)) and np.array_equal(y, x) and
+                               np.array_equal(pr, orc_ntt.mul_pointwise(x, m2)))
+                          for x, f, y, m2, pr in zip(before, fwd, back, b2, prod)))
+        parity.update({"ntt_rows_compared": int(rows.numel()), "ntt_rows_identical": ok_rows,
+                       "ntt_what": "rows of one extra full-batch forward / inverse / pointwise launch (same calls as the timed ones) "
+                                   "vs the oracle: forward values, inverse(forward) = input, pointwise products"})
+        if ok_rows != rows.numel():
+            raise SystemExit("bench.py: PARITY FAILURE in the NTT block")
 
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     EB = args.e2e_batch
@@ -362,7 +403,6 @@ def run_gpu(args):
     # the device, cut into m / n ring elements, each committed; weak scaling over witnesses (every rank proves its own)
     prover = None
     if args.prover_logm > 0:
-        import numpy as np
         PM = 1 << args.prover_logm
         PW = args.prover_witnesses
         GOLD = 2**64 - 2**32 + 1
@@ -432,6 +472,31 @@ def run_gpu(args):
                                       "sample": f"1 quotient of 2^{args.prover_logm} constraints in {dt_q:.2f}s, oracle C port (O(m log m)); "
                                                 f"commitments of the phase are covered by the top-level cpu_baseline",
                                       "gpu_quotients_per_s": PW / (ms_q * 1e-3)}
+        # one proof, strong scaling (BASELINE configs[4] as written: ONE 2^20-constraint witness over N GPUs): every rank
+        # computes the quotient (it does not shard: six dependent size-m transforms) and commits ITS slice of the
+        # `chunks` units; at N > 1 the containers land in rank 0's HBM through peer stores (no collective)
+        lo, hi = (rank * chunks) // world, ((rank + 1) * chunks) // world
+        sw_pg = None
+        sw_out = pout.data_ptr()
+        if world > 1:
+            from lambda_snark_r_b200 import gather as G
+            sw_pg = G.PeerGather(rank, world, ((chunks + world - 1) // world) * words * 8, G.torch_bcast())
+            sw_out = sw_pg.slice_ptr
+
+        def single_witness_step():
+            st = r1cs.commit_quotient_device(ctx, zs.data_ptr(), 1, pseeds.data_ptr(), sw_out, lo, hi)
+            assert not st.any()
+
+        ms_sw = timed(single_witness_step, args.warmup, psteps) / psteps
+        ms_sw_q = timed(lambda: r1cs.commit_quotient_device(ctx, zs.data_ptr(), 1, pseeds.data_ptr(), sw_out, lo, lo),
+                        args.warmup, psteps) / psteps
+        prover["single_witness"] = {"what": "latency of the commitment phase of ONE 2^20-constraint proof: quotient on every rank "
+                                            "(replicated), units [r*C/N, (r+1)*C/N) committed by rank r"
+                                            + (", containers stored into rank 0's HBM over NVLink" if world > 1 else ""),
+                                    "ms": ms_sw, "ms_quotient_replicated": ms_sw_q, "ms_commit_slice": ms_sw - ms_sw_q,
+                                    "units_per_rank": hi - lo, "proofs_per_s": 1e3 / ms_sw}
+        if sw_pg:
+            sw_pg.close()
         del zs, pout
         r1cs.close()
 
@@ -444,21 +509,73 @@ def run_gpu(args):
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- final gather over NVLink (outside the timed step: no data-path collective in the hot path)
+    # ---- final gather over NVLink / NVSwitch, for the WHOLE step batch, inside the timed step
+    #  (a) containers -> rank 0's HBM, fused: the commitment kernel of every rank stores its container rows straight into
+    #      rank 0's buffer through peer memory (lambda_snark_r_b200/gather.py): no collective follows the kernel.  Bounded by
+    #      rank 0's NVLink ingress: (N-1) * B * 64 KiB per step.
+    #  (b) digests: SHA3-256 of every container on its owner (the Fiat-Shamir transcript hash of N2 -- work a single GPU does
+    #      too), then an NCCL all-gather of 32 bytes per commitment; the containers stay with their owners.
     gather = None
     if world > 1:
+        from lambda_snark_r_b200 import gather as G
+        lib = capi.load()
+        pg = G.PeerGather(rank, world, B * words * 8, G.torch_bcast())
+
+        def step_peer():
+            ctx.commit_batch_device(msgs.data_ptr(), N_RING, seeds.data_ptr(), B, pg.slice_ptr, stream)
+
+        ms_peer = timed(step_peer, args.warmup, args.steps) / args.steps
+        # checksum of checksums: every rank's slice in rank 0's buffer equals what the rank computed locally
+        local_sum = out.sum(dim=1).sum().reshape(1)
+        sums = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sums, local_sum)
+        gathered_ok = None
+        if rank == 0:
+            view = G.device_view(pg.base, world * B * words, dev).view(world, B * words)
+            gathered_ok = bool(torch.equal(view.sum(dim=1), sums))
+            if not gathered_ok:
+                raise SystemExit("bench.py: the peer-memory gather does not hold what the ranks computed")
+        d_ab = torch.empty((B, 2), dtype=torch.int64, device=dev)
+        d_hash = torch.empty((B, 2, 4), dtype=torch.int64, device=dev)
+        d_all = torch.empty((world * B, 2, 4), dtype=torch.int64, device=dev)
+        d_pub = torch.zeros(8, dtype=torch.int64, device=dev)
+
+        def transcript():
+            if lib.lsr_fs_challenge_batch_device(d_pub.data_ptr(), 0, out.data_ptr(), words, B, Q_MOD, 0, d_ab.data_ptr(),
+                                                 d_hash.data_ptr(), stream) != 0:
+                raise RuntimeError("lsr_fs_challenge_batch_device failed")
+
+        def step_digest_gather():
+            step(); dist.all_gather_into_tensor(d_all, d_hash)
+
+        def step_transcript_gather():
+            step(); transcript(); dist.all_gather_into_tensor(d_all, d_hash)
+
+        transcript()
+        ms_dg = timed(step_digest_gather, args.warmup, args.steps) / args.steps
+        ms_tg = timed(step_transcript_gather, args.warmup, max(3, args.steps // 2)) / max(3, args.steps // 2)
+        # the NCCL all-gather of whole containers the first round used, for comparison (one eighth of the step batch)
         GB_ = min(B, 2048)
         part = out[:GB_].contiguous()
         full = torch.empty((world * GB_, words), device=dev, dtype=torch.int64)
-        for _ in range(2):
-            dist.all_gather_into_tensor(full, part)
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.all_gather_into_tensor(full, part); e1.record()
-        barrier()
-        gms = max_over_ranks(e0.elapsed_time(e1))
-        gather = {"op": "ncclAllGather of the commitment containers", "commitments_per_rank": GB_, "ms": gms,
-                  "GBps_in_per_rank": (world - 1) * GB_ * words * 8 / (gms * 1e-3) / 1e9}
+        ms_ag = timed(lambda: dist.all_gather_into_tensor(full, part), 2, 3) / 3
+        del full
+        gather = {
+            "containers_to_rank0_peer_stores": {
+                "what": "fused: every rank's commitment kernel writes its containers into rank 0's HBM over NVLink (no collective)",
+                "commitments_per_rank": B, "ms_per_step": ms_peer, "value_with_gather": world * B / (ms_peer * 1e-3),
+                "frac_of_value": (ms_step / ms_peer), "rank0_ingress_GBps": (world - 1) * B * words * 8 / (ms_peer * 1e-3) / 1e9,
+                "nvlink_peak_GBps_per_direction": 900.0, "verified": gathered_ok},
+            "digests_all_gather": {
+                "what": "owner hashes its containers (SHA3-256 transcript, N2), NCCL all-gather of 32 B per commitment",
+                "commitments_per_rank": B, "ms_per_step_commit_plus_gather": ms_dg,
+                "value_with_gather": world * B / (ms_dg * 1e-3), "frac_of_value": ms_step / ms_dg,
+                "ms_per_step_commit_plus_transcript_plus_gather": ms_tg,
+                "value_with_transcript_and_gather": world * B / (ms_tg * 1e-3)},
+            "containers_nccl_all_gather": {"commitments_per_rank": GB_, "ms": ms_ag,
+                                           "GBps_in_per_rank": (world - 1) * GB_ * words * 8 / (ms_ag * 1e-3) / 1e9},
+        }
+        pg.close()
 
     # ---- integer roofline denominator (measured on this GPU)
     imad_wide = C.c_double(0); imad_lo = C.c_double(0); mhz = C.c_double(0)
@@ -508,42 +625,80 @@ def run_gpu(args):
     ntt_cpu_rate, _, ntt_cpu_count, ntt_cpu_dt = cpu_ntt_rate(min(args.cpu_seconds, 5.0))
 
     mul_gbs = NB * N_RING * 24 / (ms_mul * 1e-3) / 1e9
+    fwd_block, inv_block = ntt_block(ms_fwd, FP64_NTT_FWD), ntt_block(ms_inv, FP64_NTT_INV, N_RING // 2)
+    # The roof that binds the fused kernel is the one its multiplications run on: the FP64 pipe (arith fp64: 8 FP64
+    # instructions per butterfly at 64 lanes/clk/SM, measured on this GPU in this run) or, with --arith u64, the IMAD pipe
+    # under SURVEY 8d's normalisation.  HBM is reported beside it (`hbm`), not as the headline: the kernel moves 98 312 B
+    # per commitment and sits at ~0.14 of the copy peak by construction.
+    if arith == "fp64":
+        bound = {"bound": "fp64", "achieved": commit_fp64, "peak": fp64_peak, "unit": "Ginst/s",
+                 "frac": commit_fp64 / fp64_peak if fp64_peak else None,
+                 "peak_source": "lsr_measure_fp64_peak on this GPU in this run (dependent-free DFMA chains, 64 lanes/clk/SM)",
+                 "model": f"{FP64_COMMIT} FP64 instructions/commitment = {K_RANK} fwd + {K_RANK} inv NTT x {FP64_PER_BUTTERFLY}/butterfly"
+                          f" + {K_RANK * K_RANK * N_RING} mat-vec MACs x {FP64_PER_MODMUL + 1}; sampler (ALU pipe) not counted"}
+    else:
+        bound = {"bound": "imad", "achieved": commit_imad, "peak": imad_peak, "unit": "GIMAD/s",
+                 "frac": commit_imad / imad_peak if imad_peak else None,
+                 "peak_source": "lsr_measure_imad_peak on this GPU in this run (64 lanes/clk/SM)",
+                 "model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d normalisation)"}
+    tr_per = tr.get("fused_commit_bytes_per_commitment")
+    roofline = {
+        "kernel": "fused_commit_kernel<12,2,0,%s>" % ("POL_F64" if arith == "fp64" else "POL_LAZY"), **bound,
+        "arith": arith,
+        "traffic": tr_per * B if tr_per else None,
+        "traffic_source": "static: dram bytes per commitment of the ncu --set full capture recorded in profiles/traffic.json x batch "
+                          "(not measured in this run)" if tr_per else None,
+        "algorithmic_bytes_per_commitment": ALG_BYTES_COMMIT,
+        "hbm": {"achieved": commit_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": commit_gbs / hbm_peak, "peak_source": hbm_src},
+        "imad_survey": {"frac": commit_imad / imad_peak if imad_peak else None,
+                        "model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d normalisation; with "
+                                 f"arith=fp64 the multiplications run on the FP64 pipe instead); IMAD {imad_lo.value:.0f} GIMAD/s"
+                                 f" (= 64 lanes/clk/SM at {mhz.value:.0f} MHz), IMAD.WIDE {imad_wide.value:.0f} GIMAD/s measured"},
+        "bounds_commitments_per_s": {"hbm": hbm_peak * 1e9 / ALG_BYTES_COMMIT,
+                                     "fp64": fp64_peak * 1e9 / FP64_COMMIT if fp64_peak else None,
+                                     "imad_survey": imad_peak * 1e9 / (MODMUL_COMMIT * IMAD_PER_MODMUL) if imad_peak else None},
+        # the other half of BASELINE.json's metric (batched NTTs/s at n = 4096) and the other kernels of the path, one
+        # line each: value per GPU, fraction of the slower of its compute and HBM roofs
+        "kernels": {
+            "ntt_forward": {"value": NB / (ms_fwd * 1e-3), "unit": "NTT/s", "batch": NB,
+                            "bound": fwd_block["roofline"]["slower_bound"], "frac": fwd_block["roofline"]["frac_of_slower_bound"],
+                            "hbm_frac": fwd_block["roofline"]["frac"]},
+            "ntt_inverse": {"value": NB / (ms_inv * 1e-3), "unit": "NTT/s", "batch": NB,
+                            "bound": inv_block["roofline"]["slower_bound"], "frac": inv_block["roofline"]["frac_of_slower_bound"],
+                            "hbm_frac": inv_block["roofline"]["frac"]},
+            "pointwise": {"value": NB * N_RING / (ms_mul * 1e-3), "unit": "coefficients/s", "bound": "hbm",
+                          "frac": mul_gbs / hbm_peak},
+        },
+    }
+    if prover:
+        prover["quotient_hbm_frac"] = prover["quotient_GBps"] / hbm_peak
+        roofline["kernels"]["quotient_pipeline"] = {
+            "value": PW * PM / (prover["ms_quotient"] * 1e-3), "unit": "constraints/s", "bound": "hbm",
+            "frac": prover["quotient_hbm_frac"], "ms": prover["ms_quotient"],
+            "model": f"{QUOTIENT_BYTES_PER_CONSTRAINT} algorithmic bytes per constraint, 2^{args.prover_logm} constraints x {PW} witnesses"}
+    e2e = {"value": e2e_value, "unit": "commitments/s", "h2d_bytes_per_step": EB * (N_RING + 1) * 8,
+           "d2h_bytes_per_step": EB * words * 8, "batch_per_gpu": EB, "ms_per_step": e2e_ms,
+           "api": "lwe_commit_batch (C ABI, pinned host buffers)", "numa_node": numa,
+           "ntt_forward": {"value": world * EB / (ntt_e2e_ms * 1e-3), "unit": "NTT/s",
+                           "api": "ntt_forward_batch (C ABI, pinned host buffers, in place)"}}
+    if prover:
+        e2e["prover"] = {"value": prover["e2e"]["value"], "unit": "witnesses/s", "api": "lsr_prover_commit_quotient"}
     line = {
         "metric": "lwe_commitments_per_sec", "value": value, "unit": "commitments/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(B, "hbm-resident"),
-        "roofline": {
-            "kernel": "fused_commit_kernel<12,2,0,%s>" % ("POL_F64" if arith == "fp64" else "POL_LAZY"), "bound": "hbm", "achieved": commit_gbs, "peak": hbm_peak,
-            "unit": "GB/s", "frac": commit_gbs / hbm_peak, "peak_source": hbm_src,
-            "traffic": (tr.get("fused_commit_bytes_per_commitment") or 0) * B or None,
-            "algorithmic_bytes_per_commitment": ALG_BYTES_COMMIT,
-            "arith": arith,
-            "binding_bound": "instruction issue: FP64 butterflies (2 issue cycles each, nothing co-issues with them) plus the "
-                             "ChaCha/CDT sampler on the ALU pipe; not hbm",
-            "fp64_achieved_ginst_s": commit_fp64 if arith == "fp64" else None, "fp64_peak_ginst_s": fp64_peak,
-            "fp64_frac": commit_fp64 / fp64_peak if (arith == "fp64" and fp64_peak) else None,
-            "fp64_model": f"{FP64_COMMIT} FP64 instructions/commitment = {K_RANK} fwd + {K_RANK} inv NTT x {FP64_PER_BUTTERFLY}/butterfly"
-                          f" + {K_RANK * K_RANK * N_RING} mat-vec MACs x {FP64_PER_MODMUL + 1}; sampler (ALU pipe) not counted",
-            "fp64_peak_source": "lsr_measure_fp64_peak on this GPU (dependent-free DFMA chains, 64 lanes/clk/SM)",
-            "bounds_commitments_per_s": {"hbm": hbm_peak * 1e9 / ALG_BYTES_COMMIT,
-                                         "fp64": fp64_peak * 1e9 / FP64_COMMIT if fp64_peak else None,
-                                         "imad_survey": imad_peak * 1e9 / (MODMUL_COMMIT * IMAD_PER_MODMUL) if imad_peak else None},
-            "imad_survey_frac": commit_imad / imad_peak if imad_peak else None,
-            "imad_survey_model": f"{MODMUL_COMMIT} modmul/commitment x {IMAD_PER_MODMUL} IMAD (SURVEY 8d normalisation; with "
-                                 f"arith=fp64 the multiplications run on the FP64 pipe instead); IMAD {imad_lo.value:.0f} GIMAD/s"
-                                 f" (= 64 lanes/clk/SM at {mhz.value:.0f} MHz), IMAD.WIDE {imad_wide.value:.0f} GIMAD/s measured",
-        },
+        "roofline": roofline,
         "cpu_baseline": {"value": cpu_rate, "unit": "commitments/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_count} commitments in {cpu_dt:.1f}s, oracle C port, {cpu_threads} OpenMP threads"
                                    f"{' -march=native' if native else ''}",
                          "ntt_forward_per_s": ntt_cpu_rate},
-        "e2e": {"value": e2e_value, "unit": "commitments/s", "h2d_bytes_per_step": EB * (N_RING + 1) * 8,
-                "d2h_bytes_per_step": EB * words * 8, "batch_per_gpu": EB, "ms_per_step": e2e_ms,
-                "api": "lwe_commit_batch (C ABI, pinned host buffers)", "numa_node": numa},
+        "e2e": e2e,
         "gpu_launches": args.steps,
         "clocks": clocks,
-        "ntt": {"batch_per_gpu": NB, "forward": ntt_block(ms_fwd, FP64_NTT_FWD), "inverse": ntt_block(ms_inv, FP64_NTT_INV, N_RING // 2),
+        "parity_checked": (parity or {}).get("containers_identical", 0) + (parity or {}).get("ntt_rows_identical", 0),
+        "parity": parity,
+        "ntt": {"batch_per_gpu": NB, "forward": fwd_block, "inverse": inv_block,
                 "e2e": {"value": world * EB / (ntt_e2e_ms * 1e-3), "unit": "NTT/s", "ms_per_step": ntt_e2e_ms, "batch_per_gpu": EB,
                         "h2d_bytes_per_step": EB * N_RING * 8, "d2h_bytes_per_step": EB * N_RING * 8,
                         "api": "ntt_forward_batch (C ABI, pinned host buffers, in place)"},
@@ -552,10 +707,13 @@ def run_gpu(args):
                                            "frac": mul_gbs / hbm_peak}}},
     }
     if prover:
-        prover["quotient_hbm_frac"] = prover["quotient_GBps"] / hbm_peak
         line["prover"] = prover
     if gather:
         line["gather"] = gather
+        best = max(gather["containers_to_rank0_peer_stores"]["value_with_gather"], gather["digests_all_gather"]["value_with_gather"])
+        line["value_with_gather"] = best
+        line["config"]["gather"] = ("value excludes the final gather; value_with_gather = the better of the two in-step forms under "
+                                    "`gather` (containers into rank 0's HBM by peer stores / digest all-gather)")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -574,6 +732,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--prover-logm", type=int, default=20, help="log2 constraints of the prover-phase block (0 = skip)")
     ap.add_argument("--prover-witnesses", type=int, default=4, help="witnesses per GPU per prover step")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed step's output")
     ap.add_argument("--arith", default="auto", choices=["auto", "u64"],
                     help="auto: FP64-pipe butterflies (exact for q < 2^45); u64: integer Shoup butterflies (comparison)")
     args = ap.parse_args()

@@ -260,6 +260,19 @@ const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnosti
 void* lsr_host_alloc(size_t bytes) LSR_NOEXCEPT;
 void  lsr_host_free(void* p) LSR_NOEXCEPT;
 
+/* ---- Final gather over NVLink peer memory (collective C1).  One process per GPU: the gathering rank
+ * allocates the destination with lsr_device_alloc and exports it (lsr_peer_export, a 64-byte handle any transport can
+ * carry); every other rank maps it (lsr_peer_open) and passes `mapped + its slice offset` as d_out_words of
+ * lsr_lwe_commit_batch_device / lsr_prover_commit_quotient_device.  The fused commitment kernel then stores its
+ * container rows straight into the peer's HBM through NVLink / NVSwitch: compute and gather are ONE kernel, there is no
+ * separate collective and no second pass over the containers.  Buffers come from plain cudaMalloc (a handle names a
+ * whole allocation).  lsr_peer_open returns NULL when the two devices have no peer path.                          */
+void* lsr_device_alloc(size_t bytes) LSR_NOEXCEPT;
+void  lsr_device_free(void* d_ptr) LSR_NOEXCEPT;
+int   lsr_peer_export(void* d_ptr, uint8_t handle[64]) LSR_NOEXCEPT;
+void* lsr_peer_open(const uint8_t handle[64]) LSR_NOEXCEPT;
+int   lsr_peer_close(void* d_mapped) LSR_NOEXCEPT;
+
 /* Integer-multiply roofline denominator: dependency-free mad.wide.u32 (wide=1)
  * or mad.lo.u32 (wide=0) on every SM, timed with CUDA events; result in
  * 10^9 IMAD per second.  sm_mhz_effective (optional) = the SM clock implied by

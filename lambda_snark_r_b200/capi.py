@@ -128,6 +128,11 @@ SIGNATURES = {
                                        C.POINTER(C.c_int)]),
     "lsr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "lsr_host_free": (None, [C.c_void_p]),
+    "lsr_device_alloc": (C.c_void_p, [C.c_size_t]),
+    "lsr_device_free": (None, [C.c_void_p]),
+    "lsr_peer_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "lsr_peer_open": (C.c_void_p, [C.c_char_p]),
+    "lsr_peer_close": (C.c_int, [C.c_void_p]),
     "lsr_ntt_set_arith": (C.c_int, [C.c_void_p, C.c_int]),
     "lsr_ntt_arith": (C.c_int, [C.c_void_p]),
     "lsr_lwe_set_arith": (C.c_int, [C.c_void_p, C.c_int]),

@@ -295,6 +295,49 @@ void lsr_host_free(void* p) LSR_NOEXCEPT {
     if (p) cudaFreeHost(p);
 }
 
+/* ------------------------------------------------ peer-memory gather (C1) */
+void* lsr_device_alloc(size_t bytes) LSR_NOEXCEPT {
+    LSR_TRY
+    void* p = nullptr;
+    if (bytes == 0 || !lsr::cuda_ok(cudaSetDevice(lsr::current_device_choice()), "cudaSetDevice") ||
+        !lsr::cuda_ok(cudaMalloc(&p, bytes), "cudaMalloc")) return nullptr;
+    return p;
+    LSR_CATCH(nullptr)
+}
+
+void lsr_device_free(void* d_ptr) LSR_NOEXCEPT {
+    if (d_ptr) cudaFree(d_ptr);
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+
+int lsr_peer_export(void* d_ptr, uint8_t handle[64]) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!d_ptr || !handle) return -1;
+    cudaIpcMemHandle_t h;
+    if (!lsr::cuda_ok(cudaIpcGetMemHandle(&h, d_ptr), "cudaIpcGetMemHandle")) return -1;
+    std::memcpy(handle, &h, sizeof h);
+    return 0;
+    LSR_CATCH(-1)
+}
+
+void* lsr_peer_open(const uint8_t handle[64]) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!handle) return nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    void* p = nullptr;
+    if (!lsr::cuda_ok(cudaSetDevice(lsr::current_device_choice()), "cudaSetDevice") ||
+        !lsr::cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+    return p;
+    LSR_CATCH(nullptr)
+}
+
+int lsr_peer_close(void* d_mapped) LSR_NOEXCEPT {
+    if (!d_mapped) return 0;
+    return lsr::cuda_ok(cudaIpcCloseMemHandle(d_mapped), "cudaIpcCloseMemHandle") ? 0 : -1;
+}
+
 int ntt_mul_pointwise_batch(const NttContext* ctx, uint64_t* result, const uint64_t* a, const uint64_t* b,
                             size_t total) LSR_NOEXCEPT {
     LSR_TRY
