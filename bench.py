@@ -364,6 +364,22 @@ def run_gpu(args):
         if ok_rows != rows.numel():
             raise SystemExit("bench.py: PARITY FAILURE in the NTT block")
 
+    # ---- BASELINE configs[2] in brief: ring degrees 2^10 .. 2^16 at 2^26 coefficients per launch (512 MiB > L2), forward and
+    # inverse; q = 17592169062401 has 2-adicity 13 (n <= 4096), above that 17592180539393.  tools/sweep.py is the full grid.
+    sweep = []
+    if args.sweep:
+        for logn in range(10, 17):
+            sn, sq = 1 << logn, (Q_MOD if logn <= 12 else 17592180539393)
+            sctx = ntt if logn == 12 else api.NttContext(sq, sn)
+            sb = (1 << 26) >> logn
+            sd = data[: (sb * sn) // N_RING].view(sb, sn) if NB * N_RING >= sb * sn else torch.randint(
+                0, sq, (sb, sn), device=dev, dtype=torch.int64, generator=g)
+            tf = timed(lambda: sctx.forward_device(sd.data_ptr(), sb, stream), 3, 5) / 5
+            ti = timed(lambda: sctx.inverse_device(sd.data_ptr(), sb, stream), 3, 5) / 5
+            sweep.append((logn, sb, tf, ti))
+            if sctx is not ntt:
+                sctx.close()
+
     # ---- end to end through the host-pointer C ABI, pinned host buffers
     EB = args.e2e_batch
     h_msgs = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
@@ -670,6 +686,24 @@ def run_gpu(args):
                           "frac": mul_gbs / hbm_peak},
         },
     }
+    if sweep:
+        # per ring degree: NTT/s per GPU and the fraction of the slower of the two roofs (FP64 pipe: 8 instructions per
+        # butterfly, + 6 per coefficient pair of the inverse's n^-1 stage; HBM: 16 B per coefficient, one round trip)
+        rows = []
+        for logn, sb, tf, ti in sweep:
+            sn = 1 << logn
+            bf = (sn // 2) * logn
+            roofs_f = {"hbm": hbm_peak * 1e9 / (16 * sn), "fp64": fp64_peak * 1e9 / (bf * FP64_PER_BUTTERFLY)}
+            roofs_i = {"hbm": roofs_f["hbm"], "fp64": fp64_peak * 1e9 / (bf * FP64_PER_BUTTERFLY + (sn // 2) * FP64_PER_MODMUL)}
+            if arith != "fp64":
+                roofs_f = {"hbm": roofs_f["hbm"], "imad_survey": imad_peak * 1e9 / (bf * IMAD_PER_MODMUL)}
+                roofs_i = {"hbm": roofs_f["hbm"], "imad_survey": imad_peak * 1e9 / ((bf + sn // 2) * IMAD_PER_MODMUL)}
+            bfk, bik = min(roofs_f, key=roofs_f.get), min(roofs_i, key=roofs_i.get)
+            rows.append({"n": sn, "batch": sb, "fwd_per_s": sb / (tf * 1e-3), "inv_per_s": sb / (ti * 1e-3),
+                         "fwd_bound": bfk, "fwd_frac": sb / (tf * 1e-3) / roofs_f[bfk],
+                         "inv_bound": bik, "inv_frac": sb / (ti * 1e-3) / roofs_i[bik],
+                         "fwd_hbm_frac": sb / (tf * 1e-3) / roofs_f["hbm"]})
+        roofline["kernels"]["ntt_sweep"] = rows
     if prover:
         prover["quotient_hbm_frac"] = prover["quotient_GBps"] / hbm_peak
         roofline["kernels"]["quotient_pipeline"] = {
@@ -732,6 +766,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--prover-logm", type=int, default=20, help="log2 constraints of the prover-phase block (0 = skip)")
     ap.add_argument("--prover-witnesses", type=int, default=4, help="witnesses per GPU per prover step")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the ring-degree sweep (configs[2] in brief)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed step's output")
     ap.add_argument("--arith", default="auto", choices=["auto", "u64"],
                     help="auto: FP64-pipe butterflies (exact for q < 2^45); u64: integer Shoup butterflies (comparison)")
