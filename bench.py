@@ -399,6 +399,25 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     e2e_value = world * EB / (e2e_ms * 1e-3)
+    # the same bytes as raw page-locked copies (H2D of the messages and D2H of the containers at the same time, all ranks
+    # at once): what the host's DMA path sustains for this mix, the ceiling of any end-to-end path with this container format
+    d_raw_in = torch.empty((EB, N_RING), dtype=torch.int64, device=dev)
+    d_raw_out = out[:EB] if B >= EB else torch.empty((EB, words), dtype=torch.int64, device=dev)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def raw_copies():
+        with torch.cuda.stream(s_in):
+            d_raw_in.copy_(h_msgs, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_out.copy_(d_raw_out, non_blocking=True)
+
+    raw_copies(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        raw_copies()
+    torch.cuda.synchronize()
+    raw_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    del d_raw_in
     # ---- forward NTT end to end: ntt_forward_batch on page-locked host polynomials (in place: 32 KiB in, 32 KiB out each)
     h_polys = torch.randint(0, Q_MOD, (EB, N_RING), dtype=torch.int64).pin_memory()
 
@@ -713,6 +732,11 @@ def run_gpu(args):
     e2e = {"value": e2e_value, "unit": "commitments/s", "h2d_bytes_per_step": EB * (N_RING + 1) * 8,
            "d2h_bytes_per_step": EB * words * 8, "batch_per_gpu": EB, "ms_per_step": e2e_ms,
            "api": "lwe_commit_batch (C ABI, pinned host buffers)", "numa_node": numa,
+           "raw_copy_ceiling": {"what": "the step's H2D + D2H bytes as bare page-locked copies on two streams, all ranks at once, "
+                                        "slowest rank (no kernels): the host's DMA ceiling for this byte mix",
+                                "ms_per_step": raw_ms, "commitments_per_s_equivalent": world * EB / (raw_ms * 1e-3),
+                                "GBps_total": world * EB * (N_RING + words) * 8 / (raw_ms * 1e-3) / 1e9},
+           "frac_of_raw_copy_ceiling": raw_ms / e2e_ms,
            "ntt_forward": {"value": world * EB / (ntt_e2e_ms * 1e-3), "unit": "NTT/s",
                            "api": "ntt_forward_batch (C ABI, pinned host buffers, in place)"}}
     if prover:

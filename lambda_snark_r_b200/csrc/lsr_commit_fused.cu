@@ -99,10 +99,25 @@ __device__ __forceinline__ u64 commit_finish(u32 idx, u64 v, int ev, const u64* 
     return csub(v, q);
 }
 
+// same without the error term (already added): v canonical -> + Delta * (m[x] mod p) on row K-1
+template <int LOGN, int K>
+__device__ __forceinline__ u64 commit_finish_msg(u32 idx, u64 v, const u64* __restrict__ msg, u64 q, u64 delta,
+                                                 u64 p, u64 pinv, u32 msg_used, u64 pd, u64 pdi) {
+    const u32 x = idx - ((u32)(K - 1) << LOGN);                                // wraps for earlier rows
+    if ((K == 1 || idx >= ((u32)(K > 1 ? K - 1 : 1) << LOGN)) && x < msg_used) {
+        u64 word = __ldcs(msg + x);
+        if (pd) word = div_small(word, pd, pdi);                               // uniform over the CTA
+        const u64 m = p < (1ull << 21) ? (u64)mod_small(word, (u32)p, pinv) : word % p;
+        v = csub(v + delta * m, q);                                            // delta*m <= q-1
+    }
+    return v;
+}
+
 // legacy epilogue: e comes from the int8 buffer in shared memory
 template <int LOGN, int K>
 struct CommitEpilogue {
     static constexpr bool kWholeItem = false;
+    static constexpr bool kRawF64 = false;
     struct Pre {};
     const signed char* E;
     const u64* msg;
@@ -184,9 +199,15 @@ __device__ __forceinline__ int unpack_s8(const u32 (&pk)[4], u32 j) {
 
 // FAST epilogue: the work item (row, tau) samples its own 16 error terms -- before its coefficients are loaded --
 // and finishes + stores its coefficients
-template <int LOGN, int K, int NCH8>
+// POL_F64: the last inverse pass hands over balanced doubles r (|r| <= 0.75 q, lsr_ntt.cuh RAW) and the error term is
+// added BEFORE the one canonicalisation: e + 128 sits in the low word of the double 2^52 + (e + 128) (no conversion
+// instruction), x = r + that is exact, and the compare / select / add of f_to_canonical works on the biased value --
+// 6 FP64-pipe and select instructions per coefficient where the integer form (canonicalise, 64-bit e mod q, add,
+// conditional subtract) took 19.
+template <int LOGN, int K, int NCH8, int POL>
 struct CommitEpilogueFast {
     static constexpr bool kWholeItem = true;
+    static constexpr bool kRawF64 = POL == POL_F64;
     struct Pre { u32 pk[4]; };
     const FusedParams& fp;
     const CdtLanes<NCH8>& cdtl;
@@ -204,10 +225,24 @@ struct CommitEpilogueFast {
     __device__ __forceinline__ void item(u64* __restrict__ g, u32, u32 base, const u64 (&v)[16], const Pre& pre) const {
         constexpr u32 LG = LOGN - 4;
         const ModParams& mp = fp.mp;
+        if constexpr (kRawF64) {
+            const double bias = kTwo52 + 128.0;                         // x = r + e + bias
+            const double off_neg = mp.qd - 128.0, off_pos = -128.0;     // -> (r + e [+ q]) + 2^52
 #pragma unroll
-        for (u32 j = 0; j < 16; j++) {
-            const u32 idx = base + (j << LG);
-            __stcs(g + idx, commit_finish<LOGN, K>(idx, v[j], unpack_s8(pre.pk, j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
+            for (u32 j = 0; j < 16; j++) {
+                const u32 idx = base + (j << LG);
+                const u32 byte = ((pre.pk[j >> 2] >> (8u * (j & 3u))) & 0xffu) ^ 0x80u;        // e + 128
+                const double x = __dadd_rn(as_d(v[j]), as_d(kTwo52Bits | (u64)byte));
+                const double off = x < bias ? off_neg : off_pos;
+                const u64 c = as_u(__dadd_rn(x, off)) & 0x000fffffffffffffull;                 // (r + e) mod q, canonical
+                __stcs(g + idx, commit_finish_msg<LOGN, K>(idx, c, msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
+            }
+        } else {
+#pragma unroll
+            for (u32 j = 0; j < 16; j++) {
+                const u32 idx = base + (j << LG);
+                __stcs(g + idx, commit_finish<LOGN, K>(idx, v[j], unpack_s8(pre.pk, j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
+            }
         }
     }
 };
@@ -299,8 +334,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         // ---- phase 4+5: inverse transform of the K rows; its last pass (thread tau again owns tau + 256 j) samples
         // e in registers, adds it (and Delta*m on the last row) and stores the container straight to HBM
         if (!LSR_SKIP(fp, 8u)) {
-            const CommitEpilogueFast<LOGN, K, NCH8> epi{fp, cdtl, msg_row, s_lo, s_hi, pd, pdi};
-            tile_inverse_to_global<LOGN, LOGN, POL, CommitEpilogueFast<LOGN, K, NCH8>, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
+            const CommitEpilogueFast<LOGN, K, NCH8, POL> epi{fp, cdtl, msg_row, s_lo, s_hi, pd, pdi};
+            tile_inverse_to_global<LOGN, LOGN, POL, CommitEpilogueFast<LOGN, K, NCH8, POL>, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
         }
         return;
     }

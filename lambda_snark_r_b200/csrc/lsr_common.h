@@ -83,4 +83,16 @@ struct NttTables {
     ulonglong2 head_inv[32];   // first forward pass (up to 5 stages) are uniform over the whole grid
 };
 
+// Optional fusions around an INVERSE transform (the quotient pipeline, lsr_quotient.cu):
+//   mul       the transform's input is data[i] * mul[i] (the pointwise product of two evaluation vectors) instead of data[i]
+//   dst       where the FIRST kernel of the transform writes (nullptr: in place); later kernels work in place on dst
+//   fin_c     the LAST kernel stores (fin_c[i] - x) * fin_scale instead of x
+// All-zero: the plain transform.  Forward kernels ignore it.
+struct InvFusion {
+    const u64* mul;
+    u64* dst;
+    const u64* fin_c;
+    u64 fin_scale;
+};
+
 }  // namespace lsr

@@ -135,6 +135,10 @@ void ntt_destroy(NttContext* ctx);
 // asynchronous launches on `stream`; data on the context's device
 bool ntt_forward_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
 bool ntt_inverse_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream);
+// inverse transform with the quotient pipeline's neighbours fused in (InvFusion, lsr_common.h): input data * mul, first
+// kernel writing to dst, last kernel storing (fin_c - x) * fin_scale.  Not for n <= 16 (ntt_inverse_fused_supported).
+bool ntt_inverse_fused_supported(const NttContext* ctx);
+bool ntt_inverse_fused_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream, const InvFusion& fz);
 bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64* d_b, size_t total,
                       cudaStream_t stream);
 

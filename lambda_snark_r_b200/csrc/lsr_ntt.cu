@@ -71,8 +71,8 @@ static int policy_of(const NttContext* c, bool inverse) {
 }
 
 // d = log n - LT for block tiles (WHOLE = false), ignored otherwise
-template <int LT, bool WHOLE, bool INV>
-static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s, u32 dlog = 0) {
+template <int LT, bool WHOLE, bool INV, bool FUSED = false>
+static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s, u32 dlog = 0, const InvFusion fz = InvFusion{}) {
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
     const size_t smem = (sizeof(u64) << TL) + (ntt_pad<INV>() ? (sizeof(u64) << (TL - 4)) : 0);
     const size_t tiles = (total + ((size_t)1 << TL) - 1) >> TL;
@@ -80,62 +80,65 @@ static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t 
     if (tiles > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
     if (pol == POL_F64) {
-        auto k = ntt_tile_kernel<LT, WHOLE, POL_F64, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_F64, INV, FUSED>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables_f, d, total, dlog);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables_f, d, total, dlog, fz);
     } else if (pol == POL_LAZY) {
-        auto k = ntt_tile_kernel<LT, WHOLE, POL_LAZY, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_LAZY, INV, FUSED>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog, fz);
     } else if (pol == POL_GOLD) {
-        auto k = ntt_tile_kernel<LT, WHOLE, POL_GOLD, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_GOLD, INV, FUSED>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog, fz);
     } else {
-        auto k = ntt_tile_kernel<LT, WHOLE, POL_GUARD, INV>;
+        auto k = ntt_tile_kernel<LT, WHOLE, POL_GUARD, INV, FUSED>;
         if (!ensure_smem(k, smem)) return false;
-        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog);
+        k<<<(unsigned)tiles, kNttThreads, smem, s>>>(c->mp, c->tables, d, total, dlog, fz);
     }
     return cuda_ok(cudaGetLastError(), "ntt_tile_kernel launch");
 }
 
 template <int S, bool INV, bool FIRST>
-static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0,
+                          const u64* fin_c = nullptr, u64 fin_scale = 0) {
     const size_t cols = batch << (logn - S);
     const size_t blocks = (cols + kNttThreads - 1) / kNttThreads;
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
-    if (pol == POL_F64)       ntt_column_kernel<S, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0);
-    else if (pol == POL_LAZY) ntt_column_kernel<S, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
-    else if (pol == POL_GOLD) ntt_column_kernel<S, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
-    else                      ntt_column_kernel<S, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    if (pol == POL_F64)       ntt_column_kernel<S, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
+    else if (pol == POL_LAZY) ntt_column_kernel<S, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+    else if (pol == POL_GOLD) ntt_column_kernel<S, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+    else                      ntt_column_kernel<S, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
     return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
 }
 
 template <bool INV, bool FIRST>
-static bool launch_column_s(int S, const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+static bool launch_column_s(int S, const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0,
+                            const u64* fin_c = nullptr, u64 fin_scale = 0) {
     switch (S) {
-        case 1: return launch_column<1, INV, FIRST>(c, d, batch, s, logn, s0);
-        case 2: return launch_column<2, INV, FIRST>(c, d, batch, s, logn, s0);
-        case 3: return launch_column<3, INV, FIRST>(c, d, batch, s, logn, s0);
-        case 4: return launch_column<4, INV, FIRST>(c, d, batch, s, logn, s0);
-        case 5: return launch_column<5, INV, FIRST>(c, d, batch, s, logn, s0);
+        case 1: return launch_column<1, INV, FIRST>(c, d, batch, s, logn, s0, fin_c, fin_scale);
+        case 2: return launch_column<2, INV, FIRST>(c, d, batch, s, logn, s0, fin_c, fin_scale);
+        case 3: return launch_column<3, INV, FIRST>(c, d, batch, s, logn, s0, fin_c, fin_scale);
+        case 4: return launch_column<4, INV, FIRST>(c, d, batch, s, logn, s0, fin_c, fin_scale);
+        case 5: return launch_column<5, INV, FIRST>(c, d, batch, s, logn, s0, fin_c, fin_scale);
         default: set_error("bad column pass"); return false;
     }
 }
 
 // S1 + S2 column stages in one HBM round trip (ntt_column2_kernel)
 template <int S1, int S2, bool INV, bool FIRST>
-static bool launch_column2(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0) {
+static bool launch_column2(const NttContext* c, u64* d, size_t batch, cudaStream_t s, u32 logn, u32 s0,
+                           const u64* fin_c = nullptr, u64 fin_scale = 0) {
     const size_t blocks = batch << (logn - 12);          // 4096 coefficients per CTA
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
-    if (pol == POL_F64)       ntt_column2_kernel<S1, S2, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0);
-    else if (pol == POL_LAZY) ntt_column2_kernel<S1, S2, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
-    else if (pol == POL_GOLD) ntt_column2_kernel<S1, S2, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
-    else                      ntt_column2_kernel<S1, S2, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0);
+    if (pol == POL_F64)       ntt_column2_kernel<S1, S2, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
+    else if (pol == POL_LAZY) ntt_column2_kernel<S1, S2, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+    else if (pol == POL_GOLD) ntt_column2_kernel<S1, S2, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+    else                      ntt_column2_kernel<S1, S2, POL_GUARD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
     return cuda_ok(cudaGetLastError(), "ntt_column2_kernel launch");
 }
 
@@ -156,13 +159,19 @@ static bool column2_enabled() {
 // (Issuing the two kernels in L2-sized batch chunks so the second finds the first one's output on chip
 // was measured and rejected: 16/32/64 MB chunks ran at 0.60/0.77/0.85 of the whole-batch rate -- the
 // small dependent launches cost more in tails than the second HBM round trip does.)
-template <int LOGN, bool INV>
-static bool launch_whole(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
-    return launch_tile<LOGN, true, INV>(c, d, batch << LOGN, s);
+template <int LOGN, bool INV, bool FUSED>
+static bool launch_whole(const NttContext* c, u64* d, size_t batch, cudaStream_t s, const InvFusion& fz) {
+    return launch_tile<LOGN, true, INV, FUSED>(c, d, batch << LOGN, s, 0u, fz);
 }
 
-template <bool INV>
-static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
+// fz (inverse only): the first kernel (tile kernel on 4096-blocks) takes the product and the destination, the kernel that
+// ends the transform takes the finishing step; everything after the first kernel works in place on the destination
+template <bool INV, bool FUSED>
+static bool launch_big(const NttContext* c, u64* d_in, size_t batch, cudaStream_t s, const InvFusion& fz) {
+    const InvFusion first{fz.mul, fz.dst, nullptr, 0};
+    u64* d = (INV && fz.dst) ? fz.dst : d_in;
+    const u64* fin_c = INV ? fz.fin_c : nullptr;
+    const u64 fin_scale = fz.fin_scale;
     const u32 logn = c->logn;
     const int C = (int)logn - 12;                       // column stages
     const int passes = (C + 4) / 5;
@@ -178,9 +187,9 @@ static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s
         // 6 .. 8 column stages: one shared-memory pass; 9 .. 12: a register pass of C - 8 stages + one of 8
         const int head = C > 8 ? C - 8 : 0;
         auto fused = [&](bool first) -> bool {
-            if (C == 6) return launch_column2<3, 3, INV, true>(c, d, batch, s, logn, 0u);
-            if (C == 7) return launch_column2<4, 3, INV, true>(c, d, batch, s, logn, 0u);
-            return first ? launch_column2<4, 4, INV, true>(c, d, batch, s, logn, 0u)
+            if (C == 6) return launch_column2<3, 3, INV, true>(c, d, batch, s, logn, 0u, fin_c, fin_scale);
+            if (C == 7) return launch_column2<4, 3, INV, true>(c, d, batch, s, logn, 0u, fin_c, fin_scale);
+            return first ? launch_column2<4, 4, INV, true>(c, d, batch, s, logn, 0u, fin_c, fin_scale)
                          : launch_column2<4, 4, INV, false>(c, d, batch, s, logn, (u32)head);
         };
         if (!INV) {
@@ -188,9 +197,9 @@ static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s
             if (!fused(head == 0)) return false;
             return launch_tile<12, false, false>(c, d, total, s, (u32)C);
         }
-        if (!launch_tile<12, false, true>(c, d, total, s, (u32)C)) return false;
+        if (!launch_tile<12, false, true, FUSED>(c, d_in, total, s, (u32)C, first)) return false;
         if (!fused(head == 0)) return false;
-        return head ? launch_column_s<true, true>(head, c, d, batch, s, logn, 0u) : true;
+        return head ? launch_column_s<true, true>(head, c, d, batch, s, logn, 0u, fin_c, fin_scale) : true;
     }
     if (!INV) {
         for (int i = 0; i < passes; i++) {
@@ -200,40 +209,55 @@ static bool launch_big(const NttContext* c, u64* d, size_t batch, cudaStream_t s
         }
         return launch_tile<12, false, false>(c, d, total, s, (u32)C);
     }
-    if (!launch_tile<12, false, true>(c, d, total, s, (u32)C)) return false;
+    if (!launch_tile<12, false, true, FUSED>(c, d_in, total, s, (u32)C, first)) return false;
     for (int i = passes - 1; i >= 0; i--) {
-        const bool ok = i == 0 ? launch_column_s<true, true>(S[i], c, d, batch, s, logn, (u32)s0[i])
+        const bool ok = i == 0 ? launch_column_s<true, true>(S[i], c, d, batch, s, logn, (u32)s0[i], fin_c, fin_scale)
                                : launch_column_s<true, false>(S[i], c, d, batch, s, logn, (u32)s0[i]);
         if (!ok) return false;
     }
     return true;
 }
 
-template <bool INV>
-static bool dispatch(const NttContext* c, u64* d, size_t batch, cudaStream_t s) {
-    if (reinterpret_cast<uintptr_t>(d) & 15u) {     // unit-stride passes use 16-byte global accesses
+static bool plan_is_one_pass(uint32_t logn);
+
+template <bool INV, bool FUSED = false>
+static bool dispatch(const NttContext* c, u64* d, size_t batch, cudaStream_t s, const InvFusion fz = InvFusion{}) {
+    if ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(fz.dst)) & 15u) {     // unit-stride passes use 16-byte global accesses
         set_error("device polynomial buffer must be 16-byte aligned");
         return false;
     }
+    if ((fz.mul || fz.dst || fz.fin_c) && (!FUSED || plan_is_one_pass(c->logn))) {
+        set_error("fused inverse transform: unsupported shape");           // callers fall back to separate kernels
+        return false;
+    }
     switch (c->logn) {
-        case 1: return launch_whole<1, INV>(c, d, batch, s);
-        case 2: return launch_whole<2, INV>(c, d, batch, s);
-        case 3: return launch_whole<3, INV>(c, d, batch, s);
-        case 4: return launch_whole<4, INV>(c, d, batch, s);
-        case 5: return launch_whole<5, INV>(c, d, batch, s);
-        case 6: return launch_whole<6, INV>(c, d, batch, s);
-        case 7: return launch_whole<7, INV>(c, d, batch, s);
-        case 8: return launch_whole<8, INV>(c, d, batch, s);
-        case 9: return launch_whole<9, INV>(c, d, batch, s);
-        case 10: return launch_whole<10, INV>(c, d, batch, s);
-        case 11: return launch_whole<11, INV>(c, d, batch, s);
-        case 12: return launch_whole<12, INV>(c, d, batch, s);
-        case 13: return launch_whole<13, INV>(c, d, batch, s);
+        case 1: return launch_whole<1, INV, FUSED>(c, d, batch, s, fz);
+        case 2: return launch_whole<2, INV, FUSED>(c, d, batch, s, fz);
+        case 3: return launch_whole<3, INV, FUSED>(c, d, batch, s, fz);
+        case 4: return launch_whole<4, INV, FUSED>(c, d, batch, s, fz);
+        case 5: return launch_whole<5, INV, FUSED>(c, d, batch, s, fz);
+        case 6: return launch_whole<6, INV, FUSED>(c, d, batch, s, fz);
+        case 7: return launch_whole<7, INV, FUSED>(c, d, batch, s, fz);
+        case 8: return launch_whole<8, INV, FUSED>(c, d, batch, s, fz);
+        case 9: return launch_whole<9, INV, FUSED>(c, d, batch, s, fz);
+        case 10: return launch_whole<10, INV, FUSED>(c, d, batch, s, fz);
+        case 11: return launch_whole<11, INV, FUSED>(c, d, batch, s, fz);
+        case 12: return launch_whole<12, INV, FUSED>(c, d, batch, s, fz);
+        case 13: return launch_whole<13, INV, FUSED>(c, d, batch, s, fz);
         default:
-            if (c->logn >= 14 && c->logn <= (uint32_t)kMaxEngineLogN) return launch_big<INV>(c, d, batch, s);
+            if (c->logn >= 14 && c->logn <= (uint32_t)kMaxEngineLogN) return launch_big<INV, FUSED>(c, d, batch, s, fz);
             set_error("unsupported ring degree");
             return false;
     }
+}
+
+// one-pass plans (n <= 16) read and write global memory inside the single pass: no staging loop to fuse into
+static bool plan_is_one_pass(uint32_t logn) { return logn <= 4; }
+
+bool ntt_inverse_fused_supported(const NttContext* ctx) { return !plan_is_one_pass(ctx->logn); }
+
+bool ntt_inverse_fused_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream, const InvFusion& fz) {
+    return dispatch<true, true>(ctx, d_data, batch, stream, fz);
 }
 
 bool ntt_forward_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStream_t stream) {
@@ -269,9 +293,10 @@ bool ntt_bitrev_launch(const NttContext* ctx, u64* d_data, size_t batch, cudaStr
 bool pointwise_launch(const NttContext* ctx, u64* d_r, const u64* d_a, const u64* d_b, size_t total,
                       cudaStream_t stream) {
     if (total == 0) return true;
-    size_t blocks = (total / 2 + 255) / 256;
-    blocks = std::max<size_t>(1, std::min<size_t>(blocks, 148 * 16));   // grid-stride, multiple of the SM count
-    pointwise_mul_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ctx->mp, d_r, d_a, d_b, total);
+    size_t blocks = (total / 2 + 256 * kPointwiseU - 1) / (256 * kPointwiseU);
+    blocks = std::max<size_t>(1, std::min<size_t>(blocks, 148 * 32));   // tile-stride loop, multiple of the SM count
+    if (ctx->mp.gold) pointwise_mul_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(ctx->mp, d_r, d_a, d_b, total);
+    else pointwise_mul_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(ctx->mp, d_r, d_a, d_b, total);
     return cuda_ok(cudaGetLastError(), "pointwise_mul_kernel launch");
 }
 

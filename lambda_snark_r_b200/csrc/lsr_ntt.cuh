@@ -141,15 +141,19 @@ __device__ __forceinline__ void fwd_network(u64 (&v)[1 << R], const ulonglong2* 
 // last inverse stage (m = 1): scalar n^-1 folded in (SEAL transform_from_rev
 // with scalar; w_scaled = inv[1] is already multiplied by n^-1), then the
 // final correction to [0, q)
-template <int POL>
+// RAW (POL_F64 only): leave the two outputs as balanced doubles, |r| <= 0.75 q, for an epilogue that keeps working
+// in FP64 and canonicalises itself (the fused commitment adds its error term first)
+template <int POL, bool RAW = false>
 __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglong2 w_scaled,
                                                    const ulonglong2 n_inv, int sigma,
                                                    const ModParams& mp) {
     const u64 X = x, Y = y;
     if (POL == POL_F64) {
         const double Xd = as_d(X), Yd = as_d(Y);
-        x = f_to_canonical(mulmod_f(__dadd_rn(Xd, Yd), as_d(n_inv.x), as_d(n_inv.y), mp.qd), mp);
-        y = f_to_canonical(mulmod_f(__dadd_rn(Xd, -Yd), as_d(w_scaled.x), as_d(w_scaled.y), mp.qd), mp);
+        const double rx = mulmod_f(__dadd_rn(Xd, Yd), as_d(n_inv.x), as_d(n_inv.y), mp.qd);
+        const double ry = mulmod_f(__dadd_rn(Xd, -Yd), as_d(w_scaled.x), as_d(w_scaled.y), mp.qd);
+        x = RAW ? as_u(rx) : f_to_canonical(rx, mp);
+        y = RAW ? as_u(ry) : f_to_canonical(ry, mp);
     } else if (POL == POL_GOLD) {
         x = gold_mul(gold_add(X, Y), n_inv.x);
         y = gold_mul(gold_sub(X, Y), w_scaled.x);
@@ -166,7 +170,7 @@ __device__ __forceinline__ void inv_last_butterfly(u64& x, u64& y, const ulonglo
 // sigma0 = number of inverse stages already done before this pass (growth
 // bound: a value entering inverse stage sigma is < 4q * 2^sigma on the lazy
 // path).  FINAL: the pass ends with the m = 1 stage (forward stage 0).
-template <int R, int r, int POL, bool FINAL, bool LL, bool HEAD>
+template <int R, int r, int POL, bool FINAL, bool LL, bool HEAD, bool RAW = false>
 __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                           const ulonglong2* __restrict__ head,
                                           u32 T0, u32 stride, int sigma0, const ulonglong2 n_inv,
@@ -183,7 +187,7 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                 const int j = (t << (r + 1)) + jl;
                 const int jj = j + half;
                 if constexpr (FINAL && r == R - 1) {
-                    inv_last_butterfly<POL>(v[j], v[jj], w, n_inv, sigma0 + r, mp);
+                    inv_last_butterfly<POL, RAW>(v[j], v[jj], w, n_inv, sigma0 + r, mp);
                 } else {
                     const u64 X = v[j], Y = v[jj];
                     if (POL == POL_F64) {
@@ -203,7 +207,7 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        inv_stage<R, r + 1, POL, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
+        inv_stage<R, r + 1, POL, FINAL, LL, HEAD, RAW>(v, tw, head, T0, stride, sigma0, n_inv, mp);
     }
 }
 
@@ -213,12 +217,12 @@ __device__ __forceinline__ void inv_stage(u64 (&v)[1 << R], const ulonglong2* __
 // bound of a product.  Reducing the 2^(R-2) elements with the largest bounds (j < 2^(R-2)) leaves
 // every element <= 2P = 1.5 q, so the next pass (R <= 5) sees |X - Y| <= 2^R * 1.5 q <= 48 q
 // < 2^51 for q < 2^45.  Cost: 3 FP64 instructions on a quarter of the elements per pass.
-template <int R, int POL, bool FINAL, bool LL = false, bool HEAD = false>
+template <int R, int POL, bool FINAL, bool LL = false, bool HEAD = false, bool RAW = false>
 __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                             u32 T0, int sigma0, const ulonglong2 n_inv,
                                             const ModParams& mp, u32 stride = 0,
                                             const ulonglong2* __restrict__ head = nullptr) {
-    inv_stage<R, 0, POL, FINAL, LL, HEAD>(v, tw, head, T0, stride, sigma0, n_inv, mp);
+    inv_stage<R, 0, POL, FINAL, LL, HEAD, RAW>(v, tw, head, T0, stride, sigma0, n_inv, mp);
     if constexpr (POL == POL_F64 && !FINAL) {
         constexpr int NRED = R >= 2 ? (1 << (R - 2)) : 1;
 #pragma unroll
@@ -305,8 +309,22 @@ struct TileIo {
 // pre(W) runs before the coefficients of the work item are loaded (few live registers) and hands its result to item().
 struct NoEpilogue {
     static constexpr bool kWholeItem = false;
+    static constexpr bool kRawF64 = false;    // true: POL_F64 final inverse pass hands balanced doubles to item()
     struct Pre {};
     __device__ __forceinline__ u64 operator()(u32, u64 v) const { return v; }
+};
+
+// Final pass of a fused inverse transform (InvFusion::fin_c): value = (c[idx] - value) * scale, or the value itself when c is null.
+struct FinEpilogue {
+    static constexpr bool kWholeItem = false;
+    static constexpr bool kRawF64 = false;
+    struct Pre {};
+    const u64* c;          // tile-relative
+    u64 scale;
+    const ModParams* mp;
+    __device__ __forceinline__ u64 operator()(u32 idx, u64 v) const {
+        return c ? field_mul(field_sub(__ldcs(c + idx), v, *mp), scale, *mp) : v;
+    }
 };
 
 // WHOLE: the tile holds whole polynomials (LT == log n).  Otherwise it is one 2^LT block of a larger
@@ -385,7 +403,8 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         } else {
             constexpr int sigma0 = LT - SL - R;           // inverse stages already done
             static_assert(!INVERSE || !FINAL || (SL == 0 && WHOLE), "final inverse pass must contain stage 0");
-            inv_network<R, POL, FINAL, LL, HEAD>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
+            constexpr bool RAW = FINAL && OUT == IO_GLOBAL && POL == POL_F64 && Epi::kWholeItem && Epi::kRawF64;
+            inv_network<R, POL, FINAL, LL, HEAD, RAW>(v, tw, T0, sigma0, tb_.n_inv, mp, ll_stride, tb_.head_inv);
         }
         if constexpr (OUT == IO_GLOBAL && LG == 0 && R >= 1 && std::is_same<Epi, NoEpilogue>::value) {
             if (live) {
@@ -501,9 +520,10 @@ __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const Nt
 template <int LT>
 constexpr int ntt_min_blocks() { return LT <= 12 ? LSR_NTT_MINB : (LT == 13 ? 2 : 1); }
 
-template <int LT, bool WHOLE, int POL, bool INVERSE>
+// FUSED (inverse only): the InvFusion hooks are compiled in; the plain instantiation is exactly the stand-alone transform.
+template <int LT, bool WHOLE, int POL, bool INVERSE, bool FUSED = false>
 __global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
-ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems, u32 d) {
+ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems, u32 d, const InvFusion fz) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
     constexpr u32 TILE = 1u << TL;
@@ -533,14 +553,34 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
                 const u32 i = threadIdx.x + k * kNttThreads;
                 x[k] = i < valid ? __ldcs(g + i) : 0ull;
             }
+            if (FUSED && fz.mul) {                         // fused pointwise product (uniform branch): input = data * mul
+                const u64* __restrict__ g2 = fz.mul + tile0;
+                u64 y[PER_THREAD];
+#pragma unroll
+                for (u32 k = 0; k < PER_THREAD; k++) {
+                    const u32 i = threadIdx.x + k * kNttThreads;
+                    y[k] = i < valid ? __ldcs(g2 + i) : 0ull;
+                }
+#pragma unroll
+                for (u32 k = 0; k < PER_THREAD; k++) x[k] = mulmod_exact(x[k], y[k], mp);
+            }
 #pragma unroll
             for (u32 k = 0; k < PER_THREAD; k++) {
                 const u32 i = threadIdx.x + k * kNttThreads;
                 sm[sidx<ntt_pad<true>()>(i)] = to_working<POL>(sanitize(x[k], io.limit, mp));
             }
             __syncthreads();
+            if constexpr (FUSED) {
+                // out of place (first kernel of a fused transform) and / or the finishing epilogue on the last pass
+                const TileIo io_out{fz.dst ? fz.dst + tile0 : g, valid, io.sanitize, io.limit};
+                const FinEpilogue fin{(WHOLE && fz.fin_c) ? fz.fin_c + tile0 : nullptr, fz.fin_scale, &mp};
+                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, FinEpilogue, ntt_pad<true>()>(sm, io_out, tbl, mp, TILE, tb, d, fin);
+            } else {
+                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true>()>(sm, io, tbl, mp, TILE, tb, d);
+            }
+        } else {
+            tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true>()>(sm, io, tbl, mp, TILE, tb, d);
         }
-        tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true>()>(sm, io, tbl, mp, TILE, tb, d);
     }
 }
 
@@ -556,7 +596,8 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 // ---------------------------------------------------------------------------
 template <int S, int POL, bool INVERSE, bool FIRST>
 __global__ void __launch_bounds__(kNttThreads)
-ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0) {
+ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0,
+                  const u64* __restrict__ fin_c, u64 fin_scale) {
     const u32 LG = logn - s0 - (u32)S;                   // log2 g
     const size_t cols = batch << (logn - (u32)S);        // (polynomial, block, column) triples
     const size_t idx = (size_t)blockIdx.x * kNttThreads + threadIdx.x;
@@ -591,6 +632,11 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
         for (int j = 0; j < (1 << S); j++) v[j] = g[(size_t)j << LG];
         inv_network<S, POL, FIRST>(v, tbl.inv, T0, (int)LG, tbl.n_inv, mp);
     }
+    if (INVERSE && FIRST && fin_c) {                     // fused finishing step: (c - x) * scale (InvFusion)
+        const u64* __restrict__ cf = fin_c + (pb << (LG + (u32)S)) + c;
+#pragma unroll
+        for (int j = 0; j < (1 << S); j++) v[j] = field_mul(field_sub(cf[(size_t)j << LG], v[j], mp), fin_scale, mp);
+    }
 #pragma unroll
     for (int j = 0; j < (1 << S); j++) g[(size_t)j << LG] = v[j];
 }
@@ -605,7 +651,8 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
 // ---------------------------------------------------------------------------
 template <int S1, int S2, int POL, bool INVERSE, bool FIRST>
 __global__ void __launch_bounds__(kNttThreads)
-ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0) {
+ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0,
+                   const u64* __restrict__ fin_c, u64 fin_scale) {
     constexpr u32 LR = S1 + S2, ROWS = 1u << LR, ELEMS = 4096u, COLS = ELEMS / ROWS, LC = 12 - LR;
     static_assert(S1 >= S2 && S1 <= 4 && COLS >= 16, "row segments of at least 128 bytes");
     __shared__ __align__(16) u64 sm[ELEMS];
@@ -645,6 +692,12 @@ ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ da
             if (!INVERSE) fwd_network<S1, POL>(v, tbl.fwd, T0, mp);
             else inv_network<S1, POL, FIRST>(v, tbl.inv, T0, (int)(LG + S2), tbl.n_inv, mp);
             if (to_global) {
+                if (INVERSE && FIRST && fin_c) {             // fused finishing step: (c - x) * scale (InvFusion)
+                    const u64* __restrict__ cf = fin_c + (pb << (LG + LR)) + c0;
+#pragma unroll
+                    for (int j = 0; j < (1 << S1); j++)
+                        v[j] = field_mul(field_sub(cf[((size_t)(r0 + ((u32)j << S2)) << LG) + cc], v[j], mp), fin_scale, mp);
+                }
 #pragma unroll
                 for (int j = 0; j < (1 << S1); j++) g[((size_t)(r0 + ((u32)j << S2)) << LG) + cc] = v[j];
             } else {
@@ -690,28 +743,41 @@ ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ da
 
 // ---------------------------------------------------------------------------
 // K3: result[i] = a[i] * b[i] mod q, exact for any u64 inputs
-// (ntt.cpp:106-119).  Grid-stride, 16-byte accesses, result may alias a or b.
+// (ntt.cpp:106-119).  16-byte accesses, result may alias a or b (same index).
+// A CTA takes tiles of 256 * U pairs; a thread issues its 2U loads before the first product (streaming: every word is
+// touched once) and stores after the last load, so exact aliasing is safe.  GOLD is a template parameter so that the
+// modulus test is not in the loop.  tools/pointwise_variants.cu: U = 4 with streaming hints 6.4 TB/s against 6.16 for
+// the one-pair-per-iteration form at the bench's 3 x 512 MiB working set.
 // ---------------------------------------------------------------------------
+constexpr int kPointwiseU = 4;
+template <bool GOLD>
 static __global__ void __launch_bounds__(256)
 pointwise_mul_kernel(const ModParams mp, u64* result, const u64* a, const u64* b, size_t total) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t pairs = total >> 1;
     const bool aligned = ((((size_t)result) | ((size_t)a) | ((size_t)b)) & 15u) == 0;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto mul = [&](u64 x, u64 y) { return GOLD ? gold_mul(x, y) : barrett128(x * y, __umul64hi(x, y), mp); };
     if (aligned) {
         const ulonglong2* a2 = reinterpret_cast<const ulonglong2*>(a);
         const ulonglong2* b2 = reinterpret_cast<const ulonglong2*>(b);
         ulonglong2* r2 = reinterpret_cast<ulonglong2*>(result);
-        for (size_t p = i; p < pairs; p += stride) {
-            const ulonglong2 x = a2[p], y = b2[p];
-            ulonglong2 r;
-            r.x = mulmod_exact(x.x, y.x, mp);
-            r.y = mulmod_exact(x.y, y.y, mp);
-            r2[p] = r;
+        const size_t tile = (size_t)blockDim.x * kPointwiseU;
+        for (size_t base = (size_t)blockIdx.x * tile; base < pairs; base += (size_t)gridDim.x * tile) {
+            ulonglong2 x[kPointwiseU], y[kPointwiseU];
+#pragma unroll
+            for (int u = 0; u < kPointwiseU; u++) {
+                const size_t p = base + (size_t)u * blockDim.x + threadIdx.x;
+                if (p < pairs) { x[u] = __ldcs(a2 + p); y[u] = __ldcs(b2 + p); }
+            }
+#pragma unroll
+            for (int u = 0; u < kPointwiseU; u++) {
+                const size_t p = base + (size_t)u * blockDim.x + threadIdx.x;
+                if (p < pairs) __stcs(r2 + p, make_ulonglong2(mul(x[u].x, y[u].x), mul(x[u].y, y[u].y)));
+            }
         }
-        if (i == 0 && (total & 1)) result[total - 1] = mulmod_exact(a[total - 1], b[total - 1], mp);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (total & 1)) result[total - 1] = mul(a[total - 1], b[total - 1]);
     } else {
-        for (size_t p = i; p < total; p += stride) result[p] = mulmod_exact(a[p], b[p], mp);
+        const size_t stride = (size_t)gridDim.x * blockDim.x;
+        for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) result[p] = mul(a[p], b[p]);
     }
 }
 

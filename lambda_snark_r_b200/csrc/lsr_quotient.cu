@@ -304,14 +304,18 @@ static bool quotient_compute(R1csHandle* h, QuotientState* st, const u64* dz, si
             ok = st->coef.reserve(em * 8) &&
                  cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
         ok = ok && ntt_forward_launch(st->coset, dE, 2 * W, s);            // A_z, B_z only (C_z stays as coefficients)
-        if (ok) {
+        if (ok && ntt_inverse_fused_supported(st->coset)) {
+            // one inverse transform with both neighbours fused in: its first kernel reads a * b (the coset product is
+            // never written) and writes to Q, its last kernel stores (C - N) / 2 -- two 24 B/coefficient sweeps less
+            ok = ntt_inverse_fused_launch(st->coset, dE, W, s, InvFusion{dE + W * (size_t)m, dQ, dE + 2 * W * (size_t)m, inv2});
+        } else if (ok) {
             coset_product_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m);
             ok = cuda_ok(cudaGetLastError(), "coset_product_kernel");
-        }
-        ok = ok && ntt_inverse_launch(st->coset, dQ, W, s);
-        if (ok) {
-            quotient_finish_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE + 2 * W * (size_t)m, dQ, W * (size_t)m, inv2);
-            ok = cuda_ok(cudaGetLastError(), "quotient_finish_kernel");
+            ok = ok && ntt_inverse_launch(st->coset, dQ, W, s);
+            if (ok) {
+                quotient_finish_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE + 2 * W * (size_t)m, dQ, W * (size_t)m, inv2);
+                ok = cuda_ok(cudaGetLastError(), "quotient_finish_kernel");
+            }
         }
     } else if (ok) {
         // m = 1: A_z, B_z, C_z are constants; the numerator a*b - c has degree 0 < deg(X - 1), so the quotient is 0
