@@ -495,6 +495,12 @@ int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,
  * when some lane's prefix ties with a table prefix.  HOST memory.                      */
 int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint32_t* out,
                              int variant) LSR_NOEXCEPT;
+/* Timing hook, the device analogue of the reference's dudect harness (cpp-core/tools/dudect_sampler.cpp:105-141): the
+ * same searches, and for every warp (32 consecutive u) the clock64() ticks it spent inside the search ->
+ * cycles_per_warp[ceil(count / 32)].  A caller feeds two input classes (fixed / random) and compares the two timing
+ * distributions with Welch's t (tests/test_gpu_timing.py, threshold |t| < 4.5 as in the reference).  HOST memory. */
+int lsr_cdt_timing_device(double sigma, const uint64_t* u, size_t count, int variant, uint32_t* out,
+                          uint64_t* cycles_per_warp) LSR_NOEXCEPT;
 
 /* Test hook for the Goldilocks (q = 2^64 - 2^32 + 1) primitives of the quotient pipeline's transforms, on any
  * 64-bit operands: out[4i..4i+3] = { a*b mod q, (a + (b mod q)) mod q through the lazy sum of the forward

@@ -104,7 +104,29 @@ def build_profiling(force: bool = False, verbose: bool = False) -> Path:
     return so
 
 
+def build_variant(name: str, defines: tuple, force: bool = False, verbose: bool = False) -> Path:
+    """tools/ only: lib/liblambda_snark_core_<name>.so compiled with extra -D switches (kernel-variant experiments;
+    never loaded by the package itself)."""
+    objdir = PKG / f"_build_{name}"
+    objdir.mkdir(exist_ok=True)
+    LIB.mkdir(exist_ok=True)
+    so = LIB / f"liblambda_snark_core_{name}.so"
+    with ThreadPoolExecutor(max_workers=min(6, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force, verbose, objdir, tuple(defines)), SOURCES))
+    if force or not so.exists() or so.stat().st_mtime < max(o.stat().st_mtime for o in objs):
+        cmd = [_nvcc(), "-shared", *ARCH, "-ccbin", shutil.which("g++") or "g++", "-cudart", "static",
+               "-o", str(so), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return so
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:      # python -m lambda_snark_r_b200._build --variant NAME -DX=1 -DY=2
+        i = sys.argv.index("--variant")
+        print("built", build_variant(sys.argv[i + 1], tuple(a for a in sys.argv[i + 2:] if a.startswith("-D")), verbose=True))
+        sys.exit(0)
     if "--profiling" in sys.argv:
         print("built", build_profiling(force="--force" in sys.argv, verbose=True))
     else:

@@ -143,6 +143,7 @@ SIGNATURES = {
                                             C.POINTER(C.c_int)]),
     "lsr_sample_gaussian_seeded": (C.c_int, [u64p, C.c_size_t, C.c_double, C.c_char_p]),
     "lsr_cdt_magnitude_device": (C.c_int, [C.c_double, u64p, C.c_size_t, C.POINTER(C.c_uint32), C.c_int]),
+    "lsr_cdt_timing_device": (C.c_int, [C.c_double, u64p, C.c_size_t, C.c_int, C.POINTER(C.c_uint32), u64p]),
     "lsr_goldilocks_probe_device": (C.c_int, [u64p, u64p, C.c_size_t, u64p]),
     "lsr_lwe_sample_se": (C.c_int, [C.c_void_p, C.c_uint64, i64p, i64p]),
     "lsr_lwe_commit_explicit": (C.c_int, [C.c_void_p, u64p, C.c_size_t, i64p, i64p, C.c_size_t, u64p]),

@@ -631,6 +631,15 @@ int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint
     LSR_CATCH(-1)
 }
 
+int lsr_cdt_timing_device(double sigma, const uint64_t* u, size_t count, int variant, uint32_t* out,
+                          uint64_t* cycles_per_warp) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!u || !out || !cycles_per_warp || count == 0 || variant < 0 || variant > 4) return -1;
+    return lsr::cdt_probe_host(sigma, reinterpret_cast<const u64*>(u), count, out, variant,
+                               reinterpret_cast<u64*>(cycles_per_warp)) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
 /* --------------------------------------------------------------- sampler */
 int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma, const uint8_t seed32[32]) LSR_NOEXCEPT {
     LSR_TRY

@@ -208,12 +208,20 @@ template <int LOGN, int K, int NCH8, int POL>
 struct CommitEpilogueFast {
     static constexpr bool kWholeItem = true;
     static constexpr bool kRawF64 = POL == POL_F64;
+    // PARKED (k >= 2): the last inverse pass takes the rows in order, and once a thread has loaded its 16 coefficients of
+    // row 0 into registers those 16 shared-memory slots are its own and dead.  It parks the 16 message words it will need
+    // on the message row (same coefficient indices) there with cp.async: no register holds them, and by the time the
+    // message row's work item reaches its epilogue they have long arrived -- the epilogue reads shared memory instead of
+    // waiting on L2 / HBM (the first use of a message word was 7.9 % of the kernel's stall samples).
+    static constexpr bool kParkMsg = kRawF64 && K >= 2;
     struct Pre { u32 pk[4]; };
     const FusedParams& fp;
     const CdtLanes<NCH8>& cdtl;
     const u64* msg;
     u32 s_lo, s_hi;
     u64 pd, pdi;
+    u64* sm;                      // the tile (padded layout)
+    static constexpr u32 kStep = (1u << (LOGN - 4)) + (1u << (LOGN - 8));      // padded stride of n/16 coefficients
     __device__ __forceinline__ Pre pre(u32 W) const {
         constexpr u32 LG = LOGN - 4;
         const u32 row = W >> LG, tau = W & ((1u << LG) - 1u);
@@ -222,10 +230,31 @@ struct CommitEpilogueFast {
         else sample_chunk_packed<NCH8>(fp.key, s_lo, s_hi, tau, (u32)K + row, cdtl, r.pk);
         return r;
     }
+    // called right after the work item's coefficients left shared memory
+    __device__ __forceinline__ void loaded(u32 W, u32 base) const {
+        if constexpr (kParkMsg) {
+            constexpr u32 LG = LOGN - 4;
+            if ((W >> LG) == 0u) {
+                const u32 tau = W;
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) {
+                    const u32 x = tau + (j << LG);
+                    if (x < fp.msg_used) {
+                        const u32 dst = (u32)__cvta_generic_to_shared(sm + padx(base) + j * kStep);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(msg + x) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
+    }
     __device__ __forceinline__ void item(u64* __restrict__ g, u32, u32 base, const u64 (&v)[16], const Pre& pre) const {
         constexpr u32 LG = LOGN - 4;
         const ModParams& mp = fp.mp;
         if constexpr (kRawF64) {
+            if constexpr (kParkMsg) {
+                if (base >= ((u32)(K - 1) << LOGN)) asm volatile("cp.async.wait_all;" ::: "memory");    // this thread's own copies
+            }
             const double bias = kTwo52 + 128.0;                         // x = r + e + bias
             const double off_neg = mp.qd - 128.0, off_pos = -128.0;     // -> (r + e [+ q]) + 2^52
 #pragma unroll
@@ -234,8 +263,20 @@ struct CommitEpilogueFast {
                 const u32 byte = ((pre.pk[j >> 2] >> (8u * (j & 3u))) & 0xffu) ^ 0x80u;        // e + 128
                 const double x = __dadd_rn(as_d(v[j]), as_d(kTwo52Bits | (u64)byte));
                 const double off = x < bias ? off_neg : off_pos;
-                const u64 c = as_u(__dadd_rn(x, off)) & 0x000fffffffffffffull;                 // (r + e) mod q, canonical
-                __stcs(g + idx, commit_finish_msg<LOGN, K>(idx, c, msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
+                u64 c = as_u(__dadd_rn(x, off)) & 0x000fffffffffffffull;                       // (r + e) mod q, canonical
+                if constexpr (kParkMsg) {
+                    // message row: its words were parked in row 0's slots of this thread (loaded())
+                    const u32 xm = idx - ((u32)(K - 1) << LOGN);                               // wraps for earlier rows
+                    if (idx >= ((u32)(K - 1) << LOGN) && xm < fp.msg_used) {
+                        u64 word = sm[padx(base - ((u32)(K - 1) << LOGN)) + j * kStep];
+                        if (pd) word = div_small(word, pd, pdi);                               // uniform over the CTA
+                        const u64 m = fp.p < (1ull << 21) ? (u64)mod_small(word, (u32)fp.p, fp.pinv) : word % fp.p;
+                        c = csub(c + fp.delta * m, mp.q);                                      // delta * m <= q - 1
+                    }
+                } else {
+                    c = commit_finish_msg<LOGN, K>(idx, c, msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi);
+                }
+                __stcs(g + idx, c);
             }
         } else {
 #pragma unroll
@@ -304,6 +345,8 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         if (!LSR_SKIP(fp, 2u)) tile_forward<LOGN, LOGN, POL, true, 1>(S, fp.tbl, mp, (u32)K * n, 0u);
 
         // ---- phase 3: mat-vec in place (each coefficient index x is owned by one thread)
+        // (requesting the A-hat pairs of the next x ahead of the products of the current one was measured: no gain in the
+        // phase alone, 2 % slower overall -- 16 more live registers)
         for (u32 x = threadIdx.x; x < (LSR_SKIP(fp, 4u) ? 0u : n); x += kNttThreads) {
             u64 sv[K];
 #pragma unroll
@@ -334,7 +377,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
         // ---- phase 4+5: inverse transform of the K rows; its last pass (thread tau again owns tau + 256 j) samples
         // e in registers, adds it (and Delta*m on the last row) and stores the container straight to HBM
         if (!LSR_SKIP(fp, 8u)) {
-            const CommitEpilogueFast<LOGN, K, NCH8, POL> epi{fp, cdtl, msg_row, s_lo, s_hi, pd, pdi};
+            const CommitEpilogueFast<LOGN, K, NCH8, POL> epi{fp, cdtl, msg_row, s_lo, s_hi, pd, pdi, S};
             tile_inverse_to_global<LOGN, LOGN, POL, CommitEpilogueFast<LOGN, K, NCH8, POL>, true>(S, o + 1, fp.tbl, mp, (u32)K * n, epi);
         }
         return;
@@ -434,9 +477,12 @@ static bool build_cdt_param(const LweContext* c, CdtParam& out) {
 // Test hook: evaluates the three CDT searches on caller-supplied u values so that the
 // boundary cases (u = cdf[k] - 1, cdf[k], cdf[k] + 1, including the 2^-60-probability tail
 // the keystream never reaches in a test) can be compared with the reference's linear scan.
+// cycles (optional): clock64() ticks each warp spent in the search -- the device analogue of the reference's dudect
+// harness (cpp-core/tools/dudect_sampler.cpp:105-141): the caller compares the distributions of two input classes
 template <int NCH8>
 __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64* __restrict__ cdf_full, u32 cdf_n,
-                                 const u64* __restrict__ u, size_t count, u32* __restrict__ out, int variant) {
+                                 const u64* __restrict__ u, size_t count, u32* __restrict__ out, int variant,
+                                 unsigned long long* __restrict__ cycles) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // count is padded to a multiple of 32
     const bool compact = variant >= 3 && cdt.compact != 0;
     const u64 lane_entry = compact ? cdt.dval[threadIdx.x & 31u]
@@ -444,6 +490,8 @@ __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64
     const u32 lane_cum = cdt.dcum[threadIdx.x & 31u];
     const u64 x = i < count ? u[i] : 0;
     u32 r;
+    __syncwarp();
+    const long long t0 = clock64();
     if (variant == 0) r = cdt_magnitude_global(cdf_full, cdf_n, x);
     else if (variant == 1) r = cdt_magnitude<NCH8>(cdt, x);
     else if (compact && variant == 4) {
@@ -456,10 +504,13 @@ __global__ void cdt_probe_kernel(const __grid_constant__ CdtParam cdt, const u64
     }
     else if (compact) r = cdt_magnitude_compact(cdt.dval[15], lane_entry, lane_cum, x);
     else r = cdt_magnitude_shfl<NCH8>(cdt, lane_entry, x);
+    // the result feeds the time stamp's dependency chain so that the search cannot be scheduled past it
+    const long long t1 = clock64() + (long long)(__shfl_sync(0xffffffffu, r, 0) >> 31);
     if (i < count) out[i] = r;
+    if (cycles && (threadIdx.x & 31u) == 0u) cycles[i >> 5] = (unsigned long long)(t1 - t0);
 }
 
-bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant) {
+bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant, u64* cycles_per_warp) {
     LweContext fake;
     fake.cdf = host::build_cdt(sigma);
     if (fake.cdf.empty()) return false;
@@ -469,17 +520,21 @@ bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int
     if (!cuda_ok(cudaSetDevice(current_device_choice()), "cudaSetDevice")) return false;
     u64 *d_u = nullptr, *d_cdf = nullptr;
     u32* d_out = nullptr;
+    unsigned long long* d_cyc = nullptr;
+    const size_t warps = (count + 31) / 32;
+    if (cycles_per_warp && !cuda_ok(cudaMalloc(&d_cyc, warps * 8), "cudaMalloc")) return false;
     bool ok = cuda_ok(cudaMalloc(&d_u, count * 8), "cudaMalloc") && cuda_ok(cudaMalloc(&d_out, count * 4), "cudaMalloc") &&
               cuda_ok(cudaMalloc(&d_cdf, fake.cdf.size() * 8), "cudaMalloc") &&
               cuda_ok(cudaMemcpy(d_u, u, count * 8, cudaMemcpyHostToDevice), "H2D") &&
               cuda_ok(cudaMemcpy(d_cdf, fake.cdf.data(), fake.cdf.size() * 8, cudaMemcpyHostToDevice), "H2D");
     if (ok) {
         const unsigned blocks = (unsigned)((count + 127) / 128);
-        if (!inline_ok || (cdt.count + 7) / 8 <= 5) cdt_probe_kernel<5><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant);
-        else cdt_probe_kernel<8><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant);
+        if (!inline_ok || (cdt.count + 7) / 8 <= 5) cdt_probe_kernel<5><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant, d_cyc);
+        else cdt_probe_kernel<8><<<blocks, 128>>>(cdt, d_cdf, (u32)fake.cdf.size(), d_u, count, d_out, variant, d_cyc);
         ok = cuda_ok(cudaGetLastError(), "cdt_probe_kernel") && cuda_ok(cudaMemcpy(out, d_out, count * 4, cudaMemcpyDeviceToHost), "D2H");
+        if (ok && d_cyc) ok = cuda_ok(cudaMemcpy(cycles_per_warp, d_cyc, warps * 8, cudaMemcpyDeviceToHost), "D2H");
     }
-    cudaFree(d_u); cudaFree(d_out); cudaFree(d_cdf);
+    cudaFree(d_u); cudaFree(d_out); cudaFree(d_cdf); cudaFree(d_cyc);
     return ok;
 }
 

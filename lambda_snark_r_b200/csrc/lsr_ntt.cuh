@@ -393,6 +393,8 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
         } else {
 #pragma unroll
             for (int j = 0; j < (1 << R); j++) v[j] = PAD ? sm[padx(base) + (u32)j * pstep] : sm[swz(base + ((u32)j << LG))];
+            // whole-item epilogues may reuse the slots just read (they belong to this thread alone in this pass)
+            if constexpr (OUT == IO_GLOBAL && Epi::kWholeItem) epi.loaded(W, base);
         }
         if constexpr (!INVERSE) {
             fwd_network<R, POL, LL, HEAD>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
@@ -517,12 +519,15 @@ __device__ __forceinline__ void tile_inverse_to_global(u64* sm, u64* g, const Nt
 //          memory -> coalesced store.  Inverse: coalesced load -> shared memory
 //          -> first pass ... last pass (coalesced map) -> HBM.
 // ---------------------------------------------------------------------------
-template <int LT>
-constexpr int ntt_min_blocks() { return LT <= 12 ? LSR_NTT_MINB : (LT == 13 ? 2 : 1); }
+#ifndef LSR_NTT_MINB_GOLD      // Goldilocks tiles: resident CTAs per SM the register allocation is held to
+#define LSR_NTT_MINB_GOLD LSR_NTT_MINB
+#endif
+template <int LT, int POL = POL_F64>
+constexpr int ntt_min_blocks() { return LT <= 12 ? (POL == POL_GOLD ? LSR_NTT_MINB_GOLD : LSR_NTT_MINB) : (LT == 13 ? 2 : 1); }
 
 // FUSED (inverse only): the InvFusion hooks are compiled in; the plain instantiation is exactly the stand-alone transform.
 template <int LT, bool WHOLE, int POL, bool INVERSE, bool FUSED = false>
-__global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT>())
+__global__ void __launch_bounds__(kNttThreads, ntt_min_blocks<LT, POL>())
 ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t total_elems, u32 d, const InvFusion fz) {
     extern __shared__ __align__(16) u64 sm[];
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;

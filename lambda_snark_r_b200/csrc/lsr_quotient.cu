@@ -107,7 +107,7 @@ spmv3_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uin
 // middle field (a = top 5 bits, b = low 5 bits); warp a reads 32 consecutive rows, the values cross a padded
 // shared-memory tile, and warp b writes the 32 consecutive destinations brv(r) = (brv5(b), brv(mid), brv5(a)),
 // a = 0..31 -- 256-byte segments instead of 32 scattered 8-byte words.  grid = (m / 1024, witnesses)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 spmv3_tiled_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
                    const u64* __restrict__ val, const u64* __restrict__ z, uint32_t rows, uint32_t cols, int logm,
                    size_t witnesses, u64* __restrict__ E, unsigned* __restrict__ flags) {
@@ -117,32 +117,65 @@ spmv3_tiled_kernel(const ModParams mp, const uint32_t* __restrict__ row_ptr, con
     const int midbits = logm - 10;
     const u64* __restrict__ zw = z + w * cols;
     bool bad = false;
-    // 256 threads, four rows each: a = threadIdx.y + 8 i.  The row pointers of all twelve (row, matrix) pairs are
-    // requested before the first entry is touched.
-    uint32_t lo[4][3], hi[4][3];
+    // 256 threads, four rows each: a = threadIdx.y + 8 i.  The kernel is bound by load latency, not by bytes (ncu: 3 TB/s at
+    // 24 % of the warp slots, long-scoreboard stalls 6.6 per issue with the entry loop of every (row, matrix) pair as a
+    // chain of three dependent loads at 96 registers).  So the FIRST entry of all twelve pairs goes as waves of independent
+    // loads -- row pointers, then column indices and values, then the witness words -- and only the first products stay
+    // live (64 registers, four CTAs per SM); rows with further entries (gate-style circuits have one or two per row) finish
+    // in the loop below, which fetches its row pointers again (L1).
+    u64 acc[4][3];
+    bool more = false;
+    {
+        uint32_t c0[4][3];
+        u64 v0[4][3];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t r = ((threadIdx.y + 8u * i) << (logm - 5)) | (mid << 5) | b;
+        for (int i = 0; i < 4; i++) {
+            const uint32_t r = ((threadIdx.y + 8u * i) << (logm - 5)) | (mid << 5) | b;
 #pragma unroll
-        for (int mat = 0; mat < 3; mat++) {
-            const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
-            lo[i][mat] = __ldg(rp + r);
-            hi[i][mat] = __ldg(rp + r + 1);
+            for (int mat = 0; mat < 3; mat++) {
+                const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
+                const uint32_t lo = __ldg(rp + r), hi = __ldg(rp + r + 1);
+                const bool has = lo < hi;
+                more |= hi - lo > 1u;
+                c0[i][mat] = has ? __ldg(col + lo) : 0u;
+                v0[i][mat] = has ? __ldg(val + lo) : 0ull;          // weight 0: column 0 (it exists) contributes nothing
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int mat = 0; mat < 3; mat++) acc[i][mat] = __ldg(zw + c0[i][mat]);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int mat = 0; mat < 3; mat++) acc[i][mat] = field_mul(v0[i][mat], reduce64(acc[i][mat], mp), mp);
+    }
+    if (more) {
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+            const uint32_t r = ((threadIdx.y + 8u * i) << (logm - 5)) | (mid << 5) | b;
+#pragma unroll 1
+            for (int mat = 0; mat < 3; mat++) {
+                const uint32_t* rp = row_ptr + (size_t)mat * (rows + 1);
+                const uint32_t hi = __ldg(rp + r + 1);
+                u64 s = 0;
+                for (uint32_t k = __ldg(rp + r) + 1u; k < hi; k++)
+                    s = field_add(s, field_mul(__ldg(val + k), reduce64(__ldg(zw + __ldg(col + k)), mp), mp), mp);
+                // acc[i][mat] with run-time indices would send the array to local memory: select instead
+#pragma unroll
+                for (int ii = 0; ii < 4; ii++)
+#pragma unroll
+                    for (int mm = 0; mm < 3; mm++)
+                        if (ii == i && mm == mat) acc[ii][mm] = field_add(acc[ii][mm], s, mp);
+            }
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t a = threadIdx.y + 8u * i;
-        u64 abc[3];
 #pragma unroll
-        for (int mat = 0; mat < 3; mat++) {
-            u64 acc = 0;
-            for (uint32_t k = lo[i][mat]; k < hi[i][mat]; k++)
-                acc = field_add(acc, field_mul(__ldg(val + k), reduce64(__ldg(zw + __ldg(col + k)), mp), mp), mp);
-            tile[mat][a][b] = acc;
-            abc[mat] = acc;
-        }
-        bad |= field_mul(abc[0], abc[1], mp) != abc[2];
+        for (int mat = 0; mat < 3; mat++) tile[mat][a][b] = acc[i][mat];
+        bad |= field_mul(acc[i][0], acc[i][1], mp) != acc[i][2];
     }
     if (bad) atomicOr(flags + w, 1u);
     __syncthreads();

@@ -97,6 +97,38 @@ def test_quotient_matches_restated_rust(gpu, q, m):
     r.close()
 
 
+@pytest.mark.parametrize("q,m", [(P, 1024), (Q0, 2048)])
+def test_quotient_with_ragged_rows(gpu, q, m):
+    """Rows with 0 .. 4 entries per matrix (the mat-vec kernel's batched first entry + the loop for the rest), empty
+    rows, wrapped 'negative' values: quotient word for word against the restated Rust."""
+    rng = random.Random(7 * m + 1)
+    v = 40                                                     # free variables z[1 .. v]; z[v + 1 + i] closes constraint i
+    z = [1] + [rng.randrange(q) for _ in range(v)] + [0] * m
+    A, B, C = [], [], []
+
+    def row(mat, i, lo):
+        acc = 0
+        for _ in range(rng.choice([lo, 1, 1, 2, 3, 4])):
+            col, val = rng.randrange(v + 1), rng.choice([1, 2, q - 1, rng.randrange(q), (1 << 64) - 1])
+            mat.append((i, col, val))
+            acc = (acc + (val % q) * z[col]) % q
+        return acc
+
+    for i in range(m):
+        a, b = row(A, i, 0), row(B, i, 0)
+        extra = row(C, i, 0) if i % 3 == 0 else 0              # C row = closing variable (+ a few more entries)
+        z[v + 1 + i] = (a * b - extra) % q
+        C.append((i, v + 1 + i, 1))
+    r = api.R1CS(m, v + 1 + m, A, B, C, q)
+    want = QO.compute_quotient_poly(m, A, B, C, z, q)
+    got = r.quotient(np.array(z, dtype=np.uint64))
+    assert [int(x) for x in got] == want
+    bad = list(z); bad[v + 1 + m // 2] = (bad[v + 1 + m // 2] + 1) % q
+    _, status = r.quotient_batch(np.array([z, bad], dtype=np.uint64))
+    assert status.tolist() == [0, 1]
+    r.close()
+
+
 def test_quotient_test_vectors(gpu):
     """TV-1 (7 * 13 = 91) and a plaquette-style instance with wrapped negative coefficients."""
     q = P

@@ -6,6 +6,9 @@ import numpy as np
 import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+from lambda_snark_r_b200 import capi
+if "--lib" in sys.argv:          # kernel-variant experiments: a library built by `_build --variant` in place of the shipped one
+    capi._lib = capi.load(Path(sys.argv.pop(sys.argv.index("--lib") + 1))); sys.argv.remove("--lib")
 from lambda_snark_r_b200 import api
 
 P = 2**64 - 2**32 + 1
