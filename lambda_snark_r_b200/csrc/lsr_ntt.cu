@@ -135,6 +135,15 @@ static bool launch_column2(const NttContext* c, u64* d, size_t batch, cudaStream
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
+    if constexpr (INV && FIRST) {
+        if (fin_c) {
+            if (pol == POL_F64)       ntt_column2_kernel<S1, S2, POL_F64, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
+            else if (pol == POL_LAZY) ntt_column2_kernel<S1, S2, POL_LAZY, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            else if (pol == POL_GOLD) ntt_column2_kernel<S1, S2, POL_GOLD, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            else                      ntt_column2_kernel<S1, S2, POL_GUARD, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            return cuda_ok(cudaGetLastError(), "ntt_column2_kernel launch");
+        }
+    }
     if (pol == POL_F64)       ntt_column2_kernel<S1, S2, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
     else if (pol == POL_LAZY) ntt_column2_kernel<S1, S2, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
     else if (pol == POL_GOLD) ntt_column2_kernel<S1, S2, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);

@@ -553,21 +553,29 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
     } else {
         if constexpr (!ONE_PASS && !LSR_NTT_DIRECT_IN) {
             u64 x[PER_THREAD];
-#pragma unroll
-            for (u32 k = 0; k < PER_THREAD; k++) {
-                const u32 i = threadIdx.x + k * kNttThreads;
-                x[k] = i < valid ? __ldcs(g + i) : 0ull;
-            }
-            if (FUSED && fz.mul) {                         // fused pointwise product (uniform branch): input = data * mul
-                const u64* __restrict__ g2 = fz.mul + tile0;
+            if constexpr (FUSED) {
+                // fused pointwise product: input = data * mul.  Both operands of all the thread's coefficients are requested
+                // before the first product (with the second operand behind the first one's use the tile kernel of the
+                // fused transform ran at 19 us per 2^20 transform against 14 for the plain one)
+                const bool has_mul = fz.mul != nullptr;
+                const u64* __restrict__ g2 = has_mul ? fz.mul + tile0 : g;
                 u64 y[PER_THREAD];
 #pragma unroll
                 for (u32 k = 0; k < PER_THREAD; k++) {
                     const u32 i = threadIdx.x + k * kNttThreads;
-                    y[k] = i < valid ? __ldcs(g2 + i) : 0ull;
+                    x[k] = i < valid ? __ldcs(g + i) : 0ull;
+                    y[k] = (has_mul && i < valid) ? __ldcs(g2 + i) : 0ull;
                 }
+                if (has_mul) {
 #pragma unroll
-                for (u32 k = 0; k < PER_THREAD; k++) x[k] = mulmod_exact(x[k], y[k], mp);
+                    for (u32 k = 0; k < PER_THREAD; k++) x[k] = mulmod_exact(x[k], y[k], mp);
+                }
+            } else {
+#pragma unroll
+                for (u32 k = 0; k < PER_THREAD; k++) {
+                    const u32 i = threadIdx.x + k * kNttThreads;
+                    x[k] = i < valid ? __ldcs(g + i) : 0ull;
+                }
             }
 #pragma unroll
             for (u32 k = 0; k < PER_THREAD; k++) {
@@ -633,14 +641,20 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
         }
         fwd_network<S, POL>(v, tbl.fwd, T0, mp);
     } else {
+        // fused finishing step (InvFusion): (c - x) * scale; the c words are requested together with the coefficients
+        const bool fin = FIRST && fin_c != nullptr;
+        const u64* __restrict__ cf = fin ? fin_c + (pb << (LG + (u32)S)) + c : g;
+        u64 cv[FIRST ? (1 << S) : 1];
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) v[j] = g[(size_t)j << LG];
+        for (int j = 0; j < (1 << S); j++) {
+            v[j] = g[(size_t)j << LG];
+            if (FIRST) cv[j] = fin ? __ldcs(cf + ((size_t)j << LG)) : 0ull;
+        }
         inv_network<S, POL, FIRST>(v, tbl.inv, T0, (int)LG, tbl.n_inv, mp);
-    }
-    if (INVERSE && FIRST && fin_c) {                     // fused finishing step: (c - x) * scale (InvFusion)
-        const u64* __restrict__ cf = fin_c + (pb << (LG + (u32)S)) + c;
+        if (FIRST && fin) {
 #pragma unroll
-        for (int j = 0; j < (1 << S); j++) v[j] = field_mul(field_sub(cf[(size_t)j << LG], v[j], mp), fin_scale, mp);
+            for (int j = 0; j < (1 << S); j++) v[j] = field_mul(field_sub(cv[FIRST ? j : 0], v[j], mp), fin_scale, mp);
+        }
     }
 #pragma unroll
     for (int j = 0; j < (1 << S); j++) g[(size_t)j << LG] = v[j];
@@ -654,8 +668,9 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
 // (b << S2) + j of sub-block b (twiddle group blk * 2^S1 + b), i.e. exactly the two chained register passes,
 // with the exchange between them on chip.  Inverse: phase B first, then phase A.
 // ---------------------------------------------------------------------------
-template <int S1, int S2, int POL, bool INVERSE, bool FIRST>
-__global__ void __launch_bounds__(kNttThreads)
+// FIN (the kernel that ends an inverse transform only): the InvFusion finishing step is compiled in
+template <int S1, int S2, int POL, bool INVERSE, bool FIRST, bool FIN = false>
+__global__ void __launch_bounds__(kNttThreads, FIN ? 2 : (INVERSE ? 4 : 3))
 ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0,
                    const u64* __restrict__ fin_c, u64 fin_scale) {
     constexpr u32 LR = S1 + S2, ROWS = 1u << LR, ELEMS = 4096u, COLS = ELEMS / ROWS, LC = 12 - LR;
@@ -675,6 +690,15 @@ ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ da
         for (u32 it = threadIdx.x; it < (ELEMS >> S1); it += kNttThreads) {
             const u32 cc = it & (COLS - 1u), r0 = it >> LC;          // r0 < 2^S2
             u64 v[1 << S1];
+            // fused finishing step (c - x) * scale: the c words are requested before the butterflies, used after them
+            u64 cv[FIN ? (1 << S1) : 1];
+            if constexpr (FIN) {
+                if (to_global) {
+                    const u64* __restrict__ cf = fin_c + (pb << (LG + LR)) + c0;
+#pragma unroll
+                    for (int j = 0; j < (1 << S1); j++) cv[j] = __ldcs(cf + ((size_t)(r0 + ((u32)j << S2)) << LG) + cc);
+                }
+            }
             if (from_global) {
 #pragma unroll
                 for (int j = 0; j < (1 << S1); j++) v[j] = g[((size_t)(r0 + ((u32)j << S2)) << LG) + cc];
@@ -697,11 +721,9 @@ ntt_column2_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ da
             if (!INVERSE) fwd_network<S1, POL>(v, tbl.fwd, T0, mp);
             else inv_network<S1, POL, FIRST>(v, tbl.inv, T0, (int)(LG + S2), tbl.n_inv, mp);
             if (to_global) {
-                if (INVERSE && FIRST && fin_c) {             // fused finishing step: (c - x) * scale (InvFusion)
-                    const u64* __restrict__ cf = fin_c + (pb << (LG + LR)) + c0;
+                if constexpr (FIN) {
 #pragma unroll
-                    for (int j = 0; j < (1 << S1); j++)
-                        v[j] = field_mul(field_sub(cf[((size_t)(r0 + ((u32)j << S2)) << LG) + cc], v[j], mp), fin_scale, mp);
+                    for (int j = 0; j < (1 << S1); j++) v[j] = field_mul(field_sub(cv[FIN ? j : 0], v[j], mp), fin_scale, mp);
                 }
 #pragma unroll
                 for (int j = 0; j < (1 << S1); j++) g[((size_t)(r0 + ((u32)j << S2)) << LG) + cc] = v[j];

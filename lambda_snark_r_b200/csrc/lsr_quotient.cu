@@ -337,10 +337,25 @@ static bool quotient_compute(R1csHandle* h, QuotientState* st, const u64* dz, si
             ok = st->coef.reserve(em * 8) &&
                  cuda_ok(cudaMemcpyAsync(st->coef.ptr, dE, em * 8, cudaMemcpyDeviceToDevice, s), "D2D coefficients");
         ok = ok && ntt_forward_launch(st->coset, dE, 2 * W, s);            // A_z, B_z only (C_z stays as coefficients)
-        if (ok && ntt_inverse_fused_supported(st->coset)) {
+#ifdef LSR_PROFILING    // tools/ build only: LSR_QUOT_FUSE bit 0 = product fused, bit 1 = finishing step fused (default 3)
+        static const int fuse = [] { const char* e = std::getenv("LSR_QUOT_FUSE"); return e ? std::atoi(e) : 3; }();
+#else
+        constexpr int fuse = 3;
+#endif
+        if (ok && fuse && ntt_inverse_fused_supported(st->coset)) {
             // one inverse transform with both neighbours fused in: its first kernel reads a * b (the coset product is
             // never written) and writes to Q, its last kernel stores (C - N) / 2 -- two 24 B/coefficient sweeps less
-            ok = ntt_inverse_fused_launch(st->coset, dE, W, s, InvFusion{dE + W * (size_t)m, dQ, dE + 2 * W * (size_t)m, inv2});
+            if (!(fuse & 1)) {
+                coset_product_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m);
+                ok = cuda_ok(cudaGetLastError(), "coset_product_kernel");
+            }
+            const InvFusion fz{(fuse & 1) ? dE + W * (size_t)m : nullptr, (fuse & 1) ? dQ : nullptr,
+                               (fuse & 2) ? dE + 2 * W * (size_t)m : nullptr, inv2};
+            ok = ok && ntt_inverse_fused_launch(st->coset, (fuse & 1) ? dE : dQ, W, s, fz);
+            if (ok && !(fuse & 2)) {
+                quotient_finish_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE + 2 * W * (size_t)m, dQ, W * (size_t)m, inv2);
+                ok = cuda_ok(cudaGetLastError(), "quotient_finish_kernel");
+            }
         } else if (ok) {
             coset_product_kernel<<<grid(W * m), 256, 0, s>>>(mp, dE, dQ, W * (size_t)m);
             ok = cuda_ok(cudaGetLastError(), "coset_product_kernel");

@@ -97,10 +97,12 @@ def test_quotient_matches_restated_rust(gpu, q, m):
     r.close()
 
 
-@pytest.mark.parametrize("q,m", [(P, 1024), (Q0, 2048)])
+@pytest.mark.parametrize("q,m", [(P, 1024), (Q0, 2048), (Q50, 1024), (Q60, 1024), (Q0, 32), (P, 64)])
 def test_quotient_with_ragged_rows(gpu, q, m):
     """Rows with 0 .. 4 entries per matrix (the mat-vec kernel's batched first entry + the loop for the rest), empty
-    rows, wrapped 'negative' values: quotient word for word against the restated Rust."""
+    rows, wrapped 'negative' values: quotient word for word against the restated Rust.  The moduli cover every arithmetic
+    policy of the fused inverse transform (Goldilocks, FP64 butterflies, lazy and guarded u64), the sizes its one-kernel
+    and multi-kernel shapes."""
     rng = random.Random(7 * m + 1)
     v = 40                                                     # free variables z[1 .. v]; z[v + 1 + i] closes constraint i
     z = [1] + [rng.randrange(q) for _ in range(v)] + [0] * m
@@ -120,11 +122,12 @@ def test_quotient_with_ragged_rows(gpu, q, m):
         z[v + 1 + i] = (a * b - extra) % q
         C.append((i, v + 1 + i, 1))
     r = api.R1CS(m, v + 1 + m, A, B, C, q)
-    want = QO.compute_quotient_poly(m, A, B, C, z, q)
-    got = r.quotient(np.array(z, dtype=np.uint64))
+    omega = api.reference_root_of_unity(q, m)                  # the interpolation domain's generator, same on both sides
+    want = QO.compute_quotient_poly(m, A, B, C, z, q, omega)
+    got = r.quotient(np.array(z, dtype=np.uint64), omega)
     assert [int(x) for x in got] == want
     bad = list(z); bad[v + 1 + m // 2] = (bad[v + 1 + m // 2] + 1) % q
-    _, status = r.quotient_batch(np.array([z, bad], dtype=np.uint64))
+    _, status = r.quotient_batch(np.array([z, bad], dtype=np.uint64), omega)
     assert status.tolist() == [0, 1]
     r.close()
 
