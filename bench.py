@@ -399,6 +399,55 @@ def run_gpu(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     e2e_value = world * EB / (e2e_ms * 1e-3)
+    # N > 1, same job with dynamic sharding: the ranks pull chunks of the N * EB * steps commitments from one shared counter
+    # instead of each taking a fixed share.  On a host whose GPUs do not get equal DMA bandwidth (the 8-GPU node: four GPUs
+    # at half the share of the other four, profiles/r02_multi_gpu_probe_8gpu.txt) the fixed split waits for the slowest
+    # rank; a dispatcher that feeds GPUs as they free up does not.  `e2e.value` stays the fixed (weak-scaling) split.
+    e2e_dyn = None
+    if world > 1:
+        import fcntl
+        DCH = 1024
+        total_chunks = world * (EB // DCH) * e2e_steps
+        path = f"/tmp/lsr_bench_counter_{os.environ.get('MASTER_PORT', '0')}"
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.write((0).to_bytes(8, "little"))
+        barrier()
+        fd = os.open(path, os.O_RDWR)
+
+        def pull():
+            fcntl.flock(fd, fcntl.LOCK_EX)
+            os.lseek(fd, 0, os.SEEK_SET)
+            c = int.from_bytes(os.read(fd, 8), "little")
+            if c < total_chunks:
+                os.lseek(fd, 0, os.SEEK_SET)
+                os.write(fd, (c + 1).to_bytes(8, "little"))
+            fcntl.flock(fd, fcntl.LOCK_UN)
+            return c
+
+        barrier()
+        t0 = time.perf_counter()
+        mine = 0
+        while True:
+            c = pull()
+            if c >= total_chunks:
+                break
+            slot = (c % (EB // DCH)) * DCH                       # this rank's buffers, slot by slot
+            ctx.commit_batch_ptr(h_msgs.data_ptr() + slot * N_RING * 8, N_RING, h_seeds.data_ptr() + slot * 8, DCH,
+                                 h_out.data_ptr() + slot * words * 8)
+            mine += 1
+        torch.cuda.synchronize()
+        dyn_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        os.close(fd)
+        counts = torch.tensor([mine], device=dev, dtype=torch.int64)
+        allc = torch.empty(world, device=dev, dtype=torch.int64)
+        dist.all_gather_into_tensor(allc, counts)
+        e2e_dyn = {"what": "the same commitments pulled in chunks of 1024 from one shared counter (dynamic sharding over the ranks)",
+                   "value": total_chunks * DCH / (dyn_ms * 1e-3), "unit": "commitments/s", "ms_total": dyn_ms,
+                   "chunks_per_rank": allc.cpu().tolist()}
+        barrier()
+        if rank == 0:
+            os.unlink(path)
     # the same bytes as raw page-locked copies (H2D of the messages and D2H of the containers at the same time, all ranks
     # at once): what the host's DMA path sustains for this mix, the ceiling of any end-to-end path with this container format
     d_raw_in = torch.empty((EB, N_RING), dtype=torch.int64, device=dev)
@@ -737,6 +786,7 @@ def run_gpu(args):
                                 "ms_per_step": raw_ms, "commitments_per_s_equivalent": world * EB / (raw_ms * 1e-3),
                                 "GBps_total": world * EB * (N_RING + words) * 8 / (raw_ms * 1e-3) / 1e9},
            "frac_of_raw_copy_ceiling": raw_ms / e2e_ms,
+           "dynamic_sharding": e2e_dyn,
            "ntt_forward": {"value": world * EB / (ntt_e2e_ms * 1e-3), "unit": "NTT/s",
                            "api": "ntt_forward_batch (C ABI, pinned host buffers, in place)"}}
     if prover:
