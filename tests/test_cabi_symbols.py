@@ -153,3 +153,15 @@ def test_no_profiling_switch_ships_in_the_library():
     blob = capi.LIB_PATH.read_bytes() + (capi.LIB_PATH.parent / "liblambda_snark_core.a").read_bytes()
     for name in (b"LSR_FUSED_SKIP", b"LSR_COMMIT_CHUNK", b"LSR_PROVER_PIPELINE", b"LSR_NTT_COLUMN2", b"LSR_FS_KERNEL"):
         assert name not in blob, name
+
+
+def test_cxx_host_mirror_compiles_and_links_without_a_gpu(tmp_path):
+    """The C++ mirror of the Rust safe wrappers (include/lambda_snark_b200.hpp) and its test program build against the
+    library here; tests/test_gpu_cabi_c.py runs the program on the GPU."""
+    exe = tmp_path / "test_host_mirror"
+    lib_dir = capi.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", str(ROOT / "include"),
+           str(ROOT / "tests" / "cabi" / "test_host_mirror.cpp"), "-L", str(lib_dir), "-llambda_snark_core",
+           f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

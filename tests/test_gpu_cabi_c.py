@@ -45,3 +45,17 @@ def test_static_archive_links_with_the_cargo_link_line_and_passes(gpu, tmp_path)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all reference assertions hold" in r.stdout
+
+
+def test_cxx_host_mirror_of_the_rust_wrappers(gpu, tmp_path):
+    """include/lambda_snark_b200.hpp mirrors context.rs / commitment.rs / opening.rs / challenge.rs in C++ (no Rust
+    toolchain here); tests/cabi/test_host_mirror.cpp ports the Rust unit tests that sit on the FFI."""
+    exe = tmp_path / "test_host_mirror"
+    lib_dir = capi.LIB_PATH.parent
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", str(ROOT / "include"), str(ROOT / "tests" / "cabi" / "test_host_mirror.cpp"),
+           "-L", str(lib_dir), "-llambda_snark_core", f"-Wl,-rpath,{lib_dir}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all ported Rust assertions hold" in r.stdout
