@@ -151,7 +151,8 @@ def test_no_profiling_switch_ships_in_the_library():
     """The phase-skip / kernel-selection switches of tools/ exist only in the -DLSR_PROFILING build: the shipped
     library reads no LSR_* environment variable."""
     blob = capi.LIB_PATH.read_bytes() + (capi.LIB_PATH.parent / "liblambda_snark_core.a").read_bytes()
-    for name in (b"LSR_FUSED_SKIP", b"LSR_COMMIT_CHUNK", b"LSR_PROVER_PIPELINE", b"LSR_NTT_COLUMN2", b"LSR_FS_KERNEL"):
+    for name in (b"LSR_FUSED_SKIP", b"LSR_COMMIT_CHUNK", b"LSR_PROVER_PIPELINE", b"LSR_NTT_COLUMN2", b"LSR_FS_KERNEL",
+                 b"LSR_QUOT_FUSE"):
         assert name not in blob, name
 
 
