@@ -1,4 +1,4 @@
-// ntt_variant_bench.cu -- times ntt_tile_kernel<12,12> (forward + inverse) in isolation for kernel-variant
+// ntt_variant_bench.cu -- times ntt_tile_kernel<12, WHOLE> (forward + inverse) in isolation for kernel-variant
 // experiments (compile with -DLSR_NTT_MINB=2|3|4 ...).  Links the product's host table builder.
 // build: nvcc -O3 -std=c++17 -lineinfo -I lambda_snark_r_b200/csrc -I include -gencode arch=compute_100a,code=sm_100a \
 //        tools/ntt_variant_bench.cu lambda_snark_r_b200/csrc/lsr_host.cpp -o tools/_bin/ntt_vb
@@ -33,7 +33,8 @@ int main(int argc, char** argv) {
     std::vector<u64> h(batch * n);
     for (size_t i = 0; i < h.size(); i++) h[i] = (i * 2654435761ull + 12345) % q;
     u64* d; cudaMalloc(&d, 8 * h.size()); cudaMemcpy(d, h.data(), 8 * h.size(), cudaMemcpyHostToDevice);
-    auto kf = ntt_tile_kernel<12, 12, VB_POL, false>; auto ki = ntt_tile_kernel<12, 12, VB_POL, true>;
+    auto kf = ntt_tile_kernel<12, true, VB_POL, false>; auto ki = ntt_tile_kernel<12, true, VB_POL, true>;
+    constexpr size_t SMEM_F = 32768 + (ntt_pad<false>() ? 2048 : 0);      // padded layout of the forward kernel
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kf);
     int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kf, kNttThreads, 32768);
     printf("threads=%d POL=%d MINB=%d regs=%d occupancy=%d CTAs/SM\n", kNttThreads, VB_POL, LSR_NTT_MINB, fa.numRegs, occ);
@@ -42,7 +43,7 @@ int main(int argc, char** argv) {
         float best = 1e9;
         for (int rep = 0; rep < 8; rep++) {
             cudaEventRecord(e0);
-            if (dir == 0) kf<<<(unsigned)batch, kNttThreads, 32768>>>(mp, t, d, batch * n); else ki<<<(unsigned)batch, kNttThreads, 32768>>>(mp, t, d, batch * n);
+            if (dir == 0) kf<<<(unsigned)batch, kNttThreads, SMEM_F>>>(mp, t, d, batch * n, 0u, InvFusion{}); else ki<<<(unsigned)batch, kNttThreads, 32768>>>(mp, t, d, batch * n, 0u, InvFusion{});
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep > 1 && ms < best) best = ms;
         }
