@@ -252,31 +252,40 @@ struct CommitEpilogueFast {
         constexpr u32 LG = LOGN - 4;
         const ModParams& mp = fp.mp;
         if constexpr (kRawF64) {
-            if constexpr (kParkMsg) {
-                if (base >= ((u32)(K - 1) << LOGN)) asm volatile("cp.async.wait_all;" ::: "memory");    // this thread's own copies
-            }
             const double bias = kTwo52 + 128.0;                         // x = r + e + bias
             const double off_neg = mp.qd - 128.0, off_pos = -128.0;     // -> (r + e [+ q]) + 2^52
-#pragma unroll
-            for (u32 j = 0; j < 16; j++) {
-                const u32 idx = base + (j << LG);
+            auto canonical = [&](u32 j) -> u64 {                        // (r + e) mod q of coefficient j of the work item
                 const u32 byte = ((pre.pk[j >> 2] >> (8u * (j & 3u))) & 0xffu) ^ 0x80u;        // e + 128
                 const double x = __dadd_rn(as_d(v[j]), as_d(kTwo52Bits | (u64)byte));
                 const double off = x < bias ? off_neg : off_pos;
-                u64 c = as_u(__dadd_rn(x, off)) & 0x000fffffffffffffull;                       // (r + e) mod q, canonical
-                if constexpr (kParkMsg) {
-                    // message row: its words were parked in row 0's slots of this thread (loaded())
-                    const u32 xm = idx - ((u32)(K - 1) << LOGN);                               // wraps for earlier rows
-                    if (idx >= ((u32)(K - 1) << LOGN) && xm < fp.msg_used) {
-                        u64 word = sm[padx(base - ((u32)(K - 1) << LOGN)) + j * kStep];
+                return as_u(__dadd_rn(x, off)) & 0x000fffffffffffffull;
+            };
+            // the row is uniform over the work item (and over the warp): rows without a message take a loop with no
+            // message code in it
+            const bool msg_row = K == 1 || base >= ((u32)(K - 1) << LOGN);
+            if (!msg_row) {
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) __stcs(g + base + (j << LG), canonical(j));
+            } else if constexpr (kParkMsg) {
+                asm volatile("cp.async.wait_all;" ::: "memory");       // this thread's own copies (loaded())
+                const u32 x0 = base - ((u32)(K - 1) << LOGN);
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) {
+                    u64 c = canonical(j);
+                    if (x0 + (j << LG) < fp.msg_used) {
+                        u64 word = sm[padx(x0) + j * kStep];           // parked in row 0's slots of this thread
                         if (pd) word = div_small(word, pd, pdi);                               // uniform over the CTA
                         const u64 m = fp.p < (1ull << 21) ? (u64)mod_small(word, (u32)fp.p, fp.pinv) : word % fp.p;
                         c = csub(c + fp.delta * m, mp.q);                                      // delta * m <= q - 1
                     }
-                } else {
-                    c = commit_finish_msg<LOGN, K>(idx, c, msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi);
+                    __stcs(g + base + (j << LG), c);
                 }
-                __stcs(g + idx, c);
+            } else {
+#pragma unroll
+                for (u32 j = 0; j < 16; j++) {
+                    const u32 idx = base + (j << LG);
+                    __stcs(g + idx, commit_finish_msg<LOGN, K>(idx, canonical(j), msg, mp.q, fp.delta, fp.p, fp.pinv, fp.msg_used, pd, pdi));
+                }
             }
         } else {
 #pragma unroll
