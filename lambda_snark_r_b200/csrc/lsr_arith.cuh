@@ -230,8 +230,28 @@ constexpr u64 kTwo52Bits = 0x4330000000000000ull;   // bit pattern of 2^52
 //        |h - c*q| < 2^53, so the fma is exact; r + l = x*w - c*q is an integer below q in
 //        magnitude, exact again.
 // Result: balanced representative, |result| <= q (1/2 + |x| 2^-53) <= 0.75 q.   6 FP64 instructions.
+// c = an integer within 3/4 of x * wq.  Two formulations: the magic-number pair DFMA + DADD (two FP64-pipe instructions, c =
+// nearest integer to the exact x * wq), or -- XR -- DMUL + FRND.F64 (one FP64-pipe instruction + one conversion-pipe
+// instruction; the product is rounded to 53 bits first: for |x| < 2^51 that adds at most 2^-3 to the 1/2, and with the
+// rounding of wq itself, |x| 2^-54 <= 2^-3, c stays within 3/4 of x * w / q -- the bound everything below assumes).
+// Results are exact either way; the two can pick different representatives only on a tie, and outputs are canonical.
+// Measured (tools/variant_bench.py): FRND issues in one cycle where DADD holds the port for two, +3.4 % on the stand-alone
+// forward transform (61.8 -> 63.9 M NTT/s at n = 4096), but its latency sits in the c -> r chain: +0.6 % on the inverse,
+// -1.4 % on the fused commitment.  So XR is a template flag and only the stand-alone forward kernels set it.
+template <bool XR = false>
+__device__ __forceinline__ double rint_prod(double x, double wq) {
+    if constexpr (XR) {
+        double c;
+        asm("cvt.rni.f64.f64 %0, %1;" : "=d"(c) : "d"(__dmul_rn(x, wq)));
+        return c;
+    } else {
+        return __dadd_rn(__fma_rn(x, wq, kRintMagic), -kRintMagic);
+    }
+}
+
+template <bool XR = false>
 __device__ __forceinline__ double mulmod_f(double x, double w, double wq, double q) {
-    const double c = __dadd_rn(__fma_rn(x, wq, kRintMagic), -kRintMagic);
+    const double c = rint_prod<XR>(x, wq);
     const double h = __dmul_rn(x, w);
     const double l = __fma_rn(x, w, -h);
     const double r = __fma_rn(-c, q, h);
@@ -239,8 +259,9 @@ __device__ __forceinline__ double mulmod_f(double x, double w, double wq, double
 }
 
 // |x| < 2^51  ->  balanced representative, |result| <= q (1/2 + |x| 2^-53).   3 FP64 instructions.
+template <bool XR = false>
 __device__ __forceinline__ double reduce_f(double x, double invq, double q) {
-    const double c = __dadd_rn(__fma_rn(x, invq, kRintMagic), -kRintMagic);
+    const double c = rint_prod<XR>(x, invq);
     return __fma_rn(-c, q, x);
 }
 

@@ -344,7 +344,7 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
                 const int sv = unpack_s8(pk, j);
                 v[j] = POL == POL_F64 ? as_u((double)sv) : (sv < 0 ? mp.q - (u64)(-sv) : (u64)sv);
             }
-            if (!LSR_SKIP(fp, 2u)) fwd_network<4, POL, false, true>(v, fp.tbl.fwd, 1u, mp, 0u, fp.tbl.head_fwd);
+            if (!LSR_SKIP(fp, 2u)) fwd_network<4, POL, false, true, (LSR_SMEM_FWD_XR != 0)>(v, fp.tbl.fwd, 1u, mp, 0u, fp.tbl.head_fwd);
             const u32 pb = padx((P << LOGN) + tau);
 #pragma unroll
             for (u32 j = 0; j < 16; j++) S[pb + j * 272u] = v[j];              // padded stride of 256 coefficients

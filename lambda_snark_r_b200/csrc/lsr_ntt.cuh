@@ -29,6 +29,9 @@
 #ifndef LSR_NTT_DIRECT_IN
 #define LSR_NTT_DIRECT_IN 0
 #endif
+#ifndef LSR_SMEM_FWD_XR   // experiment: FRND rounding in the shared-memory-only forward passes too (fused commitment)
+#define LSR_SMEM_FWD_XR 0
+#endif
 #ifndef LSR_NTT_MINB      // tools/ntt_variant_bench.cu overrides this to explore occupancy
 #define LSR_NTT_MINB 3
 #endif
@@ -89,7 +92,7 @@ __device__ __forceinline__ u32 tw_index(u32 T0, int r, int t, u32 stride) {
 // the entries (1 << r) + t are the same for every thread of the grid: they are
 // read from `head`, a by-value kernel parameter (constant bank), and reach the
 // IMADs as uniform operands -- no load, no register, one RF read less each.
-template <int R, int r, int POL, bool LL, bool HEAD>
+template <int R, int r, int POL, bool LL, bool HEAD, bool XR = false>
 __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                           const ulonglong2* __restrict__ head,
                                           u32 T0, u32 stride, const ModParams& mp) {
@@ -104,7 +107,7 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                 const int jj = j + half;
                 if (POL == POL_F64) {
                     // balanced doubles: |T| <= 0.75 q, growth +0.75 q per stage, no offset needed
-                    const double T = mulmod_f(as_d(v[jj]), as_d(w.x), as_d(w.y), mp.qd);
+                    const double T = mulmod_f<XR>(as_d(v[jj]), as_d(w.x), as_d(w.y), mp.qd);
                     const double X = as_d(v[j]);
                     v[j] = as_u(__dadd_rn(X, T));
                     v[jj] = as_u(__dadd_rn(X, -T));
@@ -127,15 +130,16 @@ __device__ __forceinline__ void fwd_stage(u64 (&v)[1 << R], const ulonglong2* __
                 }
             }
         }
-        fwd_stage<R, r + 1, POL, LL, HEAD>(v, tw, head, T0, stride, mp);
+        fwd_stage<R, r + 1, POL, LL, HEAD, XR>(v, tw, head, T0, stride, mp);
     }
 }
 
-template <int R, int POL, bool LL = false, bool HEAD = false>
+// XR: POL_F64 products round their quotient estimate with FRND.F64 (lsr_arith.cuh rint_prod); the stand-alone forward kernels
+template <int R, int POL, bool LL = false, bool HEAD = false, bool XR = false>
 __device__ __forceinline__ void fwd_network(u64 (&v)[1 << R], const ulonglong2* __restrict__ tw,
                                             u32 T0, const ModParams& mp, u32 stride = 0,
                                             const ulonglong2* __restrict__ head = nullptr) {
-    fwd_stage<R, 0, POL, LL, HEAD>(v, tw, head, T0, stride, mp);
+    fwd_stage<R, 0, POL, LL, HEAD, XR>(v, tw, head, T0, stride, mp);
 }
 
 // last inverse stage (m = 1): scalar n^-1 folded in (SEAL transform_from_rev
@@ -230,9 +234,9 @@ __device__ __forceinline__ void inv_network(u64 (&v)[1 << R], const ulonglong2* 
     }
 }
 
-template <int POL>
+template <int POL, bool XR = false>
 __device__ __forceinline__ u64 fwd_final(u64 v, const ModParams& mp) {
-    if (POL == POL_F64) return f_to_canonical(reduce_f(as_d(v), mp.invq, mp.qd), mp);
+    if (POL == POL_F64) return f_to_canonical(reduce_f<XR>(as_d(v), mp.invq, mp.qd), mp);
     if (POL == POL_GOLD) return gold_canonical(v);
     if (POL == POL_LAZY) return reduce_small(v, mp);
     return csub(csub(v, mp.q2), mp.q);
@@ -330,7 +334,8 @@ struct FinEpilogue {
 // WHOLE: the tile holds whole polynomials (LT == log n).  Otherwise it is one 2^LT block of a larger
 // polynomial and d = log n - LT (a run-time value: one kernel serves every big ring degree) only enters
 // the twiddle indices.  SL = first stage of the pass, counted inside the block.
-template <int LT, bool WHOLE, int SL, int R, int POL, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue, bool PAD = false>
+template <int LT, bool WHOLE, int SL, int R, int POL, bool INVERSE, bool FINAL, int IN, int OUT, typename Epi = NoEpilogue, bool PAD = false,
+          bool XR = false>
 __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io, const NttTables& tb_,
                                           const ModParams& mp, u32 items, u32 tb, u32 d_, const Epi& epi = Epi()) {
     constexpr int LG = LT - SL - R;           // log2 of the element stride g
@@ -397,10 +402,10 @@ __device__ __forceinline__ void tile_pass(u64* __restrict__ sm, const TileIo& io
             if constexpr (OUT == IO_GLOBAL && Epi::kWholeItem) epi.loaded(W, base);
         }
         if constexpr (!INVERSE) {
-            fwd_network<R, POL, LL, HEAD>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
+            fwd_network<R, POL, LL, HEAD, XR>(v, tw, T0, mp, ll_stride, tb_.head_fwd);
             if (FINAL) {
 #pragma unroll
-                for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<POL>(v[j], mp);
+                for (int j = 0; j < (1 << R); j++) v[j] = fwd_final<POL, XR>(v[j], mp);
             }
         } else {
             constexpr int sigma0 = LT - SL - R;           // inverse stages already done
@@ -455,7 +460,7 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && (P::N == 1 || (ntt_direct_out<POL>() && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD>(sm, io, t, mp, tile_elems >> R, tb, d);
+        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD, (GIO || LSR_SMEM_FWD_XR)>(sm, io, t, mp, tile_elems >> R, tb, d);
         if constexpr (OUT == IO_SMEM) __syncthreads();
         tile_forward_from<LT, WHOLE, POL, GIO, I + 1, FIN, PAD>(sm, io, t, mp, tile_elems, tb, d);
     }
