@@ -107,6 +107,15 @@ static bool launch_column(const NttContext* c, u64* d, size_t batch, cudaStream_
     if (blocks == 0) return true;
     if (blocks > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
     const int pol = policy_of(c, INV);
+    if constexpr (INV && FIRST) {
+        if (fin_c) {
+            if (pol == POL_F64)       ntt_column_kernel<S, POL_F64, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
+            else if (pol == POL_LAZY) ntt_column_kernel<S, POL_LAZY, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            else if (pol == POL_GOLD) ntt_column_kernel<S, POL_GOLD, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            else                      ntt_column_kernel<S, POL_GUARD, true, true, true><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
+            return cuda_ok(cudaGetLastError(), "ntt_column_kernel launch");
+        }
+    }
     if (pol == POL_F64)       ntt_column_kernel<S, POL_F64, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables_f, d, batch, logn, s0, fin_c, fin_scale);
     else if (pol == POL_LAZY) ntt_column_kernel<S, POL_LAZY, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);
     else if (pol == POL_GOLD) ntt_column_kernel<S, POL_GOLD, INV, FIRST><<<(unsigned)blocks, kNttThreads, 0, s>>>(c->mp, c->tables, d, batch, logn, s0, fin_c, fin_scale);

@@ -460,7 +460,7 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && (P::N == 1 || (ntt_direct_out<POL>() && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD, (GIO || LSR_SMEM_FWD_XR)>(sm, io, t, mp, tile_elems >> R, tb, d);
+        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD, ((GIO && WHOLE && LT <= 12) || LSR_SMEM_FWD_XR)>(sm, io, t, mp, tile_elems >> R, tb, d);      // LT = 13: 32 values per thread, FRND's extra live range spills; block tiles of the big ring degrees: -1 %
         if constexpr (OUT == IO_SMEM) __syncthreads();
         tile_forward_from<LT, WHOLE, POL, GIO, I + 1, FIN, PAD>(sm, io, t, mp, tile_elems, tb, d);
     }
@@ -612,7 +612,9 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 // pipeline (up to 2^24) chain two or three.  FIRST: the pass reads raw caller data (forward s0 == 0)
 // or ends the inverse transform (n^-1 folded in, canonical output).
 // ---------------------------------------------------------------------------
-template <int S, int POL, bool INVERSE, bool FIRST>
+// FIN (the kernel that ends an inverse transform only): the InvFusion finishing step is compiled in; the plain instantiation
+// carries no register for it
+template <int S, int POL, bool INVERSE, bool FIRST, bool FIN = false>
 __global__ void __launch_bounds__(kNttThreads)
 ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data, size_t batch, u32 logn, u32 s0,
                   const u64* __restrict__ fin_c, u64 fin_scale) {
@@ -647,18 +649,17 @@ ntt_column_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ dat
         fwd_network<S, POL>(v, tbl.fwd, T0, mp);
     } else {
         // fused finishing step (InvFusion): (c - x) * scale; the c words are requested together with the coefficients
-        const bool fin = FIRST && fin_c != nullptr;
-        const u64* __restrict__ cf = fin ? fin_c + (pb << (LG + (u32)S)) + c : g;
-        u64 cv[FIRST ? (1 << S) : 1];
+        const u64* __restrict__ cf = FIN ? fin_c + (pb << (LG + (u32)S)) + c : g;
+        u64 cv[FIN ? (1 << S) : 1];
 #pragma unroll
         for (int j = 0; j < (1 << S); j++) {
             v[j] = g[(size_t)j << LG];
-            if (FIRST) cv[j] = fin ? __ldcs(cf + ((size_t)j << LG)) : 0ull;
+            if (FIN) cv[j] = __ldcs(cf + ((size_t)j << LG));
         }
         inv_network<S, POL, FIRST>(v, tbl.inv, T0, (int)LG, tbl.n_inv, mp);
-        if (FIRST && fin) {
+        if constexpr (FIN) {
 #pragma unroll
-            for (int j = 0; j < (1 << S); j++) v[j] = field_mul(field_sub(cv[FIRST ? j : 0], v[j], mp), fin_scale, mp);
+            for (int j = 0; j < (1 << S); j++) v[j] = field_mul(field_sub(cv[FIN ? j : 0], v[j], mp), fin_scale, mp);
         }
     }
 #pragma unroll
