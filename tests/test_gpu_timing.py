@@ -47,7 +47,7 @@ def t_statistics(sigma, variant, seed):
 
 @pytest.mark.parametrize("variant", [2, 3, 4])
 def test_cdt_search_time_does_not_depend_on_the_samples(gpu, variant):
-    runs = [t_statistics(3.2, variant, 1000 + i) for i in range(3)]
+    runs = [t_statistics(3.2, variant, 1000 + i) for i in range(5)]      # median of five: one noisy launch cannot fail the suite
     t_ref = float(np.median([abs(r[0]) for r in runs]))
     t_fix = float(np.median([abs(r[1]) for r in runs]))
     print(f"variant {variant}: |t| by first-sample parity {t_ref:.2f}, fixed vs random {t_fix:.2f}")
