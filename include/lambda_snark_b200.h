@@ -256,7 +256,7 @@ const char* lsr_last_error(void) LSR_NOEXCEPT;         /* thread-local diagnosti
 /* Page-locked host buffers for the batched host-pointer entry points.  They accept any host memory: from ordinary
  * (pageable) memory -- a Rust Vec<u64>, a numpy array -- lwe_commit_batch stages chunks through its own page-locked
  * buffers with a few copy threads (0.38 M commitments/s; the driver's own pageable staging gives 0.10 M/s); from
- * these buffers there is no staging at all: 0.79 M/s, PCIe-bound (tools/latency.py, bench.py e2e).  NULL on failure. */
+ * these buffers there is no staging at all: 0.78 M/s, PCIe-bound (tools/latency.py, bench.py e2e).  NULL on failure. */
 void* lsr_host_alloc(size_t bytes) LSR_NOEXCEPT;
 void  lsr_host_free(void* p) LSR_NOEXCEPT;
 

@@ -9,6 +9,7 @@
 // lsr_commit_fused.cu holds the single-kernel fused path used for the
 // headline configuration.
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstdio>
@@ -333,7 +334,30 @@ static bool generic_commit_launch(const LweContext* c, const u64* d_msgs, size_t
     const size_t per = (size_t)k * n * sizeof(u64);
     const size_t chunk = std::max<size_t>(1, std::min<size_t>(count, ((size_t)1 << 30) / per));
     void* Sv = nullptr;
-    if (!cuda_ok(cudaMallocAsync(&Sv, chunk * per, s), "cudaMallocAsync(S)")) return false;
+    // The library's own stream-ordered pool (one per device), with a release threshold: in the device's default pool
+    // (threshold 0) every synchronisation hands the scratch back to the driver and the next call pays a fresh allocation
+    // (577 us per single commitment on this path against 115 with a cached block); the default pool is the host
+    // application's and is left alone.
+    static std::once_flag once[16];
+    static cudaMemPool_t pools[16] = {};
+    int dev = 0;
+    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice") || dev < 0 || dev >= 16) return false;
+    std::call_once(once[dev], [dev] {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            unsigned long long keep = 1ull << 31;                          // up to 2 GiB stay cached (a scratch is <= 1 GiB)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pools[dev] = pool;
+        }
+        cudaGetLastError();
+    });
+    if (pools[dev]) {
+        if (!cuda_ok(cudaMallocFromPoolAsync(&Sv, chunk * per, pools[dev], s), "cudaMallocFromPoolAsync(S)")) return false;
+    } else if (!cuda_ok(cudaMallocAsync(&Sv, chunk * per, s), "cudaMallocAsync(S)")) return false;
     u64* S = static_cast<u64*>(Sv);
     const ChaChaKey key = make_key(c);
     bool ok = true;
@@ -513,6 +537,22 @@ bool lwe_commit_host(const LweContext* c, const u64* msgs, size_t msg_len, const
     const size_t eff_len = std::max<size_t>(msg_len, 1);
     const size_t chunk = std::min<size_t>(count, kCommitHostChunk);
     const bool fused = fused_commit_supported(c) && c->commit_path != 1;
+    // A few commitments per call (the reference's lwe_commit is one): no device buffers and no copy commands.  Messages
+    // and seeds go into a page-locked buffer, the fused kernel reads them and writes the containers through the device
+    // mapping of page-locked memory, one synchronisation, one copy back.
+    if (fused && count <= 4) {
+        const size_t in_words = count * (eff_len + 1);
+        if (!c->staging[0].reserve(in_words * sizeof(u64)) || !c->staging[1].reserve(count * words * sizeof(u64))) return false;
+        u64* pin_in = static_cast<u64*>(c->staging[0].ptr);
+        u64* pin_out = static_cast<u64*>(c->staging[1].ptr);
+        if (msg_len) std::memcpy(pin_in, msgs, count * msg_len * sizeof(u64));
+        std::memcpy(pin_in + count * eff_len, seeds, count * sizeof(u64));
+        cudaStream_t s = c->ntt->stream;
+        const bool ok = lwe_commit_launch(c, pin_in, msg_len, pin_in + count * eff_len, count, pin_out, s) &&
+                        cuda_ok(cudaStreamSynchronize(s), "sync");
+        if (ok) std::memcpy(out, pin_out, count * words * sizeof(u64));
+        return ok;
+    }
     const int nbuf = (fused && count > chunk) ? 3 : 1;
     cudaStream_t streams[3] = {c->ntt->copy_streams[0], c->ntt->copy_streams[1], c->ntt->stream};
     for (int b = 0; b < nbuf; b++) {

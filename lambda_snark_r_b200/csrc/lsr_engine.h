@@ -61,6 +61,7 @@ struct NttContext {
     cudaEvent_t events[4] = {nullptr, nullptr, nullptr, nullptr};
     mutable std::mutex mu;            // serialises use of the scratch buffers
     mutable lsr::DeviceScratch scratch[3];
+    mutable lsr::PinnedScratch pin;   // small single calls: the kernel works on this page-locked buffer in place (zero copy)
 };
 
 // The opaque handle of types.h:27 (reference layout: cpp-core/src/commitment.cpp:31-40).

@@ -430,6 +430,7 @@ void ntt_destroy(NttContext* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     for (auto& s : c->scratch) s.release();
+    c->pin.release();
     if (c->d_fwd) cudaFree(c->d_fwd);
     if (c->d_inv) cudaFree(c->d_inv);
     if (c->d_fwd_last) cudaFree(c->d_fwd_last);
@@ -453,6 +454,19 @@ bool ntt_transform_host(const NttContext* c, u64* host, size_t batch, bool inver
     if (!cuda_ok(cudaSetDevice(c->device), "cudaSetDevice")) return false;
     const size_t n = c->degree;
     const size_t poly_bytes = n * sizeof(u64);
+    // Small single calls (the reference's one-polynomial ntt_forward / ntt_inverse): no device buffer and no copy
+    // commands at all.  The polynomial is copied into a page-locked buffer, the one kernel of the transform (n <= 8192)
+    // works on that buffer in place through its device mapping -- 32 KiB each way over PCIe inside the kernel -- and the
+    // result is copied back: one launch + one synchronisation instead of two staged pageable copies around them.
+    if (batch * poly_bytes <= ((size_t)256 << 10) && c->logn <= 13 && !natural) {
+        if (!c->pin.reserve((size_t)256 << 10)) return false;
+        u64* buf = static_cast<u64*>(c->pin.ptr);
+        std::memcpy(buf, host, batch * poly_bytes);
+        const bool ok = (inverse ? ntt_inverse_launch(c, buf, batch, c->stream) : ntt_forward_launch(c, buf, batch, c->stream)) &&
+                        cuda_ok(cudaStreamSynchronize(c->stream), "sync");
+        if (ok) std::memcpy(host, buf, batch * poly_bytes);
+        return ok;
+    }
     size_t chunk = std::max<size_t>(1, ((size_t)32 << 20) / poly_bytes);
     chunk = std::min(chunk, batch);
     const int nbuf = batch > chunk ? 2 : 1;
