@@ -608,11 +608,24 @@ bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs
     std::vector<int> h_inv(chunk);
     std::vector<u64> packed;
     bool ok = true;
+    // A few openings per call (the reference's lwe_verify_opening is one): containers and messages are copied into a
+    // page-locked buffer and the kernels read them through its device mapping -- no copy commands on the way in.
+    const bool small = count <= 4;
+    if (small) {
+        if (!c->staging[2].reserve(count * (words + std::max<size_t>(cmp_len, 1)) * sizeof(u64))) return false;
+        u64* pin = static_cast<u64*>(c->staging[2].ptr);
+        std::memcpy(pin, comm_words, count * words * sizeof(u64));
+        for (size_t i = 0; i < count && cmp_len; i++)
+            std::memcpy(pin + count * words + i * cmp_len, msgs + i * msg_len, cmp_len * sizeof(u64));
+        d_comm = pin;
+        d_msg = pin + count * words;
+    }
     for (size_t done = 0; ok && done < count; done += chunk) {
         const size_t cnt = std::min(chunk, count - done);
-        ok = cuda_ok(cudaMemcpyAsync(d_comm, comm_words + done * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D comm") &&
-             cuda_ok(cudaMemsetAsync(d_diff, 0, chunk * (sizeof(int) + sizeof(unsigned long long)), s), "memset");
-        if (ok && cmp_len) {
+        if (!small)
+            ok = cuda_ok(cudaMemcpyAsync(d_comm, comm_words + done * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D comm");
+        ok = ok && cuda_ok(cudaMemsetAsync(d_diff, 0, chunk * (sizeof(int) + sizeof(unsigned long long)), s), "memset");
+        if (ok && cmp_len && !small) {
             // compare only the first cmp_len words of each message (stride msg_len on the host)
             const u64* src = msgs + done * msg_len;
             if (cmp_len != msg_len) {
