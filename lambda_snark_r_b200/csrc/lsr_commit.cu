@@ -25,6 +25,9 @@ namespace lsr {
 bool fused_commit_launch(const LweContext* ctx, const u64* d_msgs, size_t msg_len, const u64* d_seeds,
                          size_t count, u64* d_out, cudaStream_t stream, uint32_t planes, size_t unit0);   // lsr_commit_fused.cu
 bool fused_prepare(LweContext* ctx, cudaStream_t stream);                  // lsr_commit_fused.cu
+bool fused_verify_supported(const LweContext* ctx);                         // lsr_commit_fused.cu
+bool fused_verify_launch(const LweContext* ctx, const u64* d_comm, size_t stride, const u64* d_msgs, size_t cmp_len,
+                         size_t count, unsigned long long* d_diff, int* d_invalid, cudaStream_t s);
 
 // commitments per pipeline slot of the host-pointer path: 444 = three fused CTAs on each of the 148 SMs, one full
 // wave per launch (28 MiB of containers at n = 4096, k = 2)
@@ -610,20 +613,39 @@ bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs
     bool ok = true;
     // A few openings per call (the reference's lwe_verify_opening is one): containers and messages are copied into a
     // page-locked buffer and the kernels read them through its device mapping -- no copy commands on the way in.
+    // The five-kernel path reads them through the buffer's device mapping (no copy commands on the way in); the one-kernel
+    // path walks the container word by word from a single CTA, which over PCIe costs a round trip per step, so it gets
+    // them by two asynchronous copies out of the page-locked buffer instead.
     const bool small = count <= 4;
+    const bool fused_v = fused_verify_supported(c);
     if (small) {
         if (!c->staging[2].reserve(count * (words + std::max<size_t>(cmp_len, 1)) * sizeof(u64))) return false;
         u64* pin = static_cast<u64*>(c->staging[2].ptr);
         std::memcpy(pin, comm_words, count * words * sizeof(u64));
         for (size_t i = 0; i < count && cmp_len; i++)
             std::memcpy(pin + count * words + i * cmp_len, msgs + i * msg_len, cmp_len * sizeof(u64));
-        d_comm = pin;
-        d_msg = pin + count * words;
+        if (fused_v) {
+            ok = cuda_ok(cudaMemcpyAsync(d_comm, pin, count * words * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D comm") &&
+                 (!cmp_len || cuda_ok(cudaMemcpyAsync(d_msg, pin + count * words, count * cmp_len * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D msgs"));
+        } else {
+            d_comm = pin;
+            d_msg = pin + count * words;
+        }
     }
     for (size_t done = 0; ok && done < count; done += chunk) {
         const size_t cnt = std::min(chunk, count - done);
         if (!small)
             ok = cuda_ok(cudaMemcpyAsync(d_comm, comm_words + done * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D comm");
+        // small calls: the two flag words per commitment live in page-locked memory and the kernels OR into them through
+        // the device mapping -- no memset command, no copies back
+        unsigned long long* pin_flags = nullptr;
+        if (small) {
+            if (!c->staging[3].reserve(chunk * (sizeof(int) + sizeof(unsigned long long)))) return false;
+            pin_flags = static_cast<unsigned long long*>(c->staging[3].ptr);
+            std::memset(pin_flags, 0, chunk * (sizeof(int) + sizeof(unsigned long long)));
+            d_diff = pin_flags;
+            d_inv = reinterpret_cast<int*>(pin_flags + chunk);
+        } else
         ok = ok && cuda_ok(cudaMemsetAsync(d_diff, 0, chunk * (sizeof(int) + sizeof(unsigned long long)), s), "memset");
         if (ok && cmp_len && !small) {
             // compare only the first cmp_len words of each message (stride msg_len on the host)
@@ -636,6 +658,9 @@ bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs
             ok = cuda_ok(cudaMemcpyAsync(d_msg, src, cnt * cmp_len * sizeof(u64), cudaMemcpyHostToDevice, s), "H2D msgs");
         }
         if (!ok) break;
+        if (fused_v) {
+            ok = fused_verify_launch(c, d_comm, words, d_msg, cmp_len, cnt, d_diff, d_inv, s);
+        } else {
         verify_prepare_kernel<<<grid_for(cnt * k * n, 256), 256, 0, s>>>(c->q, n, k, d_comm, words, cnt, d_T, d_inv);
         ok = cuda_ok(cudaGetLastError(), "verify_prepare_kernel");
         if (ok && k > 1) ok = ntt_forward_launch(c->ntt, d_T, cnt * (k - 1), s);
@@ -649,6 +674,14 @@ bool lwe_verify_host(const LweContext* c, const u64* comm_words, const u64* msgs
                                                                             d_msg, cmp_len, cnt, d_diff);
             ok = cuda_ok(cudaGetLastError(), "verify_decode_kernel");
         }
+        }
+        if (small) {
+            ok = ok && cuda_ok(cudaStreamSynchronize(s), "sync");
+            if (ok) {
+                std::memcpy(h_diff.data(), d_diff, cnt * sizeof(unsigned long long));
+                std::memcpy(h_inv.data(), d_inv, cnt * sizeof(int));
+            }
+        } else
         ok = ok && cuda_ok(cudaMemcpyAsync(h_diff.data(), d_diff, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "D2H") &&
              cuda_ok(cudaMemcpyAsync(h_inv.data(), d_inv, cnt * sizeof(int), cudaMemcpyDeviceToHost, s), "D2H") &&
              cuda_ok(cudaStreamSynchronize(s), "sync");

@@ -456,6 +456,151 @@ fused_commit_kernel(const __grid_constant__ FusedParams fp, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------
+// K6 fused: lwe_verify_opening for a batch, one CTA per commitment (n = 4096, 2 <= k <= 4).  Replaces decrypt + decode +
+// compare of the reference (cpp-core/src/commitment.cpp:200-232) by the trapdoor opening of DESIGN.md 3.4:
+//   rows t_0 .. t_{k-2} of the container -> shared memory (range check) -> forward transforms (one multi-polynomial tile)
+//   -> u^ = sum_i z'^_i * t^_i in place -> inverse transform, whose last pass (thread tau owns coefficients tau + 256 j)
+//   adds t_{k-1}, decodes round(u / Delta) mod p and ORs the difference with the caller's words mod p into a register
+//   -> one warp reduction and one atomicOr per warp.  Nothing but the container, the message and two flag words touches HBM
+//   (the generic path is five kernels with the k - 1 transforms making two round trips each).
+// ---------------------------------------------------------------------------
+struct VerifyParams {
+    ModParams mp;
+    NttTables tbl;
+    const u64* zh;            // [K-1][n] canonical residues, NTT domain
+    const u64* comm;          // [count][stride] containers
+    const u64* msgs;          // [count][cmp_len] (already cut to the compared length)
+    unsigned long long* diff; // [count], zeroed
+    int* invalid;             // [count], zeroed
+    size_t stride;
+    u64 delta, dinv;          // dinv = floor((2^64 - 1) / delta)
+    u64 p, pinv;
+    u32 cmp_len;
+};
+
+template <int LOGN, int K>
+struct VerifyEpilogue {
+    static constexpr bool kWholeItem = true;
+    static constexpr bool kRawF64 = false;
+    struct Pre {};
+    const VerifyParams& vp;
+    const u64* last;          // row K-1 of this commitment's container
+    const u64* msg;           // this commitment's message words
+    unsigned long long* acc;  // per-thread OR of the differences
+    int* bad;                 // per-thread: a container word out of range
+    __device__ __forceinline__ Pre pre(u32) const { return Pre{}; }
+    __device__ __forceinline__ void loaded(u32, u32) const {}
+    __device__ __forceinline__ void item(u64*, u32, u32 base, const u64 (&v)[16], const Pre&) const {
+        constexpr u32 LG = LOGN - 4;
+        const u64 q = vp.mp.q;
+        u64 t[16];
+#pragma unroll
+        for (u32 j = 0; j < 16; j++) t[j] = __ldcs(last + base + (j << LG));
+#pragma unroll
+        for (u32 j = 0; j < 16; j++) {
+            const u32 x = base + (j << LG);
+            u64 w = t[j];
+            if (w >= q) { *bad = 1; w = 0; }                                   // flagged invalid; keep the arithmetic in range
+            const u64 u = addmod(v[j], w, q);
+            u64 d = div_small(u + vp.delta / 2, vp.delta, vp.dinv);            // round(u / Delta) <= p
+            d = d >= vp.p ? d - vp.p : d;
+            if (x < vp.cmp_len) {
+                const u64 word = __ldcs(msg + x);
+                const u64 m = vp.p < (1ull << 21) ? (u64)mod_small(word, (u32)vp.p, vp.pinv) : word % vp.p;
+                *acc |= d ^ m;                                                  // no branch on the outcome
+            }
+        }
+    }
+};
+
+template <int LOGN, int K, int POL>
+__global__ void __launch_bounds__(kNttThreads, 3)
+fused_verify_kernel(const __grid_constant__ VerifyParams vp) {
+    constexpr u32 n = 1u << LOGN;
+    static_assert(K >= 2, "k = 1 has no trapdoor transform: the generic path decodes row 0 directly");
+    extern __shared__ __align__(16) u64 sm[];                                  // [K-1][n], swizzled
+    const ModParams& mp = vp.mp;
+    const size_t b = blockIdx.x;
+    const u64* c = vp.comm + b * vp.stride;
+    int bad = (threadIdx.x == 0 && c[0] != (u64)K * n * 8) ? 1 : 0;
+    for (u32 r = threadIdx.x; r < (u32)(K - 1) * n; r += kNttThreads) {
+        u64 v = __ldcs(c + 1 + r);
+        if (v >= mp.q) { bad = 1; v = 0; }
+        sm[swz(r)] = to_working<POL>(v);
+    }
+    __syncthreads();
+    tile_forward<LOGN, LOGN, POL>(sm, vp.tbl, mp, (u32)(K - 1) * n, 0u);
+    for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
+        if (POL == POL_F64) {
+            double acc = 0.0;
+#pragma unroll
+            for (u32 i = 0; i < (u32)(K - 1); i++) {
+                const double z = u64_to_f(__ldg(vp.zh + ((size_t)i << LOGN) + x));
+                // z / q formed on the fly: two roundings instead of one, |x| 2^-52 <= 2^-4 for the unreduced evaluations (< 2^48)
+                acc = __dadd_rn(acc, mulmod_f(as_d(sm[swz((i << LOGN) + x)]), z, __dmul_rn(z, mp.invq), mp.qd));
+            }
+            sm[swz(x)] = as_u(acc);                                             // |acc| <= 0.75 (K-1) q
+        } else {
+            u64 acc = 0;
+#pragma unroll
+            for (u32 i = 0; i < (u32)(K - 1); i++)
+                acc = addmod(acc, mulmod_exact(__ldg(vp.zh + ((size_t)i << LOGN) + x), sm[swz((i << LOGN) + x)], mp), mp.q);
+            sm[swz(x)] = acc;
+        }
+    }
+    __syncthreads();
+    unsigned long long acc = 0ull;
+    const VerifyEpilogue<LOGN, K> epi{vp, c + 1 + (size_t)(K - 1) * n, vp.msgs + b * (size_t)vp.cmp_len, &acc, &bad};
+    tile_inverse_to_global<LOGN, LOGN, POL, VerifyEpilogue<LOGN, K>>(sm, nullptr, vp.tbl, mp, n, epi);
+    // warp OR, one atomic per warp (every warp issues it: no branch on the outcome)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc |= __shfl_xor_sync(0xffffffffu, acc, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicOr(vp.diff + b, acc);
+        atomicOr(vp.invalid + b, bad);
+    }
+}
+
+bool fused_verify_supported(const LweContext* c) {
+    const bool arith_ok = (c->ntt->mp.lazy_fwd && c->ntt->mp.lazy_inv) || (c->ntt->mp.f64_ok && c->ntt->arith != 1);
+    return c->logn == 12 && c->k >= 2 && c->k <= 4 && arith_ok && c->commit_path != 1;
+}
+
+template <int K, int POL>
+static bool launch_fused_verify_pol(const VerifyParams& vp, size_t count, cudaStream_t s) {
+    constexpr size_t smem = ((size_t)(K - 1) << 12) * sizeof(u64);
+    auto kernel = fused_verify_kernel<12, K, POL>;
+    if (smem > 48 * 1024 &&
+        !cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute"))
+        return false;
+    kernel<<<(unsigned)count, kNttThreads, smem, s>>>(vp);
+    return cuda_ok(cudaGetLastError(), "fused_verify_kernel launch");
+}
+
+// d_comm [count][stride], d_msgs [count][cmp_len], d_diff / d_invalid zeroed by the caller; asynchronous on s
+bool fused_verify_launch(const LweContext* c, const u64* d_comm, size_t stride, const u64* d_msgs, size_t cmp_len,
+                         size_t count, unsigned long long* d_diff, int* d_invalid, cudaStream_t s) {
+    if (count == 0) return true;
+    if (count > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }
+    const bool f64 = c->ntt->mp.f64_ok && c->ntt->arith != 1;
+    VerifyParams vp;
+    vp.mp = c->ntt->mp;
+    vp.tbl = f64 ? c->ntt->tables_f : c->ntt->tables;
+    vp.zh = c->d_zh; vp.comm = d_comm; vp.msgs = d_msgs; vp.diff = d_diff; vp.invalid = d_invalid;
+    vp.stride = stride; vp.delta = c->delta; vp.dinv = ~0ull / c->delta; vp.p = c->p; vp.pinv = ~0ull / c->p;
+    vp.cmp_len = (u32)cmp_len;
+    switch (c->k) {
+        case 2: return f64 ? launch_fused_verify_pol<2, POL_F64>(vp, count, s) : launch_fused_verify_pol<2, POL_LAZY>(vp, count, s);
+        case 3: return f64 ? launch_fused_verify_pol<3, POL_F64>(vp, count, s) : launch_fused_verify_pol<3, POL_LAZY>(vp, count, s);
+        case 4: return f64 ? launch_fused_verify_pol<4, POL_F64>(vp, count, s) : launch_fused_verify_pol<4, POL_LAZY>(vp, count, s);
+        default: set_error("fused verify: unsupported module rank"); return false;
+    }
+}
+
 // ------------------------------------------------------------------- host side
 static bool build_cdt_param(const LweContext* c, CdtParam& out) {
     size_t used = c->cdf.size();

@@ -9,7 +9,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from conftest import Q0, Q1, Q60, uniform
+from conftest import Q0, Q1, Q50, Q60, uniform
 from lambda_snark_r_b200 import api, capi, sharding
 from oracle import oracle as O
 
@@ -336,6 +336,39 @@ def test_verify_and_lincomb_match_oracle(gpu, rng):
     nulls = (capi.LweCommitmentP * 2)(None, None)
     assert not lib.lwe_linear_combine(ctx.as_ptr(), nulls, cf.ctypes.data_as(capi.u64p), 2)
     assert not lib.lwe_linear_combine(ctx.as_ptr(), ptrs, cf.ctypes.data_as(capi.u64p), 0)
+    ctx.close()
+
+
+@pytest.mark.parametrize("k,q,msg_len,count", [(2, Q0, 4096, 37), (2, Q0, 0, 3), (2, Q0, 1, 5), (3, Q0, 777, 9), (4, Q0, 4096, 6),
+                                               (2, Q50, 300, 7), (2, Q60, 300, 4)])
+def test_fused_verification_equals_the_generic_path_and_the_oracle(gpu, rng, k, q, msg_len, count):
+    """K6: the one-kernel verification (n = 4096, k = 2 .. 4, both arithmetic policies) against the five-kernel generic path
+    and the oracle, on honest openings, flipped message words, tampered and out-of-range container words, wrong headers."""
+    ctx = mk(4096, k, q)
+    orc = O.OracleLwe(q, 4096, k, 3.19, SEED32)
+    msgs = rng.integers(0, 2**64, size=(count, max(msg_len, 1)), dtype=np.uint64)[:, :msg_len]
+    msgs = np.ascontiguousarray(msgs).reshape(count, msg_len)
+    cms = ctx.commit_batch(msgs, sharding.global_seeds(11, 0, count))
+    cases = [(cms, msgs)]
+    if msg_len:
+        bad = msgs.copy(); bad[::2, msg_len // 2] += np.uint64(1)                # a different word mod p
+        same = msgs.copy(); same[1::2, 0] += np.uint64(ctx.p)                     # the same word mod p
+        cases += [(cms, bad), (cms, same)]
+    tam = cms.copy()
+    tam[0, 1 + 5] = (tam[0, 1 + 5] + np.uint64(ctx.delta)) % np.uint64(ctx.q)     # first row: shifts every slot by z' * Delta
+    tam[1 % count, 1 + (k - 1) * 4096] = (tam[1 % count, 1 + (k - 1) * 4096] + np.uint64(ctx.delta)) % np.uint64(ctx.q)   # last row, slot 0
+    tam[2 % count, 0] += np.uint64(8)                                              # wrong header
+    tam[(3 % count), 1 + 4096 * (k - 1) + 9] = np.uint64(ctx.q)                    # out-of-range word in the last row
+    tam[(4 % count), 1 + 3] = np.uint64(2**64 - 1)                                 # out-of-range word in the first row
+    cases.append((tam, msgs))
+    for containers, words in cases:
+        want = [orc.verify(containers[i], words[i]) for i in range(count)]
+        ctx.set_commit_path(0)
+        fused = ctx.verify_batch(containers, words).tolist()
+        ctx.set_commit_path(1)
+        generic = ctx.verify_batch(containers, words).tolist()
+        ctx.set_commit_path(0)
+        assert fused == generic == want
     ctx.close()
 
 
