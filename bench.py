@@ -334,6 +334,18 @@ def run_gpu(args):
             raise SystemExit(f"bench.py: PARITY FAILURE: {pick.size - same} of {pick.size} containers of the timed step "
                              f"differ from the oracle")
 
+    # ---- K6 on the containers of the timed step: lwe_verify_opening for the whole batch, device-resident (one fused kernel);
+    # every opening must verify (outside the timed region: another whole-batch check of the step's output)
+    v_diff = torch.empty(B, device=dev, dtype=torch.int64)
+    v_inv = torch.empty(B, device=dev, dtype=torch.int32)
+
+    def verify_step():
+        ctx.verify_batch_device(out.data_ptr(), msgs.data_ptr(), N_RING, B, v_diff.data_ptr(), v_inv.data_ptr(), stream)
+
+    ms_verify = timed(verify_step, args.warmup, args.steps) / args.steps
+    if int(v_diff.count_nonzero().item()) or int(v_inv.count_nonzero().item()):
+        raise SystemExit("bench.py: PARITY FAILURE: a commitment of the timed step does not open to its message")
+
     # ---- NTT sweep point at the same n (BASELINE configs[2])
     NB = args.ntt_batch
     data = torch.randint(0, Q_MOD, (NB, N_RING), device=dev, dtype=torch.int64, generator=g)
@@ -752,6 +764,13 @@ def run_gpu(args):
                             "hbm_frac": inv_block["roofline"]["frac"]},
             "pointwise": {"value": NB * N_RING / (ms_mul * 1e-3), "unit": "coefficients/s", "bound": "hbm",
                           "frac": mul_gbs / hbm_peak},
+            # K6: k - 1 forward + 1 inverse transform + (k - 1) n products per opening; 8 k n + 8 n bytes in
+            "verify_opening": {"value": B / (ms_verify * 1e-3), "unit": "openings/s", "bound": "fp64" if arith == "fp64" else "imad",
+                               "frac": (B / (ms_verify * 1e-3)) * ((K_RANK - 1) * FP64_NTT_FWD + FP64_NTT_INV
+                                                                   + (K_RANK - 1) * N_RING * (FP64_PER_MODMUL + 1)) / 1e9 / fp64_peak
+                               if (arith == "fp64" and fp64_peak) else None,
+                               "hbm_frac": B * (8 * K_RANK * N_RING + 8 * N_RING) / (ms_verify * 1e-3) / 1e9 / hbm_peak,
+                               "all_openings_of_the_timed_step_verify": True},
         },
     }
     if sweep:

@@ -481,6 +481,15 @@ int lwe_verify_opening_batch(const LweContext* ctx, const uint64_t* comm_words,
                              const uint64_t* messages, size_t msg_len, size_t count,
                              int* results) LSR_NOEXCEPT;
 
+/* same for DEVICE memory, asynchronous on `stream`: d_diff[i] receives the OR of (decoded slot XOR message word mod p) over
+ * the first msg_len slots and d_invalid[i] a non-zero value for a malformed container, i.e. the opening verifies iff both are
+ * zero (1 / 0 / -1 of lwe_verify_opening = !invalid && !diff / !invalid && diff / invalid).  Both arrays are zeroed by the
+ * call.  msg_len <= ring_degree.  Served by the one-kernel verification (ring_degree 4096, module_rank 2..4); -1 for any
+ * other shape (use the host-pointer entry point).                                                                      */
+int lsr_lwe_verify_opening_batch_device(const LweContext* ctx, const uint64_t* d_comm_words, const uint64_t* d_messages,
+                                        size_t msg_len, size_t count, uint64_t* d_diff, int* d_invalid,
+                                        void* stream) LSR_NOEXCEPT;
+
 /* Deterministic sampler: samples a pure function of (seed32, sigma, index);
  * the oracle implements the same stream (lsro_sample_gaussian_seeded).      */
 int lsr_sample_gaussian_seeded(uint64_t* output, size_t len, double sigma,

@@ -456,6 +456,12 @@ class LweContext:
                                               C.c_void_p(out_ptr), C.c_void_p(stream)) != 0:
             raise LambdaSnarkError(f"lsr_lwe_commit_batch_device failed: {last_error()}")
 
+    def verify_batch_device(self, comm_ptr: int, msgs_ptr: int, msg_len: int, count: int, diff_ptr: int, invalid_ptr: int,
+                            stream: int = 0) -> None:
+        """lsr_lwe_verify_opening_batch_device: opening i verifies iff diff[i] == 0 and invalid[i] == 0 (asynchronous)."""
+        if _lib().lsr_lwe_verify_opening_batch_device(self._h, comm_ptr, msgs_ptr, msg_len, count, diff_ptr, invalid_ptr, stream) != 0:
+            raise LambdaSnarkError(f"lsr_lwe_verify_opening_batch_device failed: {last_error()}")
+
     def verify_batch(self, containers, messages) -> np.ndarray:
         cw = _u64(containers)
         m = _u64(messages)

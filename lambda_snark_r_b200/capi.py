@@ -139,6 +139,8 @@ SIGNATURES = {
     "lwe_commit_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "lsr_lwe_commit_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                                C.c_void_p, C.c_void_p]),
+    "lsr_lwe_verify_opening_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p]),
     "lwe_verify_opening_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t,
                                             C.POINTER(C.c_int)]),
     "lsr_sample_gaussian_seeded": (C.c_int, [u64p, C.c_size_t, C.c_double, C.c_char_p]),

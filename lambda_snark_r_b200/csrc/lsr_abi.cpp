@@ -631,6 +631,23 @@ int lsr_cdt_magnitude_device(double sigma, const uint64_t* u, size_t count, uint
     LSR_CATCH(-1)
 }
 
+int lsr_lwe_verify_opening_batch_device(const LweContext* ctx, const uint64_t* d_comm_words, const uint64_t* d_messages,
+                                        size_t msg_len, size_t count, uint64_t* d_diff, int* d_invalid,
+                                        void* stream) LSR_NOEXCEPT {
+    LSR_TRY
+    if (!ctx || !d_comm_words || (!d_messages && msg_len) || !d_diff || !d_invalid || msg_len > ctx->n) return -1;
+    if (count == 0) return 0;
+    if (!lsr::fused_verify_supported(ctx)) { lsr::set_error("device-pointer verification: unsupported (ring degree, module rank)"); return -1; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!lsr::cuda_ok(cudaSetDevice(ctx->device), "cudaSetDevice") ||
+        !lsr::cuda_ok(cudaMemsetAsync(d_diff, 0, count * sizeof(uint64_t), s), "memset") ||
+        !lsr::cuda_ok(cudaMemsetAsync(d_invalid, 0, count * sizeof(int), s), "memset")) return -1;
+    return lsr::fused_verify_launch(ctx, reinterpret_cast<const u64*>(d_comm_words), lsr::lwe_words(ctx),
+                                    reinterpret_cast<const u64*>(d_messages), msg_len, count,
+                                    reinterpret_cast<unsigned long long*>(d_diff), d_invalid, s) ? 0 : -1;
+    LSR_CATCH(-1)
+}
+
 int lsr_cdt_timing_device(double sigma, const uint64_t* u, size_t count, int variant, uint32_t* out,
                           uint64_t* cycles_per_warp) LSR_NOEXCEPT {
     LSR_TRY

@@ -120,6 +120,9 @@ bool lwe_commit_explicit_launch(const LweContext* ctx, const u64* d_msgs, size_t
                                 const int64_t* d_e, size_t count, u64* d_out, cudaStream_t stream);
 bool sample_gaussian_host(u64* out, size_t len, double sigma, const uint8_t seed32[32]);
 bool fused_commit_supported(const LweContext* ctx);
+bool fused_verify_supported(const LweContext* ctx);
+bool fused_verify_launch(const LweContext* ctx, const u64* d_comm, size_t stride, const u64* d_msgs, size_t cmp_len,
+                         size_t count, unsigned long long* d_diff, int* d_invalid, cudaStream_t s);
 bool cdt_probe_host(double sigma, const u64* u, size_t count, uint32_t* out, int variant, u64* cycles_per_warp = nullptr);
 
 NttContext* ntt_create(u64 q, uint32_t n);

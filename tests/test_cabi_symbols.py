@@ -119,6 +119,7 @@ def test_null_and_invalid_arguments_need_no_gpu():
     assert lib.lsr_lwe_commit_explicit_device(None, None, 4, None, None, 1, None, None) == -1
     assert lib.lsr_goldilocks_probe_device(None, None, 4, None) == -1
     # peer-memory gather: NULL handles / pointers are refused, NULL frees are no-ops
+    assert lib.lsr_lwe_verify_opening_batch_device(None, None, None, 4, 1, None, None, None) == -1
     assert lib.lsr_peer_export(None, None) == -1
     assert not lib.lsr_peer_open(None)
     assert lib.lsr_peer_close(None) == 0

@@ -372,6 +372,26 @@ def test_fused_verification_equals_the_generic_path_and_the_oracle(gpu, rng, k, 
     ctx.close()
 
 
+def test_device_pointer_verification(gpu, rng):
+    """lsr_lwe_verify_opening_batch_device: diff / invalid flags of a device-resident batch against lwe_verify_opening_batch."""
+    import torch
+    ctx = mk()
+    count = 33
+    msgs = rng.integers(0, 2**63, size=(count, 4096), dtype=np.int64)
+    cms = ctx.commit_batch(msgs.view(np.uint64), sharding.global_seeds(3, 0, count))
+    bad = msgs.copy(); bad[5, 100] += 1; bad[6, 4095] += 7
+    tam = cms.copy(); tam[9, 1 + 4096 + 17] = np.uint64(ctx.q); tam[10, 0] = 0
+    want = ctx.verify_batch(tam, bad.view(np.uint64)).tolist()
+    dc, dm = torch.from_numpy(tam.view(np.int64)).cuda(), torch.from_numpy(bad).cuda()
+    diff = torch.full((count,), -1, dtype=torch.int64, device="cuda")
+    inv = torch.full((count,), -1, dtype=torch.int32, device="cuda")
+    ctx.verify_batch_device(dc.data_ptr(), dm.data_ptr(), 4096, count, diff.data_ptr(), inv.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = [-1 if i else (0 if d else 1) for d, i in zip(diff.cpu().tolist(), inv.cpu().tolist())]
+    assert got == want and want[5] == 0 and want[6] == 0 and want[9] == -1 and want[10] == -1 and want[0] == 1
+    ctx.close()
+
+
 def test_words_at_or_above_p_strict_mode_and_lincomb_budget(gpu, rng):
     """lambda_snark_b200.h, lwe_commit MESSAGE RANGE / lwe_linear_combine COEFFICIENT BOUND: message words are bound
     modulo p and the library's own commitments to words >= p open; strict mode rejects such words the way SEAL's
