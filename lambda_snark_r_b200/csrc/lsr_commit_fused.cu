@@ -494,21 +494,28 @@ struct VerifyEpilogue {
     __device__ __forceinline__ void item(u64*, u32, u32 base, const u64 (&v)[16], const Pre&) const {
         constexpr u32 LG = LOGN - 4;
         const u64 q = vp.mp.q;
-        u64 t[16];
+        // four quarters of four coefficients: the last-row words and the message words of a quarter are requested together
+        // (both were pulled towards L2 at kernel start), so a work item waits four times, not once per coefficient (eight at a
+        // time spill at the 80-register budget)
 #pragma unroll
-        for (u32 j = 0; j < 16; j++) t[j] = __ldcs(last + base + (j << LG));
+        for (u32 h = 0; h < 4; h++) {
+            u64 t[4], mw[4];
 #pragma unroll
-        for (u32 j = 0; j < 16; j++) {
-            const u32 x = base + (j << LG);
-            u64 w = t[j];
-            if (w >= q) { *bad = 1; w = 0; }                                   // flagged invalid; keep the arithmetic in range
-            const u64 u = addmod(v[j], w, q);
-            u64 d = div_small(u + vp.delta / 2, vp.delta, vp.dinv);            // round(u / Delta) <= p
-            d = d >= vp.p ? d - vp.p : d;
-            if (x < vp.cmp_len) {
-                const u64 word = __ldcs(msg + x);
-                const u64 m = vp.p < (1ull << 21) ? (u64)mod_small(word, (u32)vp.p, vp.pinv) : word % vp.p;
-                *acc |= d ^ m;                                                  // no branch on the outcome
+            for (u32 jj = 0; jj < 4; jj++) {
+                const u32 x = base + ((4u * h + jj) << LG);
+                t[jj] = __ldcs(last + x);
+                mw[jj] = x < vp.cmp_len ? __ldcs(msg + x) : 0ull;
+            }
+#pragma unroll
+            for (u32 jj = 0; jj < 4; jj++) {
+                const u32 x = base + ((4u * h + jj) << LG);
+                u64 w = t[jj];
+                if (w >= q) { *bad = 1; w = 0; }                               // flagged invalid; keep the arithmetic in range
+                const u64 u = addmod(v[4u * h + jj], w, q);
+                u64 d = div_small(u + vp.delta / 2, vp.delta, vp.dinv);        // round(u / Delta) <= p
+                d = d >= vp.p ? d - vp.p : d;
+                const u64 m = vp.p < (1ull << 21) ? (u64)mod_small(mw[jj], (u32)vp.p, vp.pinv) : mw[jj] % vp.p;
+                *acc |= x < vp.cmp_len ? (d ^ m) : 0ull;                        // no branch on the outcome
             }
         }
     }
@@ -524,6 +531,14 @@ fused_verify_kernel(const __grid_constant__ VerifyParams vp) {
     const size_t b = blockIdx.x;
     const u64* c = vp.comm + b * vp.stride;
     int bad = (threadIdx.x == 0 && c[0] != (u64)K * n * 8) ? 1 : 0;
+    {   // the last row and the message are consumed by the last pass only: pull them towards L2 now (one 128-byte line each)
+        const u64* lastrow = c + 1 + (size_t)(K - 1) * n;
+        const u64* m = vp.msgs + b * (size_t)vp.cmp_len;
+        for (u32 x = threadIdx.x * 16u; x < n; x += kNttThreads * 16u) {
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(lastrow + x));
+            if (x < vp.cmp_len) asm volatile("prefetch.global.L2 [%0];" :: "l"(m + x));
+        }
+    }
     for (u32 r = threadIdx.x; r < (u32)(K - 1) * n; r += kNttThreads) {
         u64 v = __ldcs(c + 1 + r);
         if (v >= mp.q) { bad = 1; v = 0; }
