@@ -539,10 +539,22 @@ fused_verify_kernel(const __grid_constant__ VerifyParams vp) {
             if (x < vp.cmp_len) asm volatile("prefetch.global.L2 [%0];" :: "l"(m + x));
         }
     }
-    for (u32 r = threadIdx.x; r < (u32)(K - 1) * n; r += kNttThreads) {
-        u64 v = __ldcs(c + 1 + r);
-        if (v >= mp.q) { bad = 1; v = 0; }
-        sm[swz(r)] = to_working<POL>(v);
+    // rows t_0 .. t_{k-2} into shared memory: all the words of a row that a thread owns are requested before the first is
+    // checked (one word per iteration left the kernel waiting on HBM at 20 % of its bandwidth: 26 % of the stall samples sat
+    // on the range check behind the load, profiles/r02_ncu_verify.txt)
+    constexpr u32 PER_THREAD = n / kNttThreads;
+#pragma unroll 1
+    for (u32 row = 0; row < (u32)(K - 1); row++) {
+        const u64* __restrict__ src = c + 1 + ((size_t)row << LOGN) + threadIdx.x;
+        u64 x[PER_THREAD];
+#pragma unroll
+        for (u32 k = 0; k < PER_THREAD; k++) x[k] = __ldcs(src + k * kNttThreads);
+#pragma unroll
+        for (u32 k = 0; k < PER_THREAD; k++) {
+            const bool out_of_range = x[k] >= mp.q;                            // flagged invalid; keep the arithmetic in range
+            bad |= out_of_range ? 1 : 0;
+            sm[swz((row << LOGN) + threadIdx.x + k * kNttThreads)] = to_working<POL>(out_of_range ? 0ull : x[k]);
+        }
     }
     __syncthreads();
     tile_forward<LOGN, LOGN, POL>(sm, vp.tbl, mp, (u32)(K - 1) * n, 0u);
