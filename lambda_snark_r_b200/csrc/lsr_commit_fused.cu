@@ -558,22 +558,26 @@ fused_verify_kernel(const __grid_constant__ VerifyParams vp) {
     }
     __syncthreads();
     tile_forward<LOGN, LOGN, POL>(sm, vp.tbl, mp, (u32)(K - 1) * n, 0u);
-    for (u32 x = threadIdx.x; x < n; x += kNttThreads) {
-        if (POL == POL_F64) {
-            double acc = 0.0;
+    // u^ = sum_i z'^_i * t^_i in place in row 0 (each coefficient index is owned by one thread).  The trapdoor words a thread
+    // needs from a row are requested together (one dependent L2 load per coefficient was a quarter of the kernel's stall samples)
+#pragma unroll 1
+    for (u32 i = 0; i < (u32)(K - 1); i++) {
+        const u64* __restrict__ zr = vp.zh + ((size_t)i << LOGN) + threadIdx.x;
+        u64 zw[PER_THREAD];
 #pragma unroll
-            for (u32 i = 0; i < (u32)(K - 1); i++) {
-                const double z = u64_to_f(__ldg(vp.zh + ((size_t)i << LOGN) + x));
+        for (u32 k = 0; k < PER_THREAD; k++) zw[k] = __ldg(zr + k * kNttThreads);
+#pragma unroll
+        for (u32 k = 0; k < PER_THREAD; k++) {
+            const u32 x = threadIdx.x + k * kNttThreads;
+            if (POL == POL_F64) {
+                const double z = u64_to_f(zw[k]);
                 // z / q formed on the fly: two roundings instead of one, |x| 2^-52 <= 2^-4 for the unreduced evaluations (< 2^48)
-                acc = __dadd_rn(acc, mulmod_f(as_d(sm[swz((i << LOGN) + x)]), z, __dmul_rn(z, mp.invq), mp.qd));
+                const double term = mulmod_f(as_d(sm[swz((i << LOGN) + x)]), z, __dmul_rn(z, mp.invq), mp.qd);
+                sm[swz(x)] = as_u(i ? __dadd_rn(as_d(sm[swz(x)]), term) : term);        // |acc| <= 0.75 (K-1) q
+            } else {
+                const u64 term = mulmod_exact(zw[k], sm[swz((i << LOGN) + x)], mp);
+                sm[swz(x)] = i ? addmod(sm[swz(x)], term, mp.q) : term;
             }
-            sm[swz(x)] = as_u(acc);                                             // |acc| <= 0.75 (K-1) q
-        } else {
-            u64 acc = 0;
-#pragma unroll
-            for (u32 i = 0; i < (u32)(K - 1); i++)
-                acc = addmod(acc, mulmod_exact(__ldg(vp.zh + ((size_t)i << LOGN) + x), sm[swz((i << LOGN) + x)], mp), mp.q);
-            sm[swz(x)] = acc;
         }
     }
     __syncthreads();
