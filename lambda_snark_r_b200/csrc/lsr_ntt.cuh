@@ -265,18 +265,22 @@ template <> struct plan<6>  { static constexpr int N = 2; static constexpr int R
 template <> struct plan<7>  { static constexpr int N = 2; static constexpr int R[4] = {3, 4, 0, 0}; };
 template <> struct plan<8>  { static constexpr int N = 2; static constexpr int R[4] = {4, 4, 0, 0}; };
 template <> struct plan<9>  { static constexpr int N = 3; static constexpr int R[4] = {3, 2, 4, 0}; };
-template <> struct plan<10> { static constexpr int N = 3; static constexpr int R[4] = {3, 3, 4, 0}; };
+// n = 1024, 2048: the two directions want different splits (tools/plan_bench.py, M NTT/s forward / inverse at n = 1024:
+// 3+3+4 236 / 242, 4+2+4 268 / 229, 2+4+4 209 / 239; n = 2048: 4+3+4 127.5 / 108.7, 3+4+4 116.6 / 114.4) -- the forward
+// transform reads its first pass straight from HBM and gains from 16 loads in flight per thread, the inverse ends on that
+// pass and prefers the even split.  plan_inv<LT> is the plan the inverse direction runs (in reverse order).
+template <> struct plan<10> { static constexpr int N = 3; static constexpr int R[4] = {4, 2, 4, 0}; };
 template <> struct plan<11> { static constexpr int N = 3; static constexpr int R[4] = {4, 3, 4, 0}; };
 template <> struct plan<12> { static constexpr int N = 3; static constexpr int R[4] = {4, 4, 4, 0}; };
-#ifndef LSR_PLAN13_R5     // n = 8192: three passes (the first on 32 register values per thread) instead of four
-#define LSR_PLAN13_R5 1
-#endif
-#if LSR_PLAN13_R5
-template <> struct plan<13> { static constexpr int N = 3; static constexpr int R[4] = {5, 4, 4, 0}; };
-#else
-template <> struct plan<13> { static constexpr int N = 4; static constexpr int R[4] = {3, 3, 3, 4}; };
-#endif
+// n = 8192: three passes, one of them on 32 register values per thread, instead of the four of 3+3+3+4 (21.7 M NTT/s
+// forward).  The 32-value pass goes in the middle: 4+5+4 runs at 26.2 / 22.3 M NTT/s forward / inverse against 24.3 / 21.4
+// for 5+4+4 -- the pass that talks to HBM (first forward, last inverse) is better off with 16 values and the registers
+// that leaves for addressing (tools/plan_bench.py)
+template <> struct plan<13> { static constexpr int N = 3; static constexpr int R[4] = {4, 5, 4, 0}; };
 template <> struct plan<14> { static constexpr int N = 4; static constexpr int R[4] = {4, 3, 3, 4}; };
+template <int LT> struct plan_inv : plan<LT> {};
+template <> struct plan_inv<10> { static constexpr int N = 3; static constexpr int R[4] = {3, 3, 4, 0}; };
+template <> struct plan_inv<11> { static constexpr int N = 3; static constexpr int R[4] = {3, 4, 4, 0}; };
 
 // ---------------------------------------------------------------------------
 // One pass over a tile.
@@ -460,7 +464,7 @@ __device__ __forceinline__ void tile_forward_from(u64* sm, const TileIo& io, con
         constexpr int R = P::R[I];
         constexpr int IN = (GIO && I == 0) ? IO_GLOBAL : IO_SMEM;
         constexpr int OUT = (GIO && (P::N == 1 || (ntt_direct_out<POL>() && I == P::N - 1))) ? IO_GLOBAL : IO_SMEM;
-        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD, ((GIO && WHOLE && LT <= 12) || LSR_SMEM_FWD_XR)>(sm, io, t, mp, tile_elems >> R, tb, d);      // LT = 13: 32 values per thread, FRND's extra live range spills; block tiles of the big ring degrees: -1 %
+        tile_pass<LT, WHOLE, SL, R, POL, false, (FIN && I == P::N - 1), IN, OUT, NoEpilogue, PAD, ((GIO && WHOLE && LT <= 12) || LSR_SMEM_FWD_XR)>(sm, io, t, mp, tile_elems >> R, tb, d);      // LT = 13: FRND in the 32-value pass spills, in the 16-value passes alone it gains 0.6 %; block tiles of the big ring degrees: -1 %
         if constexpr (OUT == IO_SMEM) __syncthreads();
         tile_forward_from<LT, WHOLE, POL, GIO, I + 1, FIN, PAD>(sm, io, t, mp, tile_elems, tb, d);
     }
@@ -470,7 +474,8 @@ template <int LT, bool WHOLE, int POL, bool GIO, int I, typename Epi = NoEpilogu
 __device__ __forceinline__ void tile_inverse_from(u64* sm, const TileIo& io, const NttTables& t,
                                                   const ModParams& mp, u32 tile_elems, u32 tb, u32 d,
                                                   const Epi& epi = Epi()) {
-    using P = plan<LT>;
+    using P = plan_inv<LT>;
+    static_assert(P::N == plan<LT>::N, "both directions make the same number of passes");
     if constexpr (I >= 0) {
         constexpr int SL = (I > 0 ? P::R[0] : 0) + (I > 1 ? P::R[1] : 0) + (I > 2 ? P::R[2] : 0);
         constexpr int R = P::R[I];
