@@ -12,4 +12,6 @@ python tools/prof_driver.py commit 8192 && ncu --set full --clock-control none -
 python tools/prof_driver.py verify 8192 && ncu --set full --clock-control none --import-source on -k regex:fused_verify -s 1 -c 1 -o gpurun_out/${R}_verify -f python tools/prof_driver.py verify 8192 > gpurun_out/ncu_2.log 2>&1
 (python tools/ncu_summary.py gpurun_out/${R}_verify.ncu-rep --top 24; python tools/ncu_by_line.py gpurun_out/${R}_verify.ncu-rep --top 30) 2>&1 | cut -c1-200 > gpurun_out/${R}_ncu_verify.txt
 rm -f gpurun_out/*.ncu-rep
+python tools/sweep.py > gpurun_out/${R}_ntt_sweep.json 2> gpurun_out/sweep.err
+python tools/latency.py > gpurun_out/${R}_latency.txt 2>&1
 tail -c 600 gpurun_out/${R}_bench_final.err; head -c 400 gpurun_out/${R}_bench_final.json
