@@ -8,6 +8,9 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+from lambda_snark_r_b200 import capi  # noqa: E402
+if "--lib" in sys.argv:          # kernel / pipeline variant built by `_build --variant`
+    capi._lib = capi.load(Path(sys.argv.pop(sys.argv.index("--lib") + 1))); sys.argv.remove("--lib")
 from lambda_snark_r_b200 import api  # noqa: E402
 
 dev = int(sys.argv[1]) if len(sys.argv) > 1 else 0
