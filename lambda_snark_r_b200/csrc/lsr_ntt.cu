@@ -74,7 +74,7 @@ static int policy_of(const NttContext* c, bool inverse) {
 template <int LT, bool WHOLE, bool INV, bool FUSED = false>
 static bool launch_tile(const NttContext* c, u64* d, size_t total, cudaStream_t s, u32 dlog = 0, const InvFusion fz = InvFusion{}) {
     constexpr int TL = LT > kTileLogMin ? LT : kTileLogMin;
-    const size_t smem = (sizeof(u64) << TL) + (ntt_pad<INV>() ? (sizeof(u64) << (TL - 4)) : 0);
+    const size_t smem = (sizeof(u64) << TL) + (ntt_pad<INV, LT>() ? (sizeof(u64) << (TL - 4)) : 0);
     const size_t tiles = (total + ((size_t)1 << TL) - 1) >> TL;
     if (tiles == 0) return true;
     if (tiles > 0x7fffffffull) { set_error("batch too large for one launch"); return false; }

@@ -48,7 +48,11 @@ constexpr int kTileLogMin = 12;   // a CTA always works on >= 4096 coefficients
 #endif
 // shared-memory layout of the stand-alone transform kernels (see padx): measured +3.7 % on the forward kernel
 // (61.6 vs 59.4 M NTT/s at n = 4096) and -2.8 % on the inverse one, so only the forward direction pads
-template <bool INVERSE> __host__ __device__ constexpr bool ntt_pad() { return LSR_NTT_PAD != 0 && !INVERSE; }
+// (the inverse kernel with the padded layout: -2.8 % at n = 4096, -2.9 % at 1024, -2.8 % at 2048, +2.0 % at 8192 -- so it
+// pads at 8192 only, where its 32-value middle pass gains most from the constant offsets)
+template <bool INVERSE, int LT = 12> __host__ __device__ constexpr bool ntt_pad() {
+    return LSR_NTT_PAD != 0 && (!INVERSE || LT == 13);
+}
 
 // shared-memory swizzle: bits 0-3 ^= bits 4-7
 __device__ __forceinline__ u32 swz(u32 i) { return i ^ ((i >> 4) & 15u); }
@@ -590,19 +594,19 @@ ntt_tile_kernel(const ModParams mp, const NttTables tbl, u64* __restrict__ data,
 #pragma unroll
             for (u32 k = 0; k < PER_THREAD; k++) {
                 const u32 i = threadIdx.x + k * kNttThreads;
-                sm[sidx<ntt_pad<true>()>(i)] = to_working<POL>(sanitize(x[k], io.limit, mp));
+                sm[sidx<ntt_pad<true, LT>()>(i)] = to_working<POL>(sanitize(x[k], io.limit, mp));
             }
             __syncthreads();
             if constexpr (FUSED) {
                 // out of place (first kernel of a fused transform) and / or the finishing epilogue on the last pass
                 const TileIo io_out{fz.dst ? fz.dst + tile0 : g, valid, io.sanitize, io.limit};
                 const FinEpilogue fin{(WHOLE && fz.fin_c) ? fz.fin_c + tile0 : nullptr, fz.fin_scale, &mp};
-                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, FinEpilogue, ntt_pad<true>()>(sm, io_out, tbl, mp, TILE, tb, d, fin);
+                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, FinEpilogue, ntt_pad<true, LT>()>(sm, io_out, tbl, mp, TILE, tb, d, fin);
             } else {
-                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true>()>(sm, io, tbl, mp, TILE, tb, d);
+                tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true, LT>()>(sm, io, tbl, mp, TILE, tb, d);
             }
         } else {
-            tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true>()>(sm, io, tbl, mp, TILE, tb, d);
+            tile_inverse_from<LT, WHOLE, POL, true, plan<LT>::N - 1, NoEpilogue, ntt_pad<true, LT>()>(sm, io, tbl, mp, TILE, tb, d);
         }
     }
 }
