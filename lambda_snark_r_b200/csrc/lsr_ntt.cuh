@@ -285,6 +285,22 @@ template <> struct plan<14> { static constexpr int N = 4; static constexpr int R
 template <int LT> struct plan_inv : plan<LT> {};
 template <> struct plan_inv<10> { static constexpr int N = 3; static constexpr int R[4] = {3, 3, 4, 0}; };
 template <> struct plan_inv<11> { static constexpr int N = 3; static constexpr int R[4] = {3, 4, 4, 0}; };
+// every plan covers its LT stages, ends on the unit-stride radix-16 pass the transposed twiddle table is laid out for
+// (LT > 4), and keeps every earlier pass at stride >= 16 (what the swizzle and the padded layout need)
+template <typename P, int LT> constexpr bool plan_ok() {
+    int sum = 0;
+    for (int i = 0; i < P::N; i++) sum += P::R[i];
+    if (sum != LT) return false;
+    if (LT > 4 && P::R[P::N - 1] != 4) return false;
+    int done = 0;
+    for (int i = 0; i + 1 < P::N; i++) { done += P::R[i]; if (LT - done < 4) return false; }
+    return true;
+}
+template <int LT> constexpr bool plans_ok() {
+    if constexpr (LT == 0) return true;
+    else return plan_ok<plan<LT>, LT>() && plan_ok<plan_inv<LT>, LT>() && plan<LT>::N == plan_inv<LT>::N && plans_ok<LT - 1>();
+}
+static_assert(plans_ok<14>(), "pass plan table");
 
 // ---------------------------------------------------------------------------
 // One pass over a tile.
