@@ -268,7 +268,7 @@ template <> struct plan<5>  { static constexpr int N = 2; static constexpr int R
 template <> struct plan<6>  { static constexpr int N = 2; static constexpr int R[4] = {2, 4, 0, 0}; };
 template <> struct plan<7>  { static constexpr int N = 2; static constexpr int R[4] = {3, 4, 0, 0}; };
 template <> struct plan<8>  { static constexpr int N = 2; static constexpr int R[4] = {4, 4, 0, 0}; };
-template <> struct plan<9>  { static constexpr int N = 3; static constexpr int R[4] = {3, 2, 4, 0}; };
+template <> struct plan<9>  { static constexpr int N = 3; static constexpr int R[4] = {4, 1, 4, 0}; };   // forward 492 -> 550 M NTT/s against 3+2+4 (the inverse keeps it)
 // n = 1024, 2048: the two directions want different splits (tools/plan_bench.py, M NTT/s forward / inverse at n = 1024:
 // 3+3+4 236 / 242, 4+2+4 268 / 229, 2+4+4 209 / 239; n = 2048: 4+3+4 127.5 / 108.7, 3+4+4 116.6 / 114.4) -- the forward
 // transform reads its first pass straight from HBM and gains from 16 loads in flight per thread, the inverse ends on that
@@ -283,6 +283,7 @@ template <> struct plan<12> { static constexpr int N = 3; static constexpr int R
 template <> struct plan<13> { static constexpr int N = 3; static constexpr int R[4] = {4, 5, 4, 0}; };
 template <> struct plan<14> { static constexpr int N = 4; static constexpr int R[4] = {4, 3, 3, 4}; };
 template <int LT> struct plan_inv : plan<LT> {};
+template <> struct plan_inv<9>  { static constexpr int N = 3; static constexpr int R[4] = {3, 2, 4, 0}; };
 template <> struct plan_inv<10> { static constexpr int N = 3; static constexpr int R[4] = {3, 3, 4, 0}; };
 template <> struct plan_inv<11> { static constexpr int N = 3; static constexpr int R[4] = {3, 4, 4, 0}; };
 // every plan covers its LT stages, ends on the unit-stride radix-16 pass the transposed twiddle table is laid out for
