@@ -541,7 +541,7 @@ fused_verify_kernel(const __grid_constant__ VerifyParams vp) {
     }
     // rows t_0 .. t_{k-2} into shared memory: all the words of a row that a thread owns are requested before the first is
     // checked (one word per iteration left the kernel waiting on HBM at 20 % of its bandwidth: 26 % of the stall samples sat
-    // on the range check behind the load, profiles/r02_ncu_verify.txt)
+    // on the range check behind the load, profiles/r02_ncu_verify_before.txt)
     constexpr u32 PER_THREAD = n / kNttThreads;
 #pragma unroll 1
     for (u32 row = 0; row < (u32)(K - 1); row++) {
